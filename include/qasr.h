@@ -1,0 +1,222 @@
+/*
+ * qasr.h -- C ABI of the B200 (sm_100a) integer-only QuartzNet / Jasper kernels.
+ *
+ * This is the drop-in boundary for ONE path of kssteven418/Q-ASR: the fake-quant
+ * forward of nemo/quantization/utils/{quant_utils,quant_modules}.py as driven by
+ * nemo/collections/asr/parts/jasper.py and modules/conv_asr.py.  The reference has
+ * no native code; each entry point below names the Python lines it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     name ends in _host.  The caller owns all memory; nothing is allocated here.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry
+ *     point synchronises the device.
+ *   - return value: 0 on success, negative qasr_status otherwise; qasr_last_error()
+ *     returns a thread-local message.  No C++ exception crosses the ABI.
+ *   - activation codes are stored as 8-bit tensors [B][C][ld] with time contiguous
+ *     (the reference's (B,C,T) layout), `ld` = row pitch in elements, ld % 16 == 0,
+ *     base pointers 16-byte aligned.  Signedness is a property of the producer's
+ *     clamp range: qmin >= 0 -> unsigned (the reference's "act_bit+1" inputs,
+ *     jasper.py:159-164), else signed.
+ *   - lens[b] = number of valid frames of utterance b in that tensor (int32).
+ */
+#ifndef QASR_H_
+#define QASR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QASR_VERSION 100
+
+typedef enum {
+  QASR_OK = 0,
+  QASR_ERR_INVALID = -1,   /* bad argument (shape, alignment, null pointer)        */
+  QASR_ERR_CUDA = -2,      /* CUDA runtime / driver error, see qasr_last_error()    */
+  QASR_ERR_UNSUPPORTED = -3
+} qasr_status;
+
+int qasr_version(void);
+const char* qasr_last_error(void);
+/* Number of SMs of the current device (grid sizing of the persistent kernels). */
+int qasr_sm_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Fused epilogue = QuantConv1d's rescale + the consumer QuantAct's requantisation.
+ *
+ * Replaces, per output element (SURVEY.md 3.4 b,c):
+ *   quant_modules.py:305-309   A = f32(acc);  y = A * s_out[c]
+ *   jasper.py:661,687          y = relu(y)
+ *   quant_utils.py:187         z = rne(y / s_out[c])
+ *   quant_utils.py:188-196     o = rne(f64(z) * f64(m[c]) / 2^e[c])
+ *   quant_utils.py:198-211     o += rne(f64(z1) * f64(m1[c]) / 2^e1[c])   (residual branch)
+ *   quant_utils.py:213-214     q = clamp(o, qmin, qmax)
+ * optionally followed by the block-output ReLU (jasper.py:687) and ONE more scalar
+ * requantisation (the next MaskedConv1d's QuantAct, quant_modules.py:186-194), and
+ * by MaskedConv1d's length mask (jasper.py:177-181: t >= lens[b] -> code 0).
+ *
+ * Per-channel parameter record (16 bytes, device):
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  float   s_out;   /* accumulator scale s_w[c] * s_x            (quant_modules.py:293) */
+  int32_t bias;    /* b_int[c] (0 when the conv has no bias)    (quant_modules.py:296) */
+  int32_t m;       /* dyadic mantissa, [2^30, 2^31)             (quant_utils.py:139)   */
+  int32_t e;       /* dyadic shift: o = rne(z * m / 2^e)        (quant_utils.py:145)   */
+} qasr_chan;
+
+enum {
+  QASR_EPI_REQUANT_I8 = 0, /* int8/uint8 codes out                                     */
+  QASR_EPI_DEQUANT_F32 = 1,/* y = f32(acc+bias) * s_out[c] (+relu): the module-level
+                              QuantConv1d return value, quant_modules.py:307-309       */
+  QASR_EPI_RAW_I32 = 2     /* acc + bias as int32 (dynamic / calibration passes)       */
+};
+
+/* flags */
+#define QASR_F_RELU0      1   /* ReLU between conv 0 and the activation quantiser          */
+#define QASR_F_RELU1      2   /* ReLU after the first clamp (JasperBlock.mout)              */
+#define QASR_F_STAGE2     4   /* second, scalar requantisation (m2, e2, qmin2, qmax2)       */
+#define QASR_F_MASK       8   /* zero codes at t >= out_lens[b]                             */
+#define QASR_F_EXACT_F32  16  /* emulate the f32 round trip of the accumulator bit-for-bit
+                                 (needed when |acc| may reach 2^22); else z = acc           */
+#define QASR_F_EXACT_DYAD 32  /* dyadic product in double (53-bit rounding + half-to-even),
+                                 else (z*m + 2^(e-1)) >> e, valid when the host proved
+                                 there is no exact tie and no 53-bit rounding               */
+#define QASR_F_B_SIGNED   64  /* conv-0 input codes are signed (else unsigned)              */
+#define QASR_F_B1_SIGNED  128 /* conv-1 (residual branch) input codes are signed            */
+#define QASR_F_BIAS64     256 /* add the bias in 64-bit (|b_int| close to 2^31)             */
+
+typedef struct {
+  int32_t mode;              /* QASR_EPI_*                                               */
+  int32_t flags;             /* QASR_F_*                                                 */
+  const qasr_chan* ch0;      /* [C_out] parameters of conv 0                             */
+  const qasr_chan* ch1;      /* [C_out] parameters of conv 1 (residual branch) or NULL   */
+  const int8_t* prev;        /* optional int8 codes [B][C_out][prev_ld] added before the
+                                clamp: a previous res_act result of the same scale
+                                (dense residual, jasper.py:667-682; ratio exactly 1)     */
+  int32_t prev_ld;
+  int32_t qmin, qmax;        /* first clamp                                              */
+  int32_t m2, e2;            /* stage-2 scalar dyadic                                    */
+  int32_t qmin2, qmax2;      /* stage-2 clamp                                            */
+  const int32_t* out_lens;   /* [B] valid output frames (mask), or NULL                  */
+} qasr_epilogue;
+
+/* ------------------------------------------------------------------------------------
+ * K1  depthwise (time-channel-separable) 1-D convolution on 8-bit codes.
+ * Replaces F.conv1d(x_int.double(), w_int.double(), groups=C) at
+ * quant_modules.py:301-305 for groups == C_in == C_out, k in {33..87}, stride 1|2,
+ * dilation 1|2, plus the fused epilogue above.
+ *   x      [B][C][x_ld]  8-bit codes (signed iff QASR_F_B_SIGNED), already masked
+ *   w      [C][k]        int8 weight codes W_int (quant_utils.py:74-76)
+ *   out    [B][C][out_ld] int8 (REQUANT), float (DEQUANT) or int32 (RAW); pitch in elems
+ * ---------------------------------------------------------------------------------- */
+int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, void* out, int32_t out_ld,
+                     int32_t B, int32_t C, int32_t T_in, int32_t T_out, int32_t k,
+                     int32_t stride, int32_t dilation, int32_t pad,
+                     const qasr_epilogue* epi, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K2  dense 1-D convolution as int8 tensor-core GEMM / implicit GEMM
+ *     (tcgen05.mma kind::i8, TMEM accumulators, TMA-fed), k >= 1, groups == 1.
+ * Replaces F.conv1d(x_int.double(), w_int.double(), bias) at quant_modules.py:301-305
+ * for the pointwise 1x1 convs, the residual 1x1 convs, Jasper's dense k<=29 convs and
+ * the decoder projection (conv_asr.py:261), plus the fused epilogue.  With x1 != NULL
+ * a second GEMM (the residual 1x1 conv of the block, jasper.py:667-672) accumulates
+ * into a second TMEM tile and both meet in the res_act epilogue (jasper.py:681).
+ *
+ *   wp  packed weights from qasr_pack_conv_weights(): [k][C_out_pad][C_in_pad] int8,
+ *       C_*_pad = round_up(C, 128), zero filled
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  const void*   x;        /* [B][C_in][x_ld] codes                                      */
+  const int8_t* wp;       /* packed weights                                             */
+  int32_t x_ld, C_in, T_in, k, stride, dilation, pad;
+} qasr_gemm_operand;
+
+int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm_operand* op1,
+                        void* out, int32_t out_ld, int32_t B, int32_t C_out, int32_t T_out,
+                        const qasr_epilogue* epi, void* stream);
+
+/* Bytes of the packed weight buffer for (C_out, C_in, k). */
+int64_t qasr_packed_weight_bytes(int32_t C_out, int32_t C_in, int32_t k);
+/* w [C_out][C_in][k] int8 (torch Conv1d layout) -> packed.  Device to device. */
+int qasr_pack_conv_weights(const int8_t* w, int8_t* wp, int32_t C_out, int32_t C_in, int32_t k,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K3  stand-alone quantiser kernels (module-level API)
+ * ---------------------------------------------------------------------------------- */
+/* SymmetricQuantFunction on activations (first layer, quant_modules.py:180-184):
+ *   q = clamp(rne((1/s) * x), -n, n-1); optional outputs: codes (int8, pitch codes_ld,
+ *   may be NULL) and xq = q * s (float, same pitch as x, may be NULL).
+ *   t >= lens[b] -> x treated as 0 when lens != NULL.  scale is a DEVICE scalar. */
+int qasr_quantize_f32(const float* x, int32_t x_ld, const float* scale, int32_t bit,
+                      int8_t* codes, int32_t codes_ld, float* xq,
+                      int32_t B, int32_t C, int32_t T, const int32_t* lens, void* stream);
+
+/* fixedpoint_mul (quant_utils.py:164-216) on float inputs as the reference's QuantAct
+ * calls it (quant_modules.py:186-194):
+ *   z = rne(x / pre_sf[c]);  o = rne(f64(z) * m / 2^e)  [+ same on identity];  clamp;
+ *   codes (int8, optional) and xq = f32(o) * z_sf (float, optional).
+ *   pre_sf / id_sf: device arrays with n_pre / n_id entries (1 = scalar, C = per channel).
+ *   (m, e) are derived ON DEVICE from pre_sf / z_sf exactly as batch_frexp does
+ *   (quant_utils.py:121-147), so dynamic mode needs no host round trip. */
+int qasr_requant_f32(const float* x, const float* pre_sf, int32_t n_pre,
+                     const float* identity, const float* id_sf, int32_t n_id,
+                     const float* z_sf, int32_t qmin, int32_t qmax,
+                     int8_t* codes, int32_t codes_ld, float* xq, int32_t ld,
+                     int32_t B, int32_t C, int32_t T, const int32_t* lens, void* stream);
+
+/* batch_frexp + the f64 scale ratio of quant_utils.py:188-193 on device:
+ *   (m[i], e[i]) from pre_sf[i] / z_sf, i < n; results normalised to m in [2^30, 2^31). */
+int qasr_dyadic_from_scales(const float* pre_sf, int32_t n, const float* z_sf,
+                            int32_t* m, int32_t* e, void* stream);
+
+/* codes*scale floats -> 8-bit codes: q = rne(x / s) (the x_int of quant_modules.py:301,
+ * rounded).  Used by the module-level QuantConv1d to feed K1/K2. */
+int qasr_codes_from_f32(const float* x, int32_t x_ld, const float* scale, int8_t* codes,
+                        int32_t codes_ld, int32_t B, int32_t C, int32_t T, void* stream);
+
+/* int8 -> int8 requantisation through a scalar dyadic (a QuantAct whose input already
+ * has a scalar scale, e.g. a second consumer of a res_act output). */
+int qasr_requant_i8(const int8_t* in, int32_t in_ld, int32_t in_signed, int32_t m, int32_t e,
+                    int32_t qmin, int32_t qmax, int8_t* out, int32_t out_ld,
+                    int32_t B, int32_t C, int32_t T, const int32_t* lens, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K4  range statistics (calibration / dynamic mode, quant_modules.py:108-167)
+ * ---------------------------------------------------------------------------------- */
+/* Global min / max of x (or of identity + x, f32 add, quant_modules.py:108) over the
+ * logical [B][C][T] extent of a pitched tensor; masked positions (t >= lens[b]) count
+ * as 0 when lens != NULL.  out2[0] = min, out2[1] = max (device).  `workspace` must hold
+ * qasr_minmax_workspace_bytes() bytes. */
+int64_t qasr_minmax_workspace_bytes(void);
+int qasr_minmax_f32(const float* x, const float* identity, int32_t ld, int32_t B, int32_t C,
+                    int32_t T, const int32_t* lens, float* out2, void* workspace, void* stream);
+
+/* torch.quantile(x.flatten(), q) pair as used at quant_modules.py:122-123: exact k-th
+ * order statistics by radix select on the float bit patterns + torch's float32 rank
+ * arithmetic and lerp.  q_lo, q_hi are the float32 quantile levels.  out2 = (lo, hi). */
+int64_t qasr_quantile_workspace_bytes(void);
+int qasr_quantile2_f32(const float* x, const float* identity, int32_t ld, int32_t B, int32_t C,
+                       int32_t T, const int32_t* lens, float q_lo, float q_hi, float* out2,
+                       void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K5  decoder tail: greedy CTC labels from integer logits
+ * Replaces log_softmax + argmax (conv_asr.py:275, ctc_models.py:405): argmax_c of
+ * y = f32(acc) * s_out[c] (log_softmax is monotone), first maximum wins as in torch.
+ *   logits_f32 [B][V][ld] float;  labels [B][T] int32
+ * ---------------------------------------------------------------------------------- */
+int qasr_ctc_argmax(const float* logits, int32_t ld, int32_t B, int32_t V, int32_t T,
+                    int32_t* labels, void* stream);
+
+/* log_softmax over the class axis with the (B,V,T)->(B,T,V) transpose of conv_asr.py:275. */
+int qasr_log_softmax_tv(const float* logits, int32_t ld, int32_t B, int32_t V, int32_t T,
+                        float* log_probs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QASR_H_ */

@@ -1,0 +1,53 @@
+// C-ABI glue: version, thread-local error string, argument validation shared by the kernels.
+#include <stdarg.h>
+
+#include "qasr_common.cuh"
+
+namespace {
+thread_local char g_err[512] = "";
+}
+
+void qasr_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int qasr_version(void) { return QASR_VERSION; }
+extern "C" const char* qasr_last_error(void) { return g_err; }
+
+extern "C" int qasr_sm_count(void) {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+int qasr_validate_epilogue(const qasr_epilogue* e, bool allow_second_operand) {
+  QASR_CHECK_ARG(e->mode >= QASR_EPI_REQUANT_I8 && e->mode <= QASR_EPI_RAW_I32, "epilogue: unknown mode %d", e->mode);
+  QASR_CHECK_ARG(e->ch0 != nullptr && qasr_aligned16(e->ch0), "epilogue: ch0 missing or not 16-byte aligned");
+  QASR_CHECK_ARG(allow_second_operand || e->ch1 == nullptr, "epilogue: this kernel takes one conv operand");
+  QASR_CHECK_ARG(e->ch1 == nullptr || qasr_aligned16(e->ch1), "epilogue: ch1 not 16-byte aligned");
+  if (e->mode == QASR_EPI_REQUANT_I8) {
+    QASR_CHECK_ARG(e->qmin < e->qmax && e->qmin >= -256 && e->qmax <= 255, "epilogue: clamp [%d, %d]", e->qmin, e->qmax);
+    const bool s2 = e->flags & QASR_F_STAGE2;
+    const int lo = s2 ? e->qmin2 : ((e->flags & QASR_F_RELU1) ? (e->qmin > 0 ? e->qmin : 0) : e->qmin);
+    const int hi = s2 ? e->qmax2 : e->qmax;
+    QASR_CHECK_ARG(hi - lo <= 255 && lo >= -128 && hi <= 255 && !(lo < 0 && hi > 127),
+                   "epilogue: final code range [%d, %d] does not fit one 8-bit tensor", lo, hi);
+    QASR_CHECK_ARG(!s2 || (e->e2 >= 1 && e->e2 <= 62 && e->m2 > 0), "epilogue: stage-2 dyadic (m2=%d, e2=%d)", e->m2, e->e2);
+    QASR_CHECK_ARG(!(e->flags & QASR_F_MASK) || e->out_lens != nullptr, "epilogue: MASK needs out_lens");
+    QASR_CHECK_ARG(e->prev == nullptr || (e->prev_ld % 16 == 0 && qasr_aligned16(e->prev)), "epilogue: prev pitch/alignment");
+  } else {
+    QASR_CHECK_ARG(e->ch1 == nullptr && e->prev == nullptr, "epilogue: residual operands need REQUANT mode");
+  }
+  QASR_CHECK_ARG(!(e->flags & QASR_F_BIAS64) || (e->flags & QASR_F_EXACT_F32) || e->mode != QASR_EPI_REQUANT_I8,
+                 "epilogue: BIAS64 requires EXACT_F32");
+  return QASR_OK;
+}

@@ -1,0 +1,482 @@
+// K2: 1-D convolution (k >= 1, groups == 1) on 8-bit codes as an int8 tensor-core GEMM /
+// implicit GEMM for sm_100a: TMA -> shared memory -> tcgen05.mma kind::i8 -> TMEM -> fused
+// requantisation epilogue.  Restates the F.conv1d(x_int.double(), w_int.double(), bias) of
+// QuantConv1d.int_conv (nemo/quantization/utils/quant_modules.py:301-305) for the pointwise
+// 1x1 convs, the residual 1x1 convs, Jasper's dense convs and the decoder projection.
+//
+// GEMM view (per utterance b):   D[C_out, T_out] = sum_tap  W_tap[C_out, C_in] * X[C_in, T_out + shift(tap)]
+//   A operand = packed weights [tap][C_out_pad][C_in_pad], K-major, 128B swizzle
+//   B operand = activation codes in the reference's own (B, C, T) layout: time (N) contiguous,
+//               i.e. MN-major, 128B swizzle; one TMA box = 128 channels x 128 frames.  The conv
+//               taps are K-loop iterations that shift the TMA time coordinate (negative / past-the-
+//               end coordinates are zero-filled by TMA = the conv's zero padding).
+//   D         = int32 in TMEM, 128 lanes (output channels) x 128 columns (frames) per tile;
+//               two tile sets are double buffered so the epilogue of tile i overlaps the MMAs of
+//               tile i+1.  An optional second operand pair (the block's residual 1x1 conv,
+//               jasper.py:667-672) accumulates into a second TMEM tile and both meet in the
+//               res_act epilogue (jasper.py:681) without an int32 round trip through HBM.
+// Warp roles (384 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0: TMA producer (one elected lane)      warp 1: MMA issuer (one elected lane)
+//   warp 2: TMEM allocator                        warps 4..11: epilogue (TMEM -> regs -> HBM)
+#include <cuda.h>
+
+#include "qasr_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 128;
+constexpr int kStages = 5;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
+constexpr uint32_t kABytes = BM * BK, kBBytes = BK * BN;
+constexpr uint32_t kStageBytes = kABytes + kBBytes;
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kSpinLimit = 1u << 24;  // a wedged pipeline traps instead of hanging the GPU
+
+struct GemmSeg {
+  int taps, cblocks, stride, dil, pad, c_out_pad;
+  uint32_t idesc;
+};
+
+struct GemmArgs {
+  void* out;
+  int out_ld, B, C_out, T_out;
+  int nseg, m_tiles, n_tiles, total_tiles;
+  GemmSeg seg[2];
+  uint32_t b_lbo, b_sbo, a_sbo;  // smem descriptor strides (bytes)
+  EpiArgs ep;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (tcgen05): start address, leading / stride byte offsets
+// (all >> 4), descriptor version 1 (bits 46-47), 128-byte swizzle (layout type 2, bits 61-63).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+template <bool FAST>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+               const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+               const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + kStages * kStageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB0) : "memory");
+    if (g.nseg > 1) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 32 * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const int mt = tile % g.m_tiles;
+        const int rest = tile / g.m_tiles;
+        const int nt = rest % g.n_tiles, b = rest / g.n_tiles;
+        for (int sg = 0; sg < g.nseg; ++sg) {
+          const GemmSeg& s = g.seg[sg];
+          const CUtensorMap* mA = sg == 0 ? &tmA0 : &tmA1;
+          const CUtensorMap* mB = sg == 0 ? &tmB0 : &tmB1;
+          for (int tap = 0; tap < s.taps; ++tap) {
+            const int tcoord = nt * BN * s.stride + tap * s.dil - s.pad;
+            for (int cb = 0; cb < s.cblocks; ++cb) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+              mbar_expect_tx(full_bar(stage), kStageBytes);
+              tma_load_2d(sa, mA, cb * BK, tap * s.c_out_pad + mt * BM, full_bar(stage));
+              tma_load_3d(sb, mB, tcoord, cb * BK, b, full_bar(stage));
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        for (int sg = 0; sg < g.nseg; ++sg) {
+          const GemmSeg& s = g.seg[sg];
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * 2 * BN + sg * BN);
+          const int slabs = s.taps * s.cblocks;
+          for (int it = 0; it < slabs; ++it) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+#pragma unroll
+            for (int kk = 0; kk < BK / 32; ++kk) {
+              const uint64_t adesc = make_smem_desc(sa + kk * 32, 0, g.a_sbo);
+              const uint64_t bdesc = make_smem_desc(sb + kk * 32 * BN, g.b_lbo, g.b_sbo);
+              tc_mma_i8(d_tmem, adesc, bdesc, s.idesc, (it | kk) != 0 ? 1u : 0u);
+            }
+            tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        tc_commit(tfull_bar(as));  // accumulators of this tile are complete
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;         // which 64 of the tile's 128 columns
+    const double mult2 = dyad_mult(g.ep.m2, g.ep.e2);
+    const long long half2 = (g.ep.e2 >= 1 && g.ep.e2 <= 62) ? (1ll << (g.ep.e2 - 1)) : 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      const int mt = tile % g.m_tiles;
+      const int rest = tile / g.m_tiles;
+      const int nt = rest % g.n_tiles, b = rest / g.n_tiles;
+      const int c = mt * BM + quarter * 32 + lane;
+      const bool row_ok = c < g.C_out;
+      const int cc = row_ok ? c : 0;
+      const ChanRegs c0 = load_chan(g.ep.ch0, cc);
+      const ChanRegs c1 = g.nseg > 1 ? load_chan(g.ep.ch1, cc) : c0;
+      const int len = (g.ep.flags & QASR_F_MASK) ? min(g.ep.out_lens[b], g.T_out) : g.T_out;
+      const size_t row = (size_t)b * g.C_out + cc;
+
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        const int col0 = half * 64 + ch * 32;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * 2 * BN + col0);
+        int acc0[32], acc1[32];
+        tmem_ld32(taddr, acc0);
+        if (g.nseg > 1) tmem_ld32(taddr + BN, acc1);
+        tmem_ld_wait();
+        const int tbase = nt * BN + col0;
+        if (g.ep.mode == QASR_EPI_REQUANT_I8) {
+          uint8_t* orow = reinterpret_cast<uint8_t*>(g.out) + row * g.out_ld;
+          const int8_t* prow = g.ep.prev ? g.ep.prev + row * g.ep.prev_ld : nullptr;
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {   // two 16-byte vectors per 32 columns
+            const int tv = tbase + 16 * v;
+            uint4 pv = make_uint4(0, 0, 0, 0);
+            if (prow && row_ok && tv < g.T_out) pv = *reinterpret_cast<const uint4*>(prow + tv);
+            const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+            uint32_t packed[4];
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) {
+              int q[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int j = 16 * v + 4 * w4 + i;
+                const int t = tbase + j;
+                const int prev = (int)(int8_t)((pw[w4] >> (8 * i)) & 0xff);
+                q[i] = epilogue_requant<FAST>(g.ep, acc0[j], c0, g.nseg > 1, g.nseg > 1 ? acc1[j] : 0, c1,
+                                              prev, mult2, half2, t < len);
+              }
+              packed[w4] = pack4(q[0], q[1], q[2], q[3]);
+            }
+            if (row_ok && tv < g.T_out)
+              *reinterpret_cast<uint4*>(orow + tv) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          }
+        } else if (g.ep.mode == QASR_EPI_DEQUANT_F32) {
+          float* orow = reinterpret_cast<float*>(g.out) + row * g.out_ld;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (row_ok && tbase + j < g.T_out) orow[tbase + j] = epilogue_dequant(g.ep, acc0[j], c0);
+        } else {
+          int32_t* orow = reinterpret_cast<int32_t*>(g.out) + row * g.out_ld;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (row_ok && tbase + j < g.T_out) orow[tbase + j] = acc0[j] + c0.bias;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing: [C_out][C_in][k] -> [k][C_out_pad][C_in_pad], zero filled
+// ------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const int8_t* __restrict__ w, int8_t* __restrict__ wp, int C_out,
+                                    int C_in, int k, int C_out_pad, int C_in_pad) {
+  const long long total = (long long)k * C_out_pad * C_in_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % C_in_pad);
+    const long long r = i / C_in_pad;
+    const int co = (int)(r % C_out_pad);
+    const int tap = (int)(r / C_out_pad);
+    int8_t v = 0;
+    if (ci < C_in && co < C_out) v = w[((size_t)co * C_in + ci) * k + tap];
+    wp[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host: tensor maps
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_map_weights(CUtensorMap* map, const int8_t* wp, int rows, int c_in_pad) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { qasr_set_error("cuTensorMapEncodeTiled entry point not available"); return QASR_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)c_in_pad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)c_in_pad};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(wp), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { qasr_set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return QASR_ERR_CUDA; }
+  return QASR_OK;
+}
+
+int make_map_acts(CUtensorMap* map, const void* x, int T, int C, int B, int ld) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { qasr_set_error("cuTensorMapEncodeTiled entry point not available"); return QASR_ERR_CUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)C, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)ld * (cuuint64_t)C};
+  cuuint32_t box[3] = {(cuuint32_t)BN, (cuuint32_t)BK, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { qasr_set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return QASR_ERR_CUDA; }
+  return QASR_OK;
+}
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// debug overrides of the B-operand descriptor strides (set through qasr_debug_set)
+long long g_dbg[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+
+}  // namespace
+
+extern "C" int qasr_debug_set(int key, long long value) {
+  if (key < 0 || key >= 8) return QASR_ERR_INVALID;
+  g_dbg[key] = value;
+  return QASR_OK;
+}
+
+extern "C" int64_t qasr_packed_weight_bytes(int32_t C_out, int32_t C_in, int32_t k) {
+  if (C_out <= 0 || C_in <= 0 || k <= 0) return -1;
+  return (int64_t)k * round_up(C_out, BM) * round_up(C_in, BK);
+}
+
+extern "C" int qasr_pack_conv_weights(const int8_t* w, int8_t* wp, int32_t C_out, int32_t C_in, int32_t k,
+                                      void* stream) {
+  QASR_CHECK_ARG(w && wp && C_out > 0 && C_in > 0 && k > 0, "pack_conv_weights: bad arguments");
+  const long long total = qasr_packed_weight_bytes(C_out, C_in, k);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, wp, C_out, C_in, k, round_up(C_out, BM),
+                                                               round_up(C_in, BK));
+  return qasr_check_launch("pack_weights_kernel");
+}
+
+extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm_operand* op1, void* out,
+                                   int32_t out_ld, int32_t B, int32_t C_out, int32_t T_out,
+                                   const qasr_epilogue* epi, void* stream) {
+  QASR_CHECK_ARG(op0 && out && epi, "conv1d_gemm: null pointer");
+  QASR_CHECK_ARG(B > 0 && C_out > 0 && T_out > 0, "conv1d_gemm: bad shape");
+  QASR_CHECK_ARG(qasr_aligned16(out) && out_ld >= round_up(T_out, 16), "conv1d_gemm: out pitch/alignment");
+  QASR_CHECK_ARG(epi->mode != QASR_EPI_REQUANT_I8 || out_ld % 16 == 0, "conv1d_gemm: out pitch % 16");
+  int rc = qasr_validate_epilogue(epi, true);
+  if (rc) return rc;
+  QASR_CHECK_ARG((op1 != nullptr) == (epi->ch1 != nullptr), "conv1d_gemm: second operand and epi->ch1 must come together");
+  QASR_CHECK_ARG(!op1 || epi->mode == QASR_EPI_REQUANT_I8, "conv1d_gemm: second operand needs REQUANT mode");
+
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  CUtensorMap maps[4];
+  memset(maps, 0, sizeof(maps));
+  const qasr_gemm_operand* ops[2] = {op0, op1};
+  g.nseg = op1 ? 2 : 1;
+  for (int i = 0; i < g.nseg; ++i) {
+    const qasr_gemm_operand* o = ops[i];
+    QASR_CHECK_ARG(o->x && o->wp && o->C_in > 0 && o->T_in > 0 && o->k > 0, "conv1d_gemm: operand %d bad", i);
+    QASR_CHECK_ARG(o->stride == 1, "conv1d_gemm: stride %d not supported by the tensor-core path", o->stride);
+    QASR_CHECK_ARG(o->dilation >= 1 && o->pad >= 0, "conv1d_gemm: bad dilation/pad");
+    QASR_CHECK_ARG((o->T_in + 2 * o->pad - o->dilation * (o->k - 1) - 1) / o->stride + 1 == T_out,
+                   "conv1d_gemm: operand %d: T_out %d inconsistent with T_in %d", i, T_out, o->T_in);
+    QASR_CHECK_ARG(o->x_ld % 16 == 0 && o->x_ld >= o->T_in && qasr_aligned16(o->x) && qasr_aligned16(o->wp),
+                   "conv1d_gemm: operand %d pitch/alignment", i);
+    GemmSeg& s = g.seg[i];
+    s.taps = o->k;
+    s.cblocks = (o->C_in + BK - 1) / BK;
+    s.stride = o->stride;
+    s.dil = o->dilation;
+    s.pad = o->pad;
+    s.c_out_pad = round_up(C_out, BM);
+    const uint32_t b_signed = (epi->flags & (i == 0 ? QASR_F_B_SIGNED : QASR_F_B1_SIGNED)) ? 1u : 0u;
+    // instruction descriptor: D=S32, A=signed 8-bit K-major, B=(un)signed 8-bit MN-major, N=128, M=128
+    s.idesc = (2u << 4) | (1u << 7) | (b_signed << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+              ((uint32_t)(BM >> 4) << 24);
+    rc = make_map_weights(&maps[2 * i], o->wp, o->k * s.c_out_pad, round_up(o->C_in, BK));
+    if (rc) return rc;
+    rc = make_map_acts(&maps[2 * i + 1], o->x, o->T_in, o->C_in, B, o->x_ld);
+    if (rc) return rc;
+  }
+  if (g.nseg == 1) { maps[2] = maps[0]; maps[3] = maps[1]; }
+  g.out = out;
+  g.out_ld = out_ld;
+  g.B = B;
+  g.C_out = C_out;
+  g.T_out = T_out;
+  g.m_tiles = (C_out + BM - 1) / BM;
+  g.n_tiles = (T_out + BN - 1) / BN;
+  g.total_tiles = g.m_tiles * g.n_tiles * B;
+  g.a_sbo = 1024;
+  g.b_sbo = g_dbg[1] >= 0 ? (uint32_t)g_dbg[1] : 1024;
+  g.b_lbo = g_dbg[0] >= 0 ? (uint32_t)g_dbg[0] : (uint32_t)(BK * 128);
+  g.ep = make_epi_args(epi);
+
+  const bool fast = !(epi->flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64));
+  int grid = qasr_sm_count();
+  if (grid > g.total_tiles) grid = g.total_tiles;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (fast) {
+    QASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    gemm_i8_kernel<true><<<grid, kGemmThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);
+  } else {
+    QASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    gemm_i8_kernel<false><<<grid, kGemmThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);
+  }
+  return qasr_check_launch("gemm_i8_kernel");
+}

@@ -1,0 +1,183 @@
+// Shared host/device helpers of the qasr kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "qasr.h"
+
+// ---------------------------------------------------------------------------------------------
+// host: error plumbing (no exception crosses the C ABI)
+// ---------------------------------------------------------------------------------------------
+void qasr_set_error(const char* fmt, ...);
+
+#define QASR_CHECK_ARG(cond, ...)                                   \
+  do {                                                              \
+    if (!(cond)) {                                                  \
+      qasr_set_error(__VA_ARGS__);                                  \
+      return QASR_ERR_INVALID;                                      \
+    }                                                               \
+  } while (0)
+
+#define QASR_CHECK_CUDA(expr)                                                             \
+  do {                                                                                    \
+    cudaError_t err__ = (expr);                                                           \
+    if (err__ != cudaSuccess) {                                                           \
+      qasr_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, \
+                     __LINE__);                                                           \
+      return QASR_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+
+static inline int qasr_check_launch(const char* what) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    qasr_set_error("launch of %s failed: %s", what, cudaGetErrorString(err));
+    return QASR_ERR_CUDA;
+  }
+  return QASR_OK;
+}
+
+static inline bool qasr_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---------------------------------------------------------------------------------------------
+// device: the fused epilogue (see qasr.h for the reference lines each step restates)
+// ---------------------------------------------------------------------------------------------
+struct EpiArgs {  // by-value kernel-parameter copy of qasr_epilogue
+  int mode, flags;
+  const qasr_chan* ch0;
+  const qasr_chan* ch1;
+  const int8_t* prev;
+  int prev_ld;
+  int qmin, qmax, m2, e2, qmin2, qmax2;
+  const int32_t* out_lens;
+};
+
+static inline EpiArgs make_epi_args(const qasr_epilogue* e) {
+  EpiArgs a;
+  a.mode = e->mode;
+  a.flags = e->flags;
+  a.ch0 = e->ch0;
+  a.ch1 = e->ch1;
+  a.prev = e->prev;
+  a.prev_ld = e->prev_ld;
+  a.qmin = e->qmin;
+  a.qmax = e->qmax;
+  a.m2 = e->m2;
+  a.e2 = e->e2;
+  a.qmin2 = e->qmin2;
+  a.qmax2 = e->qmax2;
+  a.out_lens = e->out_lens;
+  return a;
+}
+
+int qasr_validate_epilogue(const qasr_epilogue* e, bool allow_second_operand);
+
+#ifdef __CUDACC__
+
+// m * 2^-e as a double: exact (m has 31 bits), so z * mult rounds exactly like the
+// reference's f64(z) * f64(m) followed by the exact division by 2^e (quant_utils.py:195-196).
+__device__ __forceinline__ double dyad_mult(int m, int e) { return scalbn((double)m, -e); }
+
+// Per-channel registers of one conv operand.
+struct ChanRegs {
+  float s;
+  int bias;
+  int m, e;
+  double mult;          // exact path
+  long long half;       // fast path: 2^(e-1)
+};
+
+__device__ __forceinline__ ChanRegs load_chan(const qasr_chan* p, int c) {
+  const int4 v = __ldg(reinterpret_cast<const int4*>(p) + c);
+  ChanRegs r;
+  r.s = __int_as_float(v.x);
+  r.bias = v.y;
+  r.m = v.z;
+  r.e = v.w;
+  r.mult = dyad_mult(r.m, r.e);
+  r.half = (r.e >= 1 && r.e <= 62) ? (1ll << (r.e - 1)) : 0ll;
+  return r;
+}
+
+// rne(z * m / 2^e) on the all-integer fast path (host guarantees 1 <= e <= 62, no exact tie,
+// |z * m| < 2^53 and a result that fits int32).
+__device__ __forceinline__ int dyad_fast(int z, int m, int e, long long half) {
+  const long long p = (long long)z * (long long)m + half;
+  return (int)(p >> e);
+}
+
+template <bool FAST>
+struct Epilogue {
+  // One conv operand: accumulator (without bias) -> integer contribution to the pre-clamp sum.
+  // Returned as double on the exact path (integers, exactly representable), int on the fast path.
+  __device__ __forceinline__ static double contrib_exact(int acc, const ChanRegs& c, bool relu,
+                                                         bool exact_f32, bool bias64) {
+    double z;
+    if (exact_f32) {
+      float a = bias64 ? (float)((long long)acc + (long long)c.bias) : (float)(acc + c.bias);
+      float y = __fmul_rn(a, c.s);                 // quant_modules.py:307
+      if (relu) y = fmaxf(y, 0.0f);                // jasper.py:661
+      z = (double)rintf(__fdiv_rn(y, c.s));        // quant_utils.py:187
+    } else {
+      int zi = acc + c.bias;
+      if (relu) zi = max(zi, 0);
+      z = (double)zi;
+    }
+    return rint(__dmul_rn(z, c.mult));             // quant_utils.py:195-196
+  }
+  __device__ __forceinline__ static int contrib_fast(int acc, const ChanRegs& c, bool relu) {
+    int z = acc + c.bias;
+    if (relu) z = max(z, 0);
+    return dyad_fast(z, c.m, c.e, c.half);
+  }
+};
+
+// Full per-element REQUANT pipeline.  acc1 / c1 only used when has1; prev is the optional
+// previous res_act code (already loaded).  Returns the final 8-bit code as int.
+template <bool FAST>
+__device__ __forceinline__ int epilogue_requant(const EpiArgs& ep, int acc0, const ChanRegs& c0,
+                                                bool has1, int acc1, const ChanRegs& c1, int prev,
+                                                double mult2, long long half2, bool valid) {
+  int q;
+  if (FAST) {
+    int o = Epilogue<true>::contrib_fast(acc0, c0, ep.flags & QASR_F_RELU0);
+    if (has1) o += Epilogue<true>::contrib_fast(acc1, c1, false);
+    o += prev;
+    q = min(max(o, ep.qmin), ep.qmax);
+    if (ep.flags & QASR_F_RELU1) q = max(q, 0);
+    if (ep.flags & QASR_F_STAGE2) {
+      q = dyad_fast(q, ep.m2, ep.e2, half2);
+      q = min(max(q, ep.qmin2), ep.qmax2);
+    }
+  } else {
+    const bool ex = ep.flags & QASR_F_EXACT_F32, b64 = ep.flags & QASR_F_BIAS64;
+    double o = Epilogue<false>::contrib_exact(acc0, c0, ep.flags & QASR_F_RELU0, ex, b64);
+    if (has1) o += Epilogue<false>::contrib_exact(acc1, c1, false, ex, b64);
+    o += (double)prev;
+    o = fmin(fmax(o, (double)ep.qmin), (double)ep.qmax);   // quant_utils.py:213-214
+    if (ep.flags & QASR_F_RELU1) o = fmax(o, 0.0);          // jasper.py:687
+    if (ep.flags & QASR_F_STAGE2) {
+      o = rint(__dmul_rn(o, mult2));
+      o = fmin(fmax(o, (double)ep.qmin2), (double)ep.qmax2);
+    }
+    q = (int)o;
+  }
+  return valid ? q : 0;                                       // jasper.py:177-181
+}
+
+__device__ __forceinline__ float epilogue_dequant(const EpiArgs& ep, int acc, const ChanRegs& c) {
+  float a = (ep.flags & QASR_F_BIAS64) ? (float)((long long)acc + (long long)c.bias)
+                                       : (float)(acc + c.bias);
+  float y = __fmul_rn(a, c.s);
+  if (ep.flags & QASR_F_RELU0) y = fmaxf(y, 0.0f);
+  return y;
+}
+
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
+  return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) |
+         ((uint32_t)(d & 0xff) << 24);
+}
+
+#endif  // __CUDACC__

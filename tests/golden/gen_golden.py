@@ -1,0 +1,256 @@
+"""Generate golden vectors from the UNMODIFIED reference (run in the build container):
+
+    python tests/golden/gen_golden.py            # writes tests/golden/*.npz
+
+The reference has no tests / fixtures for its quant path, so these
+vectors -- outputs of the reference's own QuantAct / QuantConv1d / JasperBlock code
+run on CPU through tests/golden/ref_loader.py -- are what pins both the oracle
+(tests/test_oracle_golden.py, CPU) and the CUDA path (tests/test_gpu_*.py).
+Integer codes are recovered from the reference's float tensors as rne(x / scale).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [HERE, os.path.join(ROOT, "q-asr_b200"), os.path.join(ROOT, "oracle")]
+
+from ref_loader import RefModel, load_reference  # noqa: E402
+from qasr.params import reestimate_bn_, synthetic_features  # noqa: E402
+from qasr import topology  # noqa: E402
+import specio  # noqa: E402
+from spec_from_modules import spec_from_model  # noqa: E402
+
+torch.set_grad_enabled(False)
+ref = load_reference()
+Q = ref.quant_modules
+qm = ref.quantize_model
+
+
+def codes_of(x, sf):
+    return torch.round(x / sf).to(torch.int32).numpy()
+
+
+def npf(t):
+    return t.detach().numpy().astype(np.float32).copy()
+
+
+# --------------------------------------------------------------------------------------
+# whole-network cases
+# --------------------------------------------------------------------------------------
+def net_case(name, topo_name, topo_kwargs, B, T, wbit, abit, mode, percentile=None, n_calib=2,
+             momentum=None):
+    torch.manual_seed(hash(name) % 10000)
+    blocks = topology.TOPOLOGIES[topo_name](**topo_kwargs)
+    m = RefModel(ref, blocks)
+    m.eval()
+    reestimate_bn_(m.encoder, frames=96)
+    state = {k: v.numpy().copy() for k, v in m.state_dict().items()
+             if not k.endswith("conv.conv.weight") and "num_batches" not in k}
+    m.set_quant_bit(wbit, "weight")
+    m.set_quant_bit(abit, "act")
+    if percentile is not None:
+        qm.set_percentile(m, percentile)
+    if momentum is not None:
+        for mod in m.modules():
+            if type(mod) is Q.QuantAct:
+                mod.act_range_momentum = momentum
+    m.encoder.bn_folding()
+    calib = []
+    if mode != "dynamic":
+        qm.calibrate(m)
+        for i in range(n_calib):
+            cx, cl = synthetic_features(B, T, seed=100 + i, ragged=(i % 2 == 1))
+            e, l, s = m.encoder(cx, cl)
+            m.decoder(e, s)
+            calib.append(dict(x=npf(cx), lens=cl.numpy()))
+    qm.evaluate(m)
+    qm.set_dynamic(m, mode == "dynamic")
+    spec = spec_from_model(m.encoder, m.decoder)
+
+    trace = {}
+
+    def hook(modname):
+        def f(mod, inp, out):
+            if type(mod) is Q.QuantAct:
+                rec = dict(codes=codes_of(out[0], out[1].reshape(1, -1, 1)), scale=npf(out[1]))
+            else:
+                rec = dict(acc=torch.round(out[0].double() / out[1].double()).to(torch.int64).numpy(),
+                           out_scale=npf(out[1]).reshape(-1), out=npf(out[0]))
+            trace.setdefault(modname, []).append(rec)
+        return f
+
+    handles = []
+    for n, mod in m.named_modules():
+        if type(mod) in (Q.QuantAct, Q.QuantConv1d) and not n.startswith("encoder.encoder_layers"):
+            handles.append(mod.register_forward_hook(hook(n.replace("encoder.encoder.", "encoder."))))
+    x, lens = synthetic_features(B, T, seed=5, ragged=True)
+    e, l, s = m.encoder(x, lens)
+    lp = m.decoder(e, s)
+    for h in handles:
+        h.remove()
+    logits, lsf = m.decoder.last_logits, m.decoder.last_logit_sf
+    case = dict(
+        name=name, topology=topo_name, topology_kwargs=topo_kwargs, weight_bit=wbit, act_bit=abit,
+        mode=mode, percentile=percentile, momentum=momentum, state_dict=state, calib=calib,
+        spec=spec, x=npf(x), lens=lens.numpy(),
+        out=dict(encoded=npf(e), encoded_scale=npf(s).reshape(-1), enc_lens=l.numpy(),
+                 logits=npf(logits), logit_scale=npf(lsf).reshape(-1),
+                 logit_codes=torch.round(logits.double() / lsf.double()).to(torch.int64).numpy(),
+                 log_probs=npf(lp), greedy=lp.argmax(-1).numpy()),
+        trace=trace)
+    path = os.path.join(HERE, name + ".npz")
+    specio.save(path, case)
+    nz = float((case["out"]["logit_codes"] != 0).mean())
+    print("%-34s %7.1f KB  nonzero logit codes %.3f" % (name, os.path.getsize(path) / 1024, nz))
+
+
+# --------------------------------------------------------------------------------------
+# op-level cases
+# --------------------------------------------------------------------------------------
+def act_cases():
+    g = torch.Generator().manual_seed(7)
+    cases = []
+
+    def run(tag, bit, calls, per_channel_sf=False, identity=False, first_layer=False, momentum=0.95,
+            percentile=None, dynamic=False, running_stat=False, x_min=None, x_max=None, C=12, T=40, B=3):
+        act = Q.QuantAct(bit, quant_mode="symmetric", act_range_momentum=momentum, dynamic=dynamic,
+                         percentile=percentile)
+        act.running_stat = running_stat
+        if x_min is not None:
+            act.x_min = torch.tensor([x_min])
+            act.x_max = torch.tensor([x_max])
+        rec = dict(tag=tag, bit=bit, momentum=momentum, percentile=percentile, dynamic=dynamic,
+                   running_stat=running_stat, x_min0=float(act.x_min), x_max0=float(act.x_max),
+                   calls=[])
+        for ci in range(calls):
+            if first_layer:
+                x = torch.randn(B, C, T, generator=g) * (1.0 + 0.5 * ci)
+                pre = ident = ident_sf = None
+            else:
+                n_in = 2 ** 15
+                pre = (torch.rand(1, C, 1, generator=g) * 2e-4 + 1e-5) if per_channel_sf else \
+                    (torch.rand(1, generator=g) * 2e-4 + 1e-5)
+                z = torch.randint(-n_in, n_in, (B, C, T), generator=g).float()
+                if ci % 2 == 1:
+                    z = z.abs()
+                x = z * (pre if per_channel_sf else pre.view(1, 1, 1))
+                ident = ident_sf = None
+                if identity:
+                    ident_sf = torch.rand(1, C, 1, generator=g) * 2e-4 + 1e-5
+                    ident = torch.randint(-n_in, n_in, (B, C, T), generator=g).float() * ident_sf
+            out, sf = act(x, pre, ident, ident_sf)
+            rec["calls"].append(dict(
+                x=npf(x), pre_sf=None if pre is None else npf(pre).reshape(-1),
+                identity=None if ident is None else npf(ident),
+                identity_sf=None if ident_sf is None else npf(ident_sf).reshape(-1),
+                out=npf(out), scale=npf(sf).reshape(-1), codes=codes_of(out, sf.reshape(1, -1, 1)),
+                x_min=float(act.x_min), x_max=float(act.x_max)))
+        cases.append(rec)
+
+    run("first_layer_static_8", 8, 1, first_layer=True, x_min=-3.1, x_max=2.7)
+    run("first_layer_static_6", 6, 1, first_layer=True, x_min=-2.0, x_max=3.3)
+    run("requant_scalar_9", 9, 2, x_min=0.0, x_max=5.5)
+    run("requant_perchannel_8", 8, 2, per_channel_sf=True, x_min=-4.2, x_max=3.9)
+    run("requant_perchannel_7", 7, 1, per_channel_sf=True, x_min=0.0, x_max=2.5)
+    run("identity_8", 8, 2, per_channel_sf=True, identity=True, x_min=-6.0, x_max=7.5)
+    run("identity_6", 6, 1, per_channel_sf=True, identity=True, x_min=-6.0, x_max=5.0)
+    run("calib_minmax_ema", 8, 3, per_channel_sf=True, running_stat=True)
+    run("calib_minmax_ema_identity", 8, 3, per_channel_sf=True, identity=True, running_stat=True)
+    run("calib_minmax_mom_neg1", 8, 3, per_channel_sf=True, running_stat=True, momentum=-1)
+    run("calib_percentile_99_9", 9, 3, per_channel_sf=True, running_stat=True, percentile=99.9)
+    run("calib_percentile_99_996_first", 8, 2, first_layer=True, running_stat=True, percentile=99.996,
+        T=400)
+    run("dynamic_minmax", 8, 2, per_channel_sf=True, dynamic=True)
+    run("dynamic_minmax_identity", 8, 2, per_channel_sf=True, identity=True, dynamic=True)
+    run("dynamic_percentile", 9, 2, per_channel_sf=True, dynamic=True, percentile=99.0)
+    run("dynamic_percentile_running", 8, 2, per_channel_sf=True, dynamic=True, percentile=99.0,
+        running_stat=True)
+    # power-of-two scale ratios: exact ties in the dyadic product (half-to-even matters)
+    act = Q.QuantAct(8, quant_mode="symmetric")
+    act.x_min, act.x_max = torch.tensor([-127.0 * 2 ** -3]), torch.tensor([127.0 * 2 ** -3])
+    pre = torch.full((1, 4, 1), 2.0 ** -6)
+    z = torch.arange(-1100, 1100).float().view(1, 1, -1).repeat(2, 4, 1)
+    out, sf = act(z * pre, pre)
+    cases.append(dict(tag="ties_pow2", bit=8, momentum=0.95, percentile=None, dynamic=False,
+                      running_stat=False, x_min0=float(act.x_min), x_max0=float(act.x_max),
+                      calls=[dict(x=npf(z * pre), pre_sf=npf(pre).reshape(-1), identity=None,
+                                  identity_sf=None, out=npf(out), scale=npf(sf).reshape(-1),
+                                  codes=codes_of(out, sf.reshape(1, -1, 1)), x_min=float(act.x_min),
+                                  x_max=float(act.x_max))]))
+    specio.save(os.path.join(HERE, "ops_act.npz"), cases)
+    print("ops_act.npz: %d cases" % len(cases))
+
+
+def conv_cases():
+    g = torch.Generator().manual_seed(11)
+    cases = []
+
+    def run(tag, cin, cout, k, stride=1, dil=1, groups=1, bias=False, bn=False, wbit=8, in_bit=9,
+            B=2, T=70, wscale=1.0):
+        pad = topology.get_same_padding(k, stride, dil)
+        conv = torch.nn.Conv1d(cin, cout, k, stride=stride, padding=pad, dilation=dil, groups=groups,
+                               bias=bias)
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * 0.1 * wscale)
+        if bias:
+            conv.bias.copy_(torch.randn(cout, generator=g) * 0.3)
+        qc = Q.QuantConv1d(wbit, bias_bit=32, quant_mode="symmetric", per_channel=True)
+        qc.set_param(conv)
+        bnrec = None
+        if bn:
+            b = torch.nn.BatchNorm1d(cout, eps=1e-3)
+            b.weight.copy_(0.3 + 1.5 * torch.rand(cout, generator=g))
+            b.bias.copy_(torch.randn(cout, generator=g) * 0.2)
+            b.running_mean.copy_(torch.randn(cout, generator=g) * 0.1)
+            # var + eps == 1.0 exactly: torch's CPU sqrt is not correctly rounded (see
+            # qasr/params.py), the per-channel spread lives in gamma instead
+            b.running_var.fill_(1.0)
+            b.running_var.sub_(b.eps)
+            b.eval()
+            qc.bn_folding(b)
+            bnrec = dict(weight=npf(b.weight), bias=npf(b.bias), mean=npf(b.running_mean),
+                         var=npf(b.running_var), eps=float(b.eps))
+        n = 2 ** (in_bit - 1)
+        lo = 0 if in_bit == 9 else -n
+        codes = torch.randint(lo, n, (B, cin, T), generator=g)
+        s_x = torch.rand(1, generator=g) * 0.05 + 0.01
+        out, sf = qc(codes.float() * s_x, s_x)
+        acc = torch.round(out.double() / sf.double()).to(torch.int64).numpy()
+        cases.append(dict(tag=tag, weight=npf(conv.weight), bias=npf(conv.bias) if bias else None,
+                          bn=bnrec, stride=stride, pad=pad, dil=dil, groups=groups, weight_bit=wbit,
+                          in_codes=codes.to(torch.int32).numpy(), s_x=npf(s_x), out=npf(out),
+                          out_scale=npf(sf).reshape(-1), acc=acc,
+                          weight_integer=qc.weight_integer.to(torch.int32).numpy(),
+                          conv_scaling_factor=npf(qc.conv_scaling_factor)))
+
+    run("dw_k33_s2_signed", 16, 16, 33, stride=2, groups=16, in_bit=8)
+    run("dw_k33", 24, 24, 33, groups=24)
+    run("dw_k87_dil2", 16, 16, 87, dil=2, groups=16, T=200)
+    run("dw_k5_w4", 8, 8, 5, groups=8, wbit=4)
+    run("pw_bn_w8", 48, 32, 1, bn=True, in_bit=8)
+    run("pw_bn_w6", 48, 32, 1, bn=True, wbit=6, in_bit=8)
+    run("pw_bn_w4", 48, 32, 1, bn=True, wbit=4, in_bit=8)
+    run("res_1x1_bn_u8", 32, 64, 1, bn=True, in_bit=9)
+    run("dense_k11_s2_bn", 16, 32, 11, stride=2, bn=True, in_bit=8)
+    run("dense_k29_dil2_bn", 24, 16, 29, dil=2, bn=True, T=120)
+    run("dense_k5_bias_bn", 24, 16, 5, bias=True, bn=True)
+    run("decoder_1x1_bias", 64, 29, 1, bias=True, in_bit=8)
+    run("dense_k25_bigacc", 768, 8, 25, in_bit=9, B=1, T=40, wscale=0.02)
+    specio.save(os.path.join(HERE, "ops_conv.npz"), cases)
+    print("ops_conv.npz: %d cases" % len(cases))
+
+
+if __name__ == "__main__":
+    act_cases()
+    conv_cases()
+    tq = dict(filters=32, kernel=9, repeat=2, n_res_blocks=2, last=48)
+    tj = dict(filters=32, kernel=5, repeat=2, n_blocks=3, last=48)
+    net_case("net_tinyqn_w8a8_static", "tiny_quartznet", tq, 3, 64, 8, 8, "static")
+    net_case("net_tinyqn_w6a6_pct_static", "tiny_quartznet", tq, 3, 64, 6, 6, "static", percentile=99.9)
+    net_case("net_tinyqn_w4a8_dynamic", "tiny_quartznet", tq, 3, 64, 4, 8, "dynamic")
+    net_case("net_tinyqn_w8a8_mom_neg1", "tiny_quartznet", tq, 2, 48, 8, 8, "static", momentum=-1, n_calib=3)
+    net_case("net_tinyjasper_w8a8_static", "tiny_jasper", tj, 3, 64, 8, 8, "static")
+    net_case("net_tinyjasper_w4a8_dynamic_pct", "tiny_jasper", tj, 2, 64, 4, 8, "dynamic", percentile=99.0)

@@ -1,0 +1,439 @@
+"""GPU: every kernel behind the C ABI against the oracle's integer arithmetic, bit-exact.
+Run stand-alone (`python tests/test_gpu_kernels.py`) for a non-stopping report."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "q-asr_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import qasr_oracle as O  # noqa: E402
+from qasr import _lib as L  # noqa: E402
+from qasr import ops  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+def to_codes_tensor(q, signed):
+    """int array (B,C,T) -> zero padded pitched device tensor."""
+    B, Cn, T = q.shape
+    t = ops.alloc_codes(B, Cn, T, DEV)
+    arr = q.astype(np.int8) if signed else q.astype(np.uint8).view(np.int8)
+    t[:, :, :T] = torch.from_numpy(arr).to(DEV)
+    return t
+
+
+def from_codes_tensor(t, T, signed):
+    a = t[:, :, :T].cpu().numpy()
+    return a.astype(np.int64) if signed else a.view(np.uint8).astype(np.int64)
+
+
+def rand_dyadic(r, n, lo=2e-5, hi=3e-3):
+    ratio = r.uniform(lo, hi, n)
+    return O.batch_frexp(ratio)
+
+
+def norm_me(m, e):
+    m = np.asarray(m, np.int64).copy()
+    e = np.asarray(e, np.int64).copy()
+    big = m >= 2 ** 31
+    m[big] //= 2
+    e[big] -= 1
+    return m, e
+
+
+def expected_requant(acc, m, e, qmin, qmax, relu0=False, acc1=None, m1=None, e1=None, prev=None,
+                     relu1=False, stage2=None, lens=None):
+    z = np.maximum(acc, 0) if relu0 else acc
+    o = O.dyadic_mul(z, m.reshape(1, -1, 1), e.reshape(1, -1, 1))
+    if acc1 is not None:
+        o = o + O.dyadic_mul(acc1, m1.reshape(1, -1, 1), e1.reshape(1, -1, 1))
+    if prev is not None:
+        o = o + prev
+    q = np.clip(o, qmin, qmax)
+    if relu1:
+        q = np.maximum(q, 0)
+    if stage2 is not None:
+        m2, e2, lo2, hi2 = stage2
+        q = np.clip(O.dyadic_mul(q, m2, e2), lo2, hi2)
+    if lens is not None:
+        T = q.shape[2]
+        q = np.where(np.arange(T)[None, None, :] < lens[:, None, None], q, 0)
+    return q.astype(np.int64)
+
+
+# ------------------------------------------------------------------------------------------
+# K2 GEMM
+# ------------------------------------------------------------------------------------------
+GEMM_CASES = [
+    # name, B, C_in, C_out, T, k, dil, signed
+    ("pw_256_256_u8", 2, 256, 256, 300, 1, 1, False),
+    ("pw_64_256_s8", 2, 64, 256, 250, 1, 1, True),
+    ("pw_512_512_s8", 1, 512, 512, 130, 1, 1, True),
+    ("dec_1024_29_s8", 2, 1024, 29, 77, 1, 1, True),
+    ("tiny_32_48_u8", 3, 32, 48, 40, 1, 1, False),
+    ("dense_k5", 2, 128, 128, 150, 5, 1, False),
+    ("dense_k11_c384", 1, 256, 384, 140, 11, 1, False),
+    ("dense_k7_dil2", 2, 96, 160, 90, 7, 2, False),
+]
+
+
+def _gemm_inputs(case, seed=0):
+    name, B, ci, co, T, k, dil, signed = case
+    r = rng(seed)
+    q = r.integers(-128, 128, (B, ci, T)) if signed else r.integers(0, 256, (B, ci, T))
+    w = r.integers(-127, 127, (co, ci, k))
+    bias = r.integers(-50000, 50000, co)
+    pad = (dil * k) // 2 - 1 if dil > 1 else k // 2
+    return q, w, bias, pad
+
+
+@pytest.mark.parametrize("case", GEMM_CASES, ids=lambda c: c[0])
+def test_gemm_raw_i32(case):
+    name, B, ci, co, T, k, dil, signed = case
+    q, w, bias, pad = _gemm_inputs(case)
+    want = O.conv1d_int(q, w, bias, 1, pad, dil, 1)
+    T_out = want.shape[2]
+    x = to_codes_tensor(q, signed)
+    wp = ops.pack_weights(torch.from_numpy(w.astype(np.int8)).to(DEV))
+    ch = ops.chan_table(np.ones(co, np.float32), bias, np.full(co, 2 ** 30), np.full(co, 30), DEV)
+    ep = ops.make_epilogue(L.EPI_RAW_I32, ch, flags=L.F_B_SIGNED if signed else 0)
+    out = torch.full((B, co, ops.round_up(T_out, 16)), -777, dtype=torch.int32, device=DEV)
+    ops.conv_gemm(ops.gemm_operand(x, T, wp, ci, k, 1, dil, pad), None, out, B, co, T_out, ep)
+    torch.cuda.synchronize()
+    got = out[:, :, :T_out].cpu().numpy().astype(np.int64)
+    assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
+
+
+@pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
+@pytest.mark.parametrize("case", GEMM_CASES[:5] + GEMM_CASES[5:6], ids=lambda c: c[0])
+def test_gemm_requant(case, fast):
+    name, B, ci, co, T, k, dil, signed = case
+    q, w, bias, pad = _gemm_inputs(case, seed=1)
+    acc = O.conv1d_int(q, w, bias, 1, pad, dil, 1)
+    T_out = acc.shape[2]
+    r = rng(2)
+    m, e = norm_me(*rand_dyadic(r, co))
+    lens = r.integers(T_out // 2, T_out + 1, B).astype(np.int32)
+    m2, e2 = norm_me(*O.batch_frexp(np.array([1.9])))
+    want = expected_requant(acc, m, e, -128, 127, relu0=True, relu1=True, stage2=(m2[0], e2[0], -256, 255),
+                            lens=lens)
+    x = to_codes_tensor(q, signed)
+    wp = ops.pack_weights(torch.from_numpy(w.astype(np.int8)).to(DEV))
+    s_out = r.uniform(1e-5, 1e-3, co).astype(np.float32)
+    ch = ops.chan_table(s_out, bias, m, e, DEV)
+    flags = L.F_RELU0 | L.F_RELU1 | L.F_STAGE2 | L.F_MASK | (L.F_B_SIGNED if signed else 0)
+    if not fast:
+        flags |= L.F_EXACT_F32 | L.F_EXACT_DYAD
+    lens_d = torch.from_numpy(lens).to(DEV)
+    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=flags, qmin=-128, qmax=127, m2=m2[0], e2=e2[0],
+                           qmin2=-256, qmax2=255, out_lens=lens_d)
+    out = ops.alloc_codes(B, co, T_out, DEV)
+    ops.conv_gemm(ops.gemm_operand(x, T, wp, ci, k, 1, dil, pad), None, out, B, co, T_out, ep)
+    torch.cuda.synchronize()
+    got = from_codes_tensor(out, T_out, signed=False)
+    assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
+    assert int(out[:, :, T_out:].abs().sum()) == 0  # pitch padding stays zero
+
+
+@pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
+def test_gemm_dual_residual(fast):
+    """pointwise conv + residual 1x1 conv meeting in the res_act epilogue (jasper.py:681)."""
+    B, ci0, ci1, co, T = 2, 256, 128, 256, 200
+    r = rng(3)
+    q0 = r.integers(-128, 128, (B, ci0, T))
+    q1 = r.integers(0, 256, (B, ci1, T))
+    w0 = r.integers(-127, 127, (co, ci0, 1))
+    w1 = r.integers(-127, 127, (co, ci1, 1))
+    b0 = r.integers(-30000, 30000, co)
+    b1 = r.integers(-30000, 30000, co)
+    acc0 = O.conv1d_int(q0, w0, b0, 1, 0, 1, 1)
+    acc1 = O.conv1d_int(q1, w1, b1, 1, 0, 1, 1)
+    m0, e0 = norm_me(*rand_dyadic(r, co, 1e-5, 2e-4))
+    m1, e1 = norm_me(*rand_dyadic(r, co, 1e-5, 2e-4))
+    prev = r.integers(-128, 128, (B, co, T))
+    m2, e2 = norm_me(*O.batch_frexp(np.array([2.01])))
+    want = expected_requant(acc0, m0, e0, -128, 127, acc1=acc1, m1=m1, e1=e1, prev=prev, relu1=True,
+                            stage2=(m2[0], e2[0], -256, 255))
+    x0, x1 = to_codes_tensor(q0, True), to_codes_tensor(q1, False)
+    wp0 = ops.pack_weights(torch.from_numpy(w0.astype(np.int8)).to(DEV))
+    wp1 = ops.pack_weights(torch.from_numpy(w1.astype(np.int8)).to(DEV))
+    one = np.full(co, 1e-4, np.float32)
+    ch0, ch1 = ops.chan_table(one, b0, m0, e0, DEV), ops.chan_table(one, b1, m1, e1, DEV)
+    flags = L.F_RELU1 | L.F_STAGE2 | L.F_B_SIGNED
+    if not fast:
+        flags |= L.F_EXACT_F32 | L.F_EXACT_DYAD
+    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch0, flags=flags, ch1=ch1, prev=to_codes_tensor(prev, True),
+                           qmin=-128, qmax=127, m2=m2[0], e2=e2[0], qmin2=-256, qmax2=255)
+    out = ops.alloc_codes(B, co, T, DEV)
+    ops.conv_gemm(ops.gemm_operand(x0, T, wp0, ci0, 1), ops.gemm_operand(x1, T, wp1, ci1, 1), out, B, co, T, ep)
+    torch.cuda.synchronize()
+    got = from_codes_tensor(out, T, signed=False)
+    assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
+
+
+def test_gemm_dequant_f32_bigacc():
+    """|acc| >= 2^24: the f32 round trip of quant_modules.py:305 rounds; dequant output bit-exact."""
+    B, ci, co, T, k = 1, 768, 128, 60, 9
+    r = rng(4)
+    q = r.integers(200, 256, (B, ci, T))
+    w = r.integers(90, 127, (co, ci, k))
+    bias = r.integers(-2 ** 30, 2 ** 30, co)
+    acc = O.conv1d_int(q, w, bias, 1, k // 2, 1, 1)
+    assert np.abs(acc).max() > 2 ** 27
+    s_out = r.uniform(1e-9, 1e-7, co).astype(np.float32)
+    want = (acc.astype(np.float32) * s_out.reshape(1, -1, 1)).astype(np.float32)
+    want = np.maximum(want, 0)
+    x = to_codes_tensor(q, False)
+    wp = ops.pack_weights(torch.from_numpy(w.astype(np.int8)).to(DEV))
+    ch = ops.chan_table(s_out, bias, np.full(co, 2 ** 30), np.full(co, 30), DEV)
+    ep = ops.make_epilogue(L.EPI_DEQUANT_F32, ch, flags=L.F_RELU0 | L.F_BIAS64)
+    out = torch.zeros((B, co, ops.round_up(T, 16)), dtype=torch.float32, device=DEV)
+    ops.conv_gemm(ops.gemm_operand(x, T, wp, ci, k, 1, 1, k // 2), None, out, B, co, T, ep)
+    torch.cuda.synchronize()
+    assert np.array_equal(out[:, :, :T].cpu().numpy(), want)
+    # and the exact requant path on those accumulators (53-bit product rounding, f32 round trip)
+    m, e = norm_me(*rand_dyadic(r, co, 1e-7, 1e-6))
+    a32 = (acc.astype(np.float32) * s_out.reshape(1, -1, 1)).astype(np.float32)
+    z = np.round((np.maximum(a32, 0) / s_out.reshape(1, -1, 1)).astype(np.float32))
+    want_q = np.clip(O.dyadic_mul(z, m.reshape(1, -1, 1), e.reshape(1, -1, 1)), -256, 255).astype(np.int64)
+    ch = ops.chan_table(s_out, bias, m, e, DEV)
+    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=L.F_RELU0 | L.F_BIAS64 | L.F_EXACT_F32 | L.F_EXACT_DYAD,
+                           qmin=-256, qmax=255)
+    outq = ops.alloc_codes(B, co, T, DEV)
+    ops.conv_gemm(ops.gemm_operand(x, T, wp, ci, k, 1, 1, k // 2), None, outq, B, co, T, ep)
+    torch.cuda.synchronize()
+    assert np.array_equal(from_codes_tensor(outq, T, False), want_q)
+
+
+# ------------------------------------------------------------------------------------------
+# K1 depthwise
+# ------------------------------------------------------------------------------------------
+DW_CASES = [
+    # name, B, C, T, k, stride, dil, signed
+    ("k33_s2_signed", 2, 64, 500, 33, 2, 1, True),
+    ("k33", 2, 256, 250, 33, 1, 1, False),
+    ("k39", 1, 256, 300, 39, 1, 1, False),
+    ("k51", 2, 96, 180, 51, 1, 1, False),
+    ("k63", 1, 128, 333, 63, 1, 1, False),
+    ("k75", 2, 64, 250, 75, 1, 1, False),
+    ("k87_dil2", 1, 64, 400, 87, 1, 2, False),
+    ("k9_tiny", 3, 32, 32, 9, 1, 1, False),
+    ("k9_s2_tiny", 3, 64, 64, 9, 2, 1, True),
+    ("k13_dil2_tiny", 2, 32, 40, 13, 1, 2, False),
+    ("k5_T17", 2, 8, 17, 5, 1, 1, True),
+]
+
+
+@pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
+@pytest.mark.parametrize("case", DW_CASES, ids=lambda c: c[0])
+def test_dwconv_requant(case, fast):
+    name, B, Cn, T, k, stride, dil, signed = case
+    r = rng(5)
+    q = r.integers(-128, 128, (B, Cn, T)) if signed else r.integers(0, 256, (B, Cn, T))
+    w = r.integers(-127, 127, (Cn, 1, k))
+    pad = (dil * k) // 2 - 1 if dil > 1 else k // 2
+    acc = O.conv1d_int(q, w, None, stride, pad, dil, Cn)
+    T_out = acc.shape[2]
+    m, e = norm_me(*rand_dyadic(r, Cn, 1e-4, 2e-3))
+    lens = r.integers(T_out // 2, T_out + 1, B).astype(np.int32)
+    want = expected_requant(acc, m, e, -128, 127, lens=lens)
+    x = to_codes_tensor(q, signed)
+    wd = torch.from_numpy(w[:, 0, :].astype(np.int8)).to(DEV).contiguous()
+    ch = ops.chan_table(r.uniform(1e-5, 1e-3, Cn).astype(np.float32), None, m, e, DEV)
+    flags = L.F_MASK | (L.F_B_SIGNED if signed else 0)
+    if not fast:
+        flags |= L.F_EXACT_F32 | L.F_EXACT_DYAD
+    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=flags, qmin=-128, qmax=127,
+                           out_lens=torch.from_numpy(lens).to(DEV))
+    out = ops.alloc_codes(B, Cn, T_out, DEV)
+    ops.dwconv(x, T, wd, out, T_out, k, stride, dil, pad, ep)
+    torch.cuda.synchronize()
+    got = from_codes_tensor(out, T_out, signed=True)
+    assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
+    assert int(out[:, :, T_out:].abs().sum()) == 0
+
+
+def test_dwconv_raw_and_dequant():
+    B, Cn, T, k = 2, 48, 100, 33
+    r = rng(6)
+    q = r.integers(0, 256, (B, Cn, T))
+    w = r.integers(-127, 127, (Cn, 1, k))
+    acc = O.conv1d_int(q, w, None, 1, k // 2, 1, Cn)
+    x = to_codes_tensor(q, False)
+    wd = torch.from_numpy(w[:, 0, :].astype(np.int8)).to(DEV).contiguous()
+    s_out = r.uniform(1e-5, 1e-3, Cn).astype(np.float32)
+    ch = ops.chan_table(s_out, None, np.full(Cn, 2 ** 30), np.full(Cn, 30), DEV)
+    out = torch.zeros((B, Cn, ops.round_up(T, 16)), dtype=torch.int32, device=DEV)
+    ops.dwconv(x, T, wd, out, T, k, 1, 1, k // 2, ops.make_epilogue(L.EPI_RAW_I32, ch))
+    outf = torch.zeros((B, Cn, ops.round_up(T, 16)), dtype=torch.float32, device=DEV)
+    ops.dwconv(x, T, wd, outf, T, k, 1, 1, k // 2, ops.make_epilogue(L.EPI_DEQUANT_F32, ch))
+    torch.cuda.synchronize()
+    assert np.array_equal(out[:, :, :T].cpu().numpy(), acc)
+    assert np.array_equal(outf[:, :, :T].cpu().numpy(), (acc.astype(np.float32) * s_out.reshape(1, -1, 1)))
+
+
+# ------------------------------------------------------------------------------------------
+# K3 / K4 / K5
+# ------------------------------------------------------------------------------------------
+def test_dyadic_from_scales():
+    r = rng(7)
+    pre = np.concatenate([r.uniform(1e-7, 1e-2, 500), [2.0 ** -6, 2.0 ** -3, 1e-3]]).astype(np.float32)
+    for zs in (np.float32(0.0123), np.float32(2.0 ** -3), np.float32(1e-3)):
+        m, e = ops.dyadic_from_scales(torch.from_numpy(pre).to(DEV), torch.tensor([zs], device=DEV))
+        wm, we = norm_me(*O.dyadic(pre, zs))
+        assert np.array_equal(m.cpu().numpy(), wm) and np.array_equal(e.cpu().numpy(), we)
+
+
+def test_quantize_and_requant_f32():
+    r = rng(8)
+    B, Cn, T = 3, 20, 37
+    x = (r.standard_normal((B, Cn, T)) * 2).astype(np.float32)
+    lens = np.array([37, 20, 5], np.int32)
+    for bit in (8, 6):
+        s = O.sym_scale(bit, -3.3, 2.9).reshape(())
+        xm = np.where(np.arange(T)[None, None, :] < lens[:, None, None], x, 0).astype(np.float32)
+        want = O.sym_quantize(xm, bit, s)
+        codes, xq = ops.quantize_f32(torch.from_numpy(x).to(DEV), torch.tensor([s], device=DEV), bit,
+                                     lens=torch.from_numpy(lens).to(DEV))
+        assert np.array_equal(codes[:, :, :T].cpu().numpy(), want)
+        assert np.array_equal(xq.cpu().numpy(), (want * s).astype(np.float32))
+    # requant with per-channel scales + identity
+    pre = r.uniform(1e-5, 2e-4, Cn).astype(np.float32)
+    ids = r.uniform(1e-5, 2e-4, Cn).astype(np.float32)
+    z = r.integers(-30000, 30000, (B, Cn, T))
+    zi = r.integers(-30000, 30000, (B, Cn, T))
+    xf = (z * pre.reshape(1, -1, 1)).astype(np.float32)
+    idf = (zi * ids.reshape(1, -1, 1)).astype(np.float32)
+    zs = np.float32(0.031)
+    want = O.fixedpoint_mul(xf, pre.reshape(1, -1, 1), 8, zs, idf, ids.reshape(1, -1, 1))
+    codes, xq = ops.requant_f32(torch.from_numpy(xf).to(DEV), torch.from_numpy(pre).to(DEV),
+                                torch.tensor([zs], device=DEV), -128, 127,
+                                identity=torch.from_numpy(idf).to(DEV), id_sf=torch.from_numpy(ids).to(DEV))
+    assert np.array_equal(codes[:, :, :T].cpu().numpy(), want)
+    assert np.array_equal(xq.cpu().numpy(), (want * zs).astype(np.float32))
+    back = ops.codes_from_f32(xq, torch.tensor([zs], device=DEV))
+    assert np.array_equal(back[:, :, :T].cpu().numpy(), want)
+
+
+def test_requant_i8_lut():
+    r = rng(9)
+    B, Cn, T = 2, 16, 50
+    q = r.integers(0, 128, (B, Cn, T))
+    m, e = norm_me(*O.batch_frexp(np.array([2.0078])))
+    lens = np.array([50, 31], np.int32)
+    want = expected_requant(q, np.repeat(m, Cn), np.repeat(e, Cn), -256, 255, lens=lens)
+    out = ops.requant_i8(to_codes_tensor(q, True), T, True, m[0], e[0], -256, 255, torch.from_numpy(lens).to(DEV))
+    assert np.array_equal(from_codes_tensor(out, T, False), want)
+
+
+def test_minmax_and_quantile():
+    r = rng(10)
+    B, Cn, T = 4, 64, 200
+    x = r.standard_normal((B, Cn, T)).astype(np.float32)
+    idn = r.standard_normal((B, Cn, T)).astype(np.float32)
+    lens = np.array([200, 150, 90, 200], np.int32)
+    xd, idd, ld = torch.from_numpy(x).to(DEV), torch.from_numpy(idn).to(DEV), torch.from_numpy(lens).to(DEV)
+    mm = ops.minmax_f32(xd).cpu().numpy()
+    assert mm[0] == x.min() and mm[1] == x.max()
+    mm = ops.minmax_f32(xd, identity=idd).cpu().numpy()
+    s = (idn + x).astype(np.float32)
+    assert mm[0] == s.min() and mm[1] == s.max()
+    xm = np.where(np.arange(T)[None, None, :] < lens[:, None, None], np.abs(x) + 1, 0).astype(np.float32)
+    mm = ops.minmax_f32(torch.from_numpy(np.abs(x) + 1).to(DEV), lens=ld).cpu().numpy()
+    assert mm[0] == 0.0 and mm[1] == xm.max()
+    for p in (99.0, 99.9, 99.996):
+        qlo, qhi = np.float32(1 - p / 100), np.float32(p / 100)
+        got = ops.quantile2_f32(xd, qlo, qhi).cpu().numpy()
+        assert got[0] == O.torch_quantile(x, qlo) and got[1] == O.torch_quantile(x, qhi)
+        got = ops.quantile2_f32(xd, qlo, qhi, identity=idd).cpu().numpy()
+        assert got[0] == O.torch_quantile(s, qlo) and got[1] == O.torch_quantile(s, qhi)
+    xr = np.maximum(x, 0)  # many ties at 0 (post-ReLU tensors)
+    got = ops.quantile2_f32(torch.from_numpy(xr).to(DEV), np.float32(0.001), np.float32(0.999)).cpu().numpy()
+    assert got[0] == O.torch_quantile(xr, np.float32(0.001)) and got[1] == O.torch_quantile(xr, np.float32(0.999))
+
+
+def test_decoder_tail():
+    r = rng(11)
+    B, V, T = 3, 29, 45
+    logits = r.standard_normal((B, V, T)).astype(np.float32)
+    logits[0, 5, 3] = logits[0, 9, 3] = 7.0  # tie: first index wins
+    t = torch.zeros((B, V, 48), dtype=torch.float32, device=DEV)
+    t[:, :, :T] = torch.from_numpy(logits).to(DEV)
+    labels = ops.ctc_argmax(t, T).cpu().numpy()
+    assert np.array_equal(labels, logits.argmax(axis=1))
+    lp = ops.log_softmax_tv(t, T).cpu()
+    want = torch.log_softmax(torch.from_numpy(logits).transpose(1, 2), dim=-1)
+    assert torch.allclose(lp, want, atol=2e-6, rtol=0)
+
+
+def test_error_paths():
+    x = ops.alloc_codes(1, 8, 32, DEV)
+    ch = ops.chan_table(np.ones(8, np.float32), None, np.full(8, 2 ** 30), np.full(8, 30), DEV)
+    with pytest.raises(ValueError):
+        ops.dwconv(x, 32, torch.zeros((8, 5), dtype=torch.int8, device=DEV), x, 32, 5, 3, 1, 2,
+                   ops.make_epilogue(L.EPI_REQUANT_I8, ch))
+    with pytest.raises(ValueError):
+        ops.quantile2_f32(torch.zeros((1, 1, 8), device=DEV), 1.5, 0.5)
+
+
+def _sweep_descriptors():
+    """Bring-up aid: try B-operand descriptor stride variants on the first GEMM case."""
+    lib = L.lib()
+    for lbo, sbo in ((16384, 1024), (1024, 16384), (128, 1024), (1024, 128), (0, 1024), (2048, 1024),
+                     (4096, 1024), (1024, 1024), (16, 1024), (1024, 2048)):
+        lib.qasr_debug_set(0, lbo)
+        lib.qasr_debug_set(1, sbo)
+        try:
+            test_gemm_raw_i32(GEMM_CASES[0])
+            print("SWEEP lbo=%d sbo=%d: MATCH" % (lbo, sbo), flush=True)
+        except AssertionError as ex:
+            print("SWEEP lbo=%d sbo=%d: %s" % (lbo, sbo, str(ex)[:80]), flush=True)
+    lib.qasr_debug_set(0, -1)
+    lib.qasr_debug_set(1, -1)
+
+
+if __name__ == "__main__":
+    # non-stopping report (first bring-up on a GPU box)
+    import traceback
+    if os.environ.get("QASR_SWEEP"):
+        _sweep_descriptors()
+    fails = 0
+    tests = []
+    for name, fn in list(globals().items()):
+        if name.startswith("test_") and callable(fn):
+            marks = [m for m in getattr(fn, "pytestmark", []) if m.name == "parametrize"]
+            if not marks:
+                tests.append((name, fn, {}))
+                continue
+            import itertools
+            axes = []
+            for m in marks:
+                argn, vals = m.args[0], m.args[1]
+                axes.append([(argn, v) for v in vals])
+            for combo in itertools.product(*axes):
+                tests.append((name + str([v[0] if isinstance(v, tuple) else v for _, v in combo]), fn, dict(combo)))
+    for name, fn, kw in tests:
+        try:
+            fn(**kw)
+            print("PASS", name, flush=True)
+        except Exception as ex:  # noqa: BLE001
+            fails += 1
+            print("FAIL", name, "->", str(ex).splitlines()[0][:200] if str(ex) else repr(ex), flush=True)
+            if os.environ.get("QASR_TRACE"):
+                traceback.print_exc()
+            if "CUDA" in str(ex) or "qasr error" in str(ex):
+                print("fatal CUDA error, stopping")
+                break
+    print("failures:", fails, "of", len(tests))
+    sys.exit(1 if fails else 0)
