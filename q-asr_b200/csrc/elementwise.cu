@@ -313,10 +313,9 @@ __global__ void quantile_scan_kernel(QuantileWs* ws, int pass) {
 
 __device__ __forceinline__ float torch_lerp(float a, float b, float w) {
   const float diff = __fsub_rn(b, a);
-  // ATen lerp (native/Lerp.h): weight < 0.5 ? a + w * diff : b - diff * (1 - w).  The oracle is
-  // pinned to the reference run on CPU, where each step rounds separately (no fma contraction).
-  return (w < 0.5f) ? __fadd_rn(a, __fmul_rn(w, diff))
-                    : __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, w)));
+  // ATen lerp (native/Lerp.h): weight < 0.5 ? a + w * diff : b - diff * (1 - w); torch's CPU and
+  // CUDA builds both contract the multiply-add into one fma (checked against torch.lerp).
+  return (w < 0.5f) ? __fmaf_rn(w, diff, a) : __fmaf_rn(-diff, __fsub_rn(1.0f, w), b);
 }
 
 __global__ void quantile_final_kernel(const QuantileWs* ws, long long n, float q_lo, float q_hi,

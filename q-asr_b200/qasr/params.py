@@ -31,6 +31,12 @@ def reestimate_bn_(encoder, feat_in=64, seed=1234, batch=4, frames=256, jitter=T
     x = torch.randn(batch, feat_in, frames, generator=g).to(dev)
     lens = torch.full((batch,), frames, dtype=torch.long, device=dev)
     encoder(x, lens)
+    # QuantAct tracks ranges even in quant_mode 'none' (quant_modules.py:111-141 run before the
+    # early return at :143-144): forget what this FP32 pass recorded.
+    for m in encoder.modules():
+        if hasattr(m, "x_min") and hasattr(m, "x_max") and hasattr(m, "act_scaling_factor"):
+            m.x_min = torch.zeros_like(m.x_min)
+            m.x_max = torch.zeros_like(m.x_max)
     for bn, (mom, training) in zip(bns, saved):
         bn.momentum = mom
         bn.train(training)
