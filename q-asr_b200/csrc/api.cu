@@ -37,7 +37,12 @@ int qasr_validate_epilogue(const qasr_epilogue* e, bool allow_second_operand) {
   if (e->mode == QASR_EPI_REQUANT_I8) {
     QASR_CHECK_ARG(e->qmin < e->qmax && e->qmin >= -256 && e->qmax <= 255, "epilogue: clamp [%d, %d]", e->qmin, e->qmax);
     const bool s2 = e->flags & QASR_F_STAGE2;
-    const int lo = s2 ? e->qmin2 : ((e->flags & QASR_F_RELU1) ? (e->qmin > 0 ? e->qmin : 0) : e->qmin);
+    // codes are non-negative after a ReLU (the reference's "act_bit + 1" unsigned inputs,
+    // jasper.py:159-164): a [-256, 255] clamp then means an unsigned 8-bit tensor
+    const bool nonneg = (e->flags & QASR_F_RELU1) ||
+                        ((e->flags & QASR_F_RELU0) && e->ch1 == nullptr && e->prev == nullptr);
+    int lo = s2 ? e->qmin2 : e->qmin;
+    if (nonneg && lo < 0) lo = 0;
     const int hi = s2 ? e->qmax2 : e->qmax;
     QASR_CHECK_ARG(hi - lo <= 255 && lo >= -128 && hi <= 255 && !(lo < 0 && hi > 127),
                    "epilogue: final code range [%d, %d] does not fit one 8-bit tensor", lo, hi);

@@ -402,8 +402,8 @@ extern "C" int qasr_requant_f32(const float* x, const float* pre_sf, int32_t n_p
   QASR_CHECK_ARG(n_pre == 1 || n_pre == C, "requant_f32: pre_sf must have 1 or C entries");
   QASR_CHECK_ARG(!identity || (id_sf && (n_id == 1 || n_id == C)), "requant_f32: identity scale");
   QASR_CHECK_ARG(B > 0 && C > 0 && T > 0 && ld >= T, "requant_f32: bad shape");
-  QASR_CHECK_ARG(qmin >= -256 && qmax <= 255 && qmin < qmax && (qmax - qmin) <= 255,
-                 "requant_f32: clamp range [%d, %d] does not fit 8 bits", qmin, qmax);
+  QASR_CHECK_ARG(qmin >= -256 && qmax <= 255 && qmin < qmax,
+                 "requant_f32: clamp range [%d, %d] wider than the 9-bit activation range", qmin, qmax);
   QASR_CHECK_ARG(!codes || (codes_ld % 4 == 0 && codes_ld >= ((T + 3) / 4) * 4), "requant_f32: codes pitch");
   const long long work = (long long)B * C * ((T + 3) / 4);
   requant_f32_kernel<<<grid_for(work, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
@@ -428,7 +428,9 @@ extern "C" int qasr_requant_i8(const int8_t* in, int32_t in_ld, int32_t in_signe
   QASR_CHECK_ARG(in && out, "requant_i8: null pointer");
   QASR_CHECK_ARG(in_ld % 16 == 0 && out_ld % 16 == 0 && in_ld >= T && out_ld >= T &&
                      qasr_aligned16(in) && qasr_aligned16(out), "requant_i8: pitch/alignment");
-  QASR_CHECK_ARG((qmax - qmin) <= 255 && qmin >= -256 && qmax <= 255, "requant_i8: clamp range");
+  // [-256, 255] is the reference's 9-bit clamp; the caller guarantees the codes fit 8 bits
+  // (non-negative input, or a signed range within [-128, 127])
+  QASR_CHECK_ARG(qmin < qmax && qmin >= -256 && qmax <= 255, "requant_i8: clamp range");
   const long long work = (long long)B * C * ((T + 15) / 16);
   requant_i8_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
       in, in_ld, in_signed, m, e, qmin, qmax, out, out_ld, B, C, T, lens);

@@ -45,6 +45,7 @@ struct GemmArgs {
   int nseg, m_tiles, n_tiles, total_tiles;
   GemmSeg seg[2];
   uint32_t b_lbo, b_sbo, a_sbo;  // smem descriptor strides (bytes)
+  int dbg_align, dbg_nonneg;     // bring-up knobs (qasr_debug_set 2 / 3)
   EpiArgs ep;
 };
 
@@ -187,7 +188,9 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const CUtensorMap* mA = sg == 0 ? &tmA0 : &tmA1;
           const CUtensorMap* mB = sg == 0 ? &tmB0 : &tmB1;
           for (int tap = 0; tap < s.taps; ++tap) {
-            const int tcoord = nt * BN * s.stride + tap * s.dil - s.pad;
+            int tcoord = nt * BN * s.stride + tap * s.dil - s.pad;
+            if (g.dbg_align > 1) tcoord = (tcoord / g.dbg_align) * g.dbg_align;
+            if (g.dbg_nonneg && tcoord < 0) tcoord = 0;
             for (int cb = 0; cb < s.cblocks; ++cb) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
               const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
@@ -431,8 +434,21 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   for (int i = 0; i < g.nseg; ++i) {
     const qasr_gemm_operand* o = ops[i];
     QASR_CHECK_ARG(o->x && o->wp && o->C_in > 0 && o->T_in > 0 && o->k > 0, "conv1d_gemm: operand %d bad", i);
-    QASR_CHECK_ARG(o->stride == 1, "conv1d_gemm: stride %d not supported by the tensor-core path", o->stride);
+    if (o->stride != 1) {
+      qasr_set_error("conv1d_gemm: stride %d not supported by the (B,C,T) tensor-core path", o->stride);
+      return QASR_ERR_UNSUPPORTED;
+    }
     QASR_CHECK_ARG(o->dilation >= 1 && o->pad >= 0, "conv1d_gemm: bad dilation/pad");
+    // TMA needs a 16-byte aligned box start along the contiguous (time) axis (measured on B200: an
+    // unaligned inner coordinate raises an illegal-instruction fault), so in the (B,C,T) layout only
+    // taps whose shift is a multiple of 16 frames can be fetched: in practice the 1x1 convs.
+    for (int tap = 0; tap < o->k; ++tap) {
+      if ((tap * o->dilation - o->pad) % 16 != 0) {
+        qasr_set_error("conv1d_gemm: k=%d dilation=%d pad=%d needs unaligned time shifts; the (B,C,T) "
+                       "tensor-core path handles 1x1 convolutions only", o->k, o->dilation, o->pad);
+        return QASR_ERR_UNSUPPORTED;
+      }
+    }
     QASR_CHECK_ARG((o->T_in + 2 * o->pad - o->dilation * (o->k - 1) - 1) / o->stride + 1 == T_out,
                    "conv1d_gemm: operand %d: T_out %d inconsistent with T_in %d", i, T_out, o->T_in);
     QASR_CHECK_ARG(o->x_ld % 16 == 0 && o->x_ld >= o->T_in && qasr_aligned16(o->x) && qasr_aligned16(o->wp),
@@ -466,17 +482,22 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   g.b_sbo = g_dbg[1] >= 0 ? (uint32_t)g_dbg[1] : 1024;
   g.b_lbo = g_dbg[0] >= 0 ? (uint32_t)g_dbg[0] : (uint32_t)(BK * 128);
   g.ep = make_epi_args(epi);
+  g.dbg_align = g_dbg[2] > 0 ? (int)g_dbg[2] : 0;
+  g.dbg_nonneg = g_dbg[3] > 0 ? 1 : 0;
 
   const bool fast = !(epi->flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64));
   int grid = qasr_sm_count();
   if (grid > g.total_tiles) grid = g.total_tiles;
   cudaStream_t st = (cudaStream_t)stream;
-  if (fast) {
-    QASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    gemm_i8_kernel<true><<<grid, kGemmThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);
-  } else {
-    QASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    gemm_i8_kernel<false><<<grid, kGemmThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);
+  static bool attr_set[2][64] = {};
+  int dev = 0;
+  QASR_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[fast ? 1 : 0][dev]) {  // once per kernel and device (not inside graph replays)
+    if (fast) QASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    else QASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr_set[fast ? 1 : 0][dev] = true;
   }
+  if (fast) gemm_i8_kernel<true><<<grid, kGemmThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);
+  else gemm_i8_kernel<false><<<grid, kGemmThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);
   return qasr_check_launch("gemm_i8_kernel");
 }

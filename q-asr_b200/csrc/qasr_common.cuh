@@ -116,7 +116,10 @@ struct Epilogue {
                                                          bool exact_f32, bool bias64) {
     double z;
     if (exact_f32) {
-      float a = bias64 ? (float)((long long)acc + (long long)c.bias) : (float)(acc + c.bias);
+      // INT32_MAX is the sentinel for b_int == 2^31: the reference's float32 clamp bound n-1 =
+      // 2^31-2 rounds to 2^31 (quant_utils.py:76 with k = 32), which no int32 can hold
+      const long long b64 = c.bias == 2147483647 ? 2147483648LL : (long long)c.bias;
+      float a = bias64 ? (float)((long long)acc + b64) : (float)(acc + c.bias);
       float y = __fmul_rn(a, c.s);                 // quant_modules.py:307
       if (relu) y = fmaxf(y, 0.0f);                // jasper.py:661
       z = (double)rintf(__fdiv_rn(y, c.s));        // quant_utils.py:187
@@ -168,8 +171,8 @@ __device__ __forceinline__ int epilogue_requant(const EpiArgs& ep, int acc0, con
 }
 
 __device__ __forceinline__ float epilogue_dequant(const EpiArgs& ep, int acc, const ChanRegs& c) {
-  float a = (ep.flags & QASR_F_BIAS64) ? (float)((long long)acc + (long long)c.bias)
-                                       : (float)(acc + c.bias);
+  const long long b64 = c.bias == 2147483647 ? 2147483648LL : (long long)c.bias;
+  float a = (ep.flags & QASR_F_BIAS64) ? (float)((long long)acc + b64) : (float)(acc + c.bias);
   float y = __fmul_rn(a, c.s);
   if (ep.flags & QASR_F_RELU0) y = fmaxf(y, 0.0f);
   return y;

@@ -1,0 +1,431 @@
+"""Drop-in `nemo.quantization.utils.quant_modules`: QuantAct, QuantConv1d (+ QuantBnConv1d),
+QuantLinear with the reference's constructor flags, buffers, methods and return conventions
+(reference nemo/quantization/utils/quant_modules.py:18-469), executing on the sm_100a kernels
+behind include/qasr.h.
+
+Module-level contract (same as the reference): every tensor between modules is a float32 tensor
+equal to integer_code * scale, handed on together with its scale.  Inside each call the integer
+work (requantisation, the convolution itself, range statistics) runs in the CUDA kernels; the
+fully fused int8-resident forward is `qasr.plan` (built by ConvASREncoder when every module is
+fixed and static).  quant_mode == 'none' is the FP32 pass-through state of the API (plain torch
+ops, used by --no_quant and BN re-estimation), not a second backend.  There is no CPU fallback
+for quantised execution.
+"""
+import logging
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn import Module, Parameter
+
+from qasr import _lib as _L
+from qasr import ops as _ops
+
+from .quant_utils import *  # noqa: F401,F403  (the reference star-exports these too)
+from .quant_utils import SymmetricQuantFunction, symmetric_linear_quantization_params
+
+logger = logging.getLogger(__name__)
+
+__all__ = ["QuantAct", "QuantConv1d", "QuantBnConv1d", "QuantLinear"]
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError("%s: quantised execution needs CUDA tensors (sm_100a kernels; there is no "
+                           "CPU fallback)" % what)
+
+
+class QuantAct(Module):
+    """Activation quantiser (reference quant_modules.py:18-194).
+
+    Parameters (identical to the reference): activation_bit, act_range_momentum=0.95,
+    running_stat=True, per_channel=False, channel_len=None, quant_mode='none', dynamic=False,
+    percentile=None.
+    """
+
+    def __init__(self, activation_bit, act_range_momentum=0.95, running_stat=True, per_channel=False,
+                 channel_len=None, quant_mode="none", dynamic=False, percentile=None):
+        super().__init__()
+        self.activation_bit = activation_bit
+        self.act_range_momentum = act_range_momentum
+        self.running_stat = running_stat
+        self.quant_mode = quant_mode
+        self.percentile = percentile
+        self.per_channel = per_channel
+        self.dynamic = dynamic
+        n = 1
+        if per_channel:
+            assert channel_len is not None
+            n = channel_len
+        self.register_buffer("x_min", torch.zeros(n))
+        self.register_buffer("x_max", torch.zeros(n))
+        self.register_buffer("act_scaling_factor", torch.zeros(n))
+        if quant_mode == "none":
+            self.act_function = None
+        elif quant_mode == "symmetric":
+            self.act_function = SymmetricQuantFunction.apply
+        elif quant_mode == "asymmetric":
+            raise NotImplementedError("unsupported quant mode: {}".format(quant_mode))
+        else:
+            raise ValueError("unknown quant mode: {}".format(quant_mode))
+
+    def __repr__(self):
+        return "{0}(activation_bit={1}, quant_mode: {2}, Act_min: {3:.2f}, Act_max: {4:.2f})".format(
+            self.__class__.__name__, self.activation_bit, self.quant_mode, self.x_min.min().item(),
+            self.x_max.max().item())
+
+    def fix(self):
+        self.running_stat = False
+
+    def unfix(self):
+        self.running_stat = True
+
+    def set_percentile(self, percentile):
+        assert not self.per_channel, "percentile mode is only available for the global quantization mode"
+        self.percentile = percentile
+
+    # -- range statistics (reference :113-125 / :150-167) ---------------------------------
+    def _batch_range(self, x, identity, percentile):
+        if x.is_cuda:
+            x3 = x if x.dim() == 3 else x.reshape(1, -1, x.shape[-1])
+            id3 = None if identity is None else identity.reshape(x3.shape)
+            if self.per_channel:
+                x_act = x3 if id3 is None else id3 + x3
+                return x_act.amin(dim=(0, 2)), x_act.amax(dim=(0, 2))
+            if percentile is None:
+                mm = _ops.minmax_f32(x3, id3)
+            else:
+                q_hi = torch.tensor(percentile / 100).item()       # float32 rounding of the level,
+                q_lo = torch.tensor(1 - percentile / 100).item()   # as torch.tensor(...) does (:122-123)
+                mm = _ops.quantile2_f32(x3, q_lo, q_hi, id3)
+            return mm[0:1], mm[1:2]
+        # quant_mode 'none' on CPU tensors (FP32 pass-through state only)
+        x_act = x if identity is None else identity + x
+        if self.per_channel:
+            return x_act.amin(dim=(0, 2)), x_act.amax(dim=(0, 2))
+        if percentile is None:
+            return x_act.min().reshape(1), x_act.max().reshape(1)
+        return (torch.quantile(x_act, torch.tensor(1 - percentile / 100)).reshape(1),
+                torch.quantile(x_act, torch.tensor(percentile / 100)).reshape(1))
+
+    def forward(self, x, pre_act_scaling_factor=None, identity=None, identity_scaling_factor=None):
+        batch_range = None
+        if self.running_stat:
+            assert self.percentile is None or not self.per_channel, \
+                "percentile mode is only available for the global quantization mode"
+            x_min, x_max = batch_range = self._batch_range(x, identity, self.percentile)
+            # first call / running min-max / EMA (:127-141) without a host round trip
+            first = torch.eq(self.x_min, self.x_max).all()
+            if self.act_range_momentum == -1:
+                upd_min, upd_max = torch.min(self.x_min, x_min), torch.max(self.x_max, x_max)
+            else:
+                mom = self.act_range_momentum
+                upd_min = self.x_min * mom + x_min * (1 - mom)
+                upd_max = self.x_max * mom + x_max * (1 - mom)
+            self.x_min = torch.where(first, self.x_min + x_min, upd_min)
+            self.x_max = torch.where(first, self.x_max + x_max, upd_max)
+
+        if self.quant_mode == "none":
+            return (x if identity is None else identity + x), None
+        assert self.quant_mode == "symmetric", "unsupported quant mode: {}".format(self.quant_mode)
+        _require_cuda(x, "QuantAct")
+
+        if self.dynamic:
+            pct = self.percentile if self.percentile else None
+            if batch_range is not None and pct == self.percentile:
+                x_min, x_max = batch_range
+            else:
+                assert pct is None or not self.per_channel
+                x_min, x_max = self._batch_range(x, identity, pct)
+        else:
+            x_min, x_max = self.x_min, self.x_max
+
+        act_scaling_factor = symmetric_linear_quantization_params(
+            self.activation_bit, x_min.view(1, -1, 1), x_max.view(1, -1, 1), per_channel=self.per_channel)
+        self.act_scaling_factor = act_scaling_factor.reshape(-1)
+        n = 2 ** (self.activation_bit - 1) - 1
+        x3 = x if x.dim() == 3 else x.reshape(1, -1, x.shape[-1])
+
+        if self.per_channel:
+            return self._forward_per_channel(x3, pre_act_scaling_factor, identity, identity_scaling_factor,
+                                             act_scaling_factor, n).view(x.shape), act_scaling_factor
+
+        z_sf = self.act_scaling_factor[:1].contiguous()
+        if pre_act_scaling_factor is None:
+            # first layer: SymmetricQuantFunction, then the identity dyadic product (:180-190)
+            if self.activation_bit > 8:
+                raise NotImplementedError("first-layer activation_bit > 8")
+            _, xq = _ops.quantize_f32(x3, z_sf, self.activation_bit, want_codes=False)
+        else:
+            id3 = None if identity is None else identity.reshape(x3.shape)
+            _, xq = _ops.requant_f32(x3, pre_act_scaling_factor.float(), z_sf, -n - 1, n, identity=id3,
+                                     id_sf=None if identity is None else identity_scaling_factor.float(),
+                                     want_codes=False)
+        return xq.view(x.shape), act_scaling_factor
+
+    def _forward_per_channel(self, x, pre_sf, identity, identity_sf, act_sf, n):
+        """per_channel=True has no caller in the reference tree; it is served by
+        one qasr_requant_f32 launch per output channel group sharing a scale, i.e. per channel."""
+        outs = []
+        for c in range(x.shape[1]):
+            z_sf = act_sf.reshape(-1)[c:c + 1].contiguous()
+            xc = x[:, c:c + 1, :].contiguous()
+            if pre_sf is None:
+                _, xq = _ops.quantize_f32(xc, z_sf, self.activation_bit, want_codes=False)
+            else:
+                p = pre_sf.reshape(-1)
+                p = p[c:c + 1] if p.numel() > 1 else p
+                idc = None if identity is None else identity[:, c:c + 1, :].contiguous()
+                isf = None
+                if identity is not None:
+                    isf = identity_sf.reshape(-1)
+                    isf = isf[c:c + 1] if isf.numel() > 1 else isf
+                _, xq = _ops.requant_f32(xc, p.float(), z_sf, -n - 1, n, identity=idc, id_sf=isf,
+                                         want_codes=False)
+            outs.append(xq)
+        return torch.cat(outs, dim=1)
+
+
+class QuantConv1d(Module):
+    """Quantised Conv1d with per-output-channel weights and optional folded BatchNorm
+    (reference quant_modules.py:197-367).  Parameters: weight_bit, bias_bit=None,
+    quant_mode='none', per_channel=False, fix_bn=True."""
+
+    def __init__(self, weight_bit, bias_bit=None, quant_mode="none", per_channel=False, fix_bn=True):
+        super().__init__()
+        self.weight_bit = weight_bit
+        self.per_channel = per_channel
+        self.bias_bit = bias_bit
+        self.quantize_bias = bias_bit is not None
+        self.quant_mode = quant_mode
+        self.fix_bn = fix_bn
+        if self.quant_mode == "symmetric":
+            self.weight_function = SymmetricQuantFunction.apply
+        self._prep_key = None
+        self._prep = None
+
+    def set_param(self, conv):
+        self.in_channels = conv.in_channels
+        self.out_channels = conv.out_channels
+        self.kernel_size = conv.kernel_size
+        self.stride = conv.stride
+        self.padding = conv.padding
+        self.dilation = conv.dilation
+        self.groups = conv.groups
+        self.weight = Parameter(conv.weight.data.clone())
+        if conv.bias is not None:
+            self.bias = Parameter(conv.bias.data.clone())
+            self.register_buffer("bias_integer", torch.zeros_like(self.bias))
+        else:
+            self.bias = None
+            self.bias_integer = None
+        self.register_buffer("weight_integer", torch.zeros_like(self.weight))
+        self.register_buffer("conv_scaling_factor", torch.zeros(self.out_channels))
+        self.conv = conv
+        self.bn = None
+
+    def __repr__(self):
+        return "{0}(weight_bit={1}, per_channel: {2}, quant_mode: {3}".format(
+            self.__class__.__name__, self.weight_bit, self.per_channel, self.quant_mode)
+
+    def fix(self):
+        self.fix_bn = True
+
+    def unfix(self):
+        self.fix_bn = False
+
+    def bn_folding(self, bn):
+        self.bn = bn
+
+    # -- parameter preparation, cached per weight / BN version (the reference redoes it every
+    #    forward, quant_modules.py:274-291,353-364) --------------------------------------
+    def folded_params(self):
+        """(weight, bias) after BN folding (reference :351-364); float32 torch ops."""
+        weight = self.weight.data
+        bias = None if self.bias is None else self.bias.data
+        if self.bn is not None and self.fix_bn:
+            running_std = torch.sqrt(self.bn.running_var.detach() + self.bn.eps)
+            scale_factor = self.bn.weight.detach() / running_std
+            weight = weight * scale_factor.reshape([-1, 1, 1])
+            b0 = bias if bias is not None else torch.zeros_like(self.bn.running_mean)
+            bias = (b0 - self.bn.running_mean.detach()) * scale_factor + self.bn.bias.detach()
+        return weight, bias
+
+    def _prepare(self):
+        key = (self.weight._version, self.weight.data_ptr(), self.weight_bit, self.per_channel,
+               None if self.bias is None else self.bias._version,
+               None if self.bn is None else (self.bn.weight._version, self.bn.bias._version,
+                                             self.bn.running_mean._version, self.bn.running_var._version,
+                                             self.fix_bn))
+        if key != self._prep_key:
+            weight, bias = self.folded_params()
+            if self.per_channel:
+                flat = weight.reshape(weight.shape[0], -1)
+                w_min, w_max = flat.min(dim=1).values, flat.max(dim=1).values
+            else:
+                w_min, w_max = weight.min().expand(1), weight.max().expand(1)
+            s_w = symmetric_linear_quantization_params(self.weight_bit, w_min.view(-1, 1, 1),
+                                                       w_max.view(-1, 1, 1), self.per_channel)
+            w_int = self.weight_function(weight, self.weight_bit, s_w)
+            s_w = s_w.reshape(-1).expand(self.out_channels).contiguous()
+            w8 = w_int.to(torch.int8).contiguous()
+            depthwise = self.groups == self.in_channels == self.out_channels and self.groups > 1
+            packed = None
+            if not depthwise:
+                if self.groups != 1:
+                    raise NotImplementedError("grouped (non-depthwise) quantised convolution")
+                packed = _ops.pack_weights(w8)
+            self._prep = dict(s_w=s_w, w_int=w_int, w8=w8.reshape(self.out_channels, -1) if depthwise else w8,
+                              packed=packed, bias=bias, depthwise=depthwise)
+            self._prep_key = key
+            self.weight_integer = w_int
+            self.conv_scaling_factor = s_w
+        return self._prep
+
+    def int_conv(self, weight, bias, x, pre_act_scaling_factor, input_unsigned=None):
+        """Integer convolution of the codes x / pre_act_scaling_factor (reference :272-309).
+        `weight` / `bias` are accepted for signature parity; the prepared (cached) integer
+        parameters of this module are what is used."""
+        p = self._prepare()
+        _require_cuda(x, "QuantConv1d")
+        s_x = pre_act_scaling_factor.reshape(-1)[:1].float().contiguous()
+        s_out = p["s_w"] * s_x                                          # :293
+        if p["bias"] is not None:
+            b_int = self.weight_function(p["bias"], self.bias_bit, s_out)  # float32 math, :296-297
+            self.bias_integer = b_int
+            b_i32 = b_int.to(torch.int64).clamp_(-2 ** 31, 2 ** 31 - 1).to(torch.int32)
+        else:
+            b_i32 = torch.zeros(self.out_channels, dtype=torch.int32, device=x.device)
+        B, Cin, T = x.shape
+        if input_unsigned is None:
+            input_unsigned = bool((x.min() >= 0).item())                # auto mode: one host sync
+        codes = _ops.codes_from_f32(x, s_x)
+        k, stride, dil, pad = self.kernel_size[0], self.stride[0], self.dilation[0], self.padding[0]
+        T_out = (T + 2 * pad - dil * (k - 1) - 1) // stride + 1
+        tab = torch.stack([s_out.contiguous().view(torch.int32), b_i32,
+                           torch.full_like(b_i32, 1 << 30), torch.full_like(b_i32, 30)], dim=1).contiguous()
+        flags = _L.F_BIAS64 | (0 if input_unsigned else _L.F_B_SIGNED)
+        ep = _ops.make_epilogue(_L.EPI_DEQUANT_F32, tab, flags=flags)
+        out = torch.empty((B, self.out_channels, _ops.round_up(T_out, 16)), dtype=torch.float32,
+                          device=x.device)
+        if p["depthwise"]:
+            _ops.dwconv(codes, T, p["w8"], out, T_out, k, stride, dil, pad, ep)
+        else:
+            _ops.conv_gemm(_ops.gemm_operand(codes, T, p["packed"], Cin, k, stride, dil, pad), None, out, B,
+                           self.out_channels, T_out, ep)
+        conv_output = out[:, :, :T_out]
+        if out.shape[-1] != T_out:
+            conv_output = conv_output.contiguous()
+        return conv_output, s_out.view(1, -1, 1)
+
+    def forward(self, x, pre_act_scaling_factor=None, input_unsigned=None):
+        if self.quant_mode == "none":
+            conv = F.conv1d(x, weight=self.weight, bias=self.bias, stride=self.stride, padding=self.padding,
+                            dilation=self.dilation, groups=self.groups)
+            if self.bn is not None:
+                conv = self.bn(conv)
+            return conv, None
+        assert self.quant_mode == "symmetric"
+        if self.bn is not None and not self.fix_bn:
+            # BN folded but not fixed: the reference's training-time statistics update (:337-349)
+            conv_output, sf = self.int_conv(None, None, x, pre_act_scaling_factor, input_unsigned)
+            batch_mean = torch.mean(conv_output, dim=(0, 2))
+            batch_var = torch.var(conv_output, dim=(0, 2))
+            mom = self.bn.momentum
+            self.bn.running_mean = self.bn.running_mean.detach() * (1 - mom) + mom * batch_mean
+            self.bn.running_var = self.bn.running_var.detach() * (1 - mom) + mom * batch_var
+            output_factor = self.bn.weight.view(1, -1, 1) / torch.sqrt(self.bn.running_var + self.bn.eps).view(1, -1, 1)
+            output = output_factor * (conv_output - self.bn.running_mean.view(1, -1, 1)) + self.bn.bias.view(1, -1, 1)
+            return output, output_factor * sf
+        return self.int_conv(None, None, x, pre_act_scaling_factor, input_unsigned)
+
+
+class QuantBnConv1d(QuantConv1d):
+    """Conv1d + folded BatchNorm1d.  The reference has no class of this name: BN folding is
+    QuantConv1d.bn_folding(bn) + fix_bn (quant_modules.py:269,351-364); this thin subclass gives
+    the north-star name the same behaviour with the BN passed at set_param time."""
+
+    def set_param(self, conv, bn=None):
+        super().set_param(conv)
+        if bn is not None:
+            self.bn_folding(bn)
+
+
+class QuantLinear(Module):
+    """Quantised Linear (reference quant_modules.py:370-469).  Never called in the reference (its
+    bias quantisation call at :462-463 passes four arguments to a three-argument function and
+    would raise); this implements the evident intent: per-row weight quantisation, 32-bit bias,
+    integer matmul on the tensor-core GEMM kernel (a Linear is a 1x1 conv over a length-N 'time'
+    axis)."""
+
+    def __init__(self, weight_bit, bias_bit=None, per_channel=False, quant_mode="none"):
+        super().__init__()
+        self.weight_bit = weight_bit
+        self.quant_mode = quant_mode
+        self.per_channel = per_channel
+        self.bias_bit = bias_bit
+        self.quantize_bias = bias_bit is not None
+        if quant_mode == "none":
+            pass
+        elif quant_mode == "symmetric":
+            self.weight_function = SymmetricQuantFunction.apply
+        elif quant_mode == "asymmetric":
+            raise NotImplementedError("unsupported quant mode: {}".format(quant_mode))
+        else:
+            raise ValueError("unknown quant mode: {}".format(quant_mode))
+
+    def __repr__(self):
+        s = super().__repr__()
+        return "(" + s + " weight_bit={}, quant_mode={})".format(self.weight_bit, self.quant_mode)
+
+    def set_param(self, linear):
+        self.in_features = linear.in_features
+        self.out_features = linear.out_features
+        self.weight = Parameter(linear.weight.data.clone())
+        self.register_buffer("fc_scaling_factor", torch.zeros(self.out_features))
+        self.register_buffer("weight_integer", torch.zeros_like(self.weight))
+        self.bias = None if linear.bias is None else Parameter(linear.bias.data.clone())
+        self.register_buffer("bias_integer", torch.zeros(self.out_features))
+
+    def fix(self):
+        pass
+
+    def unfix(self):
+        pass
+
+    def forward(self, x, prev_act_scaling_factor=None):
+        if self.quant_mode == "none":
+            return F.linear(x, weight=self.weight, bias=self.bias), None
+        assert self.quant_mode == "symmetric", "unsupported quant mode: {}".format(self.quant_mode)
+        assert prev_act_scaling_factor is not None and prev_act_scaling_factor.shape == (1,)
+        _require_cuda(x, "QuantLinear")
+        w = self.weight.data
+        if self.per_channel:
+            w_min, w_max = w.min(dim=1).values, w.max(dim=1).values
+        else:
+            w_min, w_max = w.min().expand(1), w.max().expand(1)
+        self.fc_scaling_factor = symmetric_linear_quantization_params(self.weight_bit, w_min, w_max,
+                                                                      self.per_channel)
+        self.weight_integer = self.weight_function(w, self.weight_bit, self.fc_scaling_factor.view(-1, 1))
+        s_out = (self.fc_scaling_factor * prev_act_scaling_factor).expand(self.out_features).contiguous()
+        if self.bias is not None:
+            bits = self.bias_bit if self.bias_bit is not None else 32
+            self.bias_integer = self.weight_function(self.bias.data, bits, s_out)
+            b_i32 = self.bias_integer.to(torch.int64).clamp_(-2 ** 31, 2 ** 31 - 1).to(torch.int32)
+        else:
+            b_i32 = torch.zeros(self.out_features, dtype=torch.int32, device=x.device)
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, self.in_features)
+        xt = x2.t().contiguous().unsqueeze(0)                     # (1, in, N): N plays the time axis
+        s_x = prev_act_scaling_factor.float().contiguous()
+        codes = _ops.codes_from_f32(xt, s_x)
+        N = x2.shape[0]
+        wp = _ops.pack_weights(self.weight_integer.to(torch.int8).unsqueeze(-1).contiguous())
+        tab = torch.stack([s_out.view(torch.int32), b_i32, torch.full_like(b_i32, 1 << 30),
+                           torch.full_like(b_i32, 30)], dim=1).contiguous()
+        ep = _ops.make_epilogue(_L.EPI_DEQUANT_F32, tab, flags=_L.F_BIAS64 | _L.F_B_SIGNED)
+        out = torch.empty((1, self.out_features, _ops.round_up(N, 16)), dtype=torch.float32, device=x.device)
+        _ops.conv_gemm(_ops.gemm_operand(codes, N, wp, self.in_features, 1), None, out, 1, self.out_features,
+                       N, ep)
+        y = out[0, :, :N].t().reshape(*lead, self.out_features)
+        return y, s_out

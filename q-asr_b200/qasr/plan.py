@@ -1,0 +1,518 @@
+"""Fused int8-resident execution plan for a calibrated, static Jasper / QuartzNet model.
+
+The module-level API (nemo.quantization.utils.quant_modules) hands float32 code*scale tensors
+from module to module like the reference does.  When every QuantAct is fixed and static the whole
+forward is a fixed sequence of integer kernels, so this plan walks the module tree ONCE
+(reference control flow: conv_asr.py:194-206, jasper.py:641-692, 175-194), folds every
+QuantConv1d rescale + ReLU + consumer-QuantAct requantisation (+ res_act + block ReLU + the next
+activation quantiser) into the producing kernel's epilogue, allocates the int8 tensors, and
+records the launches into one CUDA graph.  Intermediates never exist as int32 / float32 in HBM.
+
+A tensor in the plan = "value V of the reference graph as seen through QuantAct A": the int8
+codes A would produce from V, masked or not.  Distinct (V, A-range, mask) keys are materialised
+separately by re-running the producer with another epilogue, so arbitrary (even inconsistent)
+calibration ranges stay exact; in a normally calibrated model all consumers of a block output
+share one range and every producer runs once.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+
+F32, F64 = np.float32, np.float64
+
+
+# ------------------------------------------------------------------------------------------
+# host-side parameter math (once per plan; float32 / float64 steps as the reference does them)
+# ------------------------------------------------------------------------------------------
+def act_scale(bit, x_min, x_max):
+    """symmetric_linear_quantization_params on the fixed range (quant_utils.py:47-52)."""
+    n = 2 ** (bit - 1) - 1
+    r = max(abs(F32(x_min)), abs(F32(x_max)))
+    return F32(max(r, F32(1e-8)) / F32(n))
+
+
+def dyadic_np(pre_sf, z_sf):
+    """(m, e) of quant_utils.py:188-193 + batch_frexp :121-147, m normalised to [2^30, 2^31)."""
+    ratio = np.asarray(pre_sf, F32).astype(F64) / F64(F32(z_sf))
+    mant, ex = np.frexp(ratio)
+    m = np.floor(mant * 2147483648.0 + 0.5).astype(np.int64)
+    e = (31 - ex).astype(np.int64)
+    big = m >= 2 ** 31
+    m = np.where(big, m // 2, m)
+    e = np.where(big, e - 1, e)
+    return m, e
+
+
+def _tz(v):
+    v = int(v)
+    return (v & -v).bit_length() - 1 if v else 64
+
+
+def fast_ok(bound, m, e):
+    """May the all-integer epilogue ((z*m + 2^(e-1)) >> e with z = acc) replace the literal
+    float recipe for |z| <= bound?  Needs: f32 round trip of the accumulator is the identity
+    (bound < 2^22), the product stays exact in double (z*m < 2^53), the result fits int32, and no
+    z in range lands on an exact .5 tie (where half-to-even and half-up differ)."""
+    if bound >= 2 ** 22:
+        return False
+    for mi, ei in zip(np.atleast_1d(m).tolist(), np.atleast_1d(e).tolist()):
+        if mi == 0:
+            continue
+        if ei < 1 or ei > 62:
+            return False
+        if bound * mi >= 2 ** 53 or (bound * mi) >> ei >= 2 ** 30:
+            return False
+        t = ei - 1 - _tz(mi)          # z must be a multiple of 2^t for an exact tie
+        if t < 0 or (1 << t) <= bound:
+            return False
+    return True
+
+
+class ActInfo:
+    """Static view of one QuantAct."""
+
+    def __init__(self, act, masked):
+        if act.per_channel or act.dynamic or act.running_stat:
+            raise ValueError("fused plan needs fixed, static, per-tensor QuantAct modules")
+        self.bit = int(act.activation_bit)
+        self.x_min = float(act.x_min.reshape(-1)[0])
+        self.x_max = float(act.x_max.reshape(-1)[0])
+        self.scale = act_scale(self.bit, self.x_min, self.x_max)
+        self.n = 2 ** (self.bit - 1) - 1
+        self.masked = masked
+        self.module = act
+
+    def key(self):
+        return (self.bit, self.scale.tobytes(), self.masked)
+
+
+# ------------------------------------------------------------------------------------------
+# symbolic values of the reference graph
+# ------------------------------------------------------------------------------------------
+class Val:
+    relu = False
+
+
+class InputVal(Val):
+    def __init__(self, C, T):
+        self.C, self.T, self.stage = C, T, 0
+
+
+class ConvVal(Val):
+    """Output of a QuantConv1d applied to the quantised tensor `src` (a QTensor)."""
+
+    def __init__(self, conv, src, T, stage):
+        self.conv, self.src, self.T, self.stage = conv, src, T, stage
+        self.C = conv.out_channels
+
+
+class ResActVal(Val):
+    """res_act(main, branch) (jasper.py:681): main is a ConvVal or a previous ResActVal."""
+
+    def __init__(self, act, main, branch):
+        self.act, self.main, self.branch = act, main, branch
+        self.C, self.T, self.stage = main.C, main.T, main.stage
+
+
+class ReluOf(Val):
+    """ReLU applied to the float value `base` (jasper.py:661 / :687)."""
+
+    def __init__(self, base):
+        self.base = base
+        self.C, self.T, self.stage = base.C, base.T, base.stage
+
+
+class QTensor:
+    """A materialised int8 tensor: value `val` quantised by `info` (None: plain res_act codes)."""
+
+    def __init__(self, val, info, tensor, signed, scale, qabs):
+        self.val, self.info, self.tensor, self.signed, self.scale, self.qabs = val, info, tensor, signed, scale, qabs
+
+
+class ConvParams:
+    """Integer parameters of one QuantConv1d for a given input scale."""
+
+    def __init__(self, conv, s_x, in_qabs):
+        p = conv._prepare()
+        self.conv = conv
+        self.depthwise = p["depthwise"]
+        self.s_w = p["s_w"].detach().float().cpu().numpy().astype(F32)
+        self.s_out = (self.s_w * F32(s_x)).astype(F32)                       # quant_modules.py:293
+        w_abs = p["w_int"].detach().abs().reshape(conv.out_channels, -1).sum(dim=1).cpu().numpy().astype(np.int64)
+        if p["bias"] is not None:
+            b = p["bias"].detach().float().cpu().numpy().astype(F32)
+            inv = (F32(1.0) / self.s_out).astype(F32)
+            n = 2 ** 31 - 1
+            bi = np.clip(np.round((inv * b).astype(F32)), F32(-n), F32(n - 1))  # float32, :296-297
+            self.b_int = bi.astype(F64).astype(np.int64)
+        else:
+            self.b_int = np.zeros(conv.out_channels, np.int64)
+        self.bound = int((w_abs * in_qabs + np.abs(self.b_int)).max())
+        self.bias64 = self.bound >= 2 ** 31 - 1
+        self.w8, self.packed = p["w8"], p["packed"]
+        self.k, self.stride = conv.kernel_size[0], conv.stride[0]
+        self.dil, self.pad = conv.dilation[0], conv.padding[0]
+
+    def b_i32(self):
+        return np.clip(self.b_int, -2 ** 31, 2 ** 31 - 1)  # 2^31 -> INT32_MAX sentinel (BIAS64 path)
+
+
+class FusedPlan:
+    def __init__(self, encoder, decoder, in_shape, device, use_graph=True, verbose=False):
+        self.device = torch.device(device)
+        self.B, self.C_in, self.T = int(in_shape[0]), int(in_shape[1]), int(in_shape[2])
+        self.encoder, self.decoder = encoder, decoder
+        self.ops = []           # list of (name, callable)
+        self.op_bytes = []      # algorithmic HBM bytes per op (int8 in + int8/f32 out)
+        self.op_macs = []       # multiply-accumulates per op
+        self.stats = dict(kernels=0, fast=0, exact=0, rerun=0)
+        self._q = {}            # materialised QTensors
+        self._keep = []
+        self.verbose = verbose
+        B = self.B
+        self.x_in = torch.zeros((B, self.C_in, self.T), dtype=torch.float32, device=self.device)
+        self.lens = [torch.zeros(B, dtype=torch.int32, device=self.device)]   # per length stage
+        self._lens_fns = []
+        self._build()
+        self.graph = None
+        self.use_graph = use_graph
+        self._warm = False
+
+    # -- symbolic walk (conv_asr.py:194-206, jasper.py:641-692) ----------------------------
+    def _build(self):
+        from nemo.collections.asr.parts.jasper import MaskedConv1d
+        xs = [InputVal(self.C_in, self.T)]
+        stage, T = 0, self.T
+        for block in self.encoder.encoder_layers:
+            out = xs[-1]
+            stage_in, T_in = stage, T
+            for l in block.mconv:
+                if isinstance(l, MaskedConv1d):
+                    src = self._quantized(out, ActInfo(l.act, True), first_layer=isinstance(out, InputVal))
+                    k, s, d, p = l.conv.kernel_size[0], l.conv.stride[0], l.conv.dilation[0], l.conv.padding[0]
+                    T_new = (T + 2 * p - d * (k - 1) - 1) // s + 1
+                    if s != 1 or T_new != T:
+                        stage = self._new_len_stage(stage, k, s, d, p)
+                    T = T_new
+                    out = ConvVal(l.conv, src, T, stage)
+                elif isinstance(l, nn.ReLU):
+                    out = ReluOf(out)
+                elif isinstance(l, nn.Dropout):
+                    pass
+                else:
+                    raise NotImplementedError("layer %r in a fused plan (call bn_folding() first)" % (l,))
+            if block.res is not None:
+                for i, branch in enumerate(block.res):
+                    assert len(branch) == 1 and isinstance(branch[0], MaskedConv1d), "bn_folding() first"
+                    rc = branch[0]
+                    rsrc = self._quantized(xs[i], ActInfo(rc.act, True))
+                    if rc.conv.stride[0] != 1 or rc.conv.kernel_size[0] != 1:
+                        raise NotImplementedError("strided residual branch")
+                    if xs[i].T != T:
+                        raise NotImplementedError("residual across a strided block")
+                    out = ResActVal(block.res_act, out, ConvVal(rc.conv, rsrc, T, stage))
+            mout = list(block.mout)
+            if not isinstance(mout[0], nn.ReLU):
+                raise NotImplementedError("block activation %r" % (mout[0],))
+            out = ReluOf(out)
+            xs = xs + [out] if (block.res is not None and block.dense_residual) else [out]
+        self.enc_val, self.enc_T, self.enc_stage = xs[-1], T, stage
+        self.logits = self.encoded = None
+        if self.decoder is None:
+            # encoder-only plan: the API returns the float tensor relu(f32(acc) * s_out) and its scale
+            base, _ = self._strip(xs[-1])
+            if not isinstance(base, ConvVal):
+                raise NotImplementedError("encoder ending in a residual block")
+            self._emit_dequant(xs[-1], "encoded")
+        else:
+            dconv = self.decoder.decoder_layers[0]
+            src = self._quantized(xs[-1], ActInfo(self.decoder.act, False))
+            self._emit_dequant(ConvVal(dconv, src, T, stage), "logits")
+
+    def _new_len_stage(self, stage, k, s, d, p):
+        prev = self.lens[stage]
+        self.lens.append(torch.zeros_like(prev))
+        idx = len(self.lens) - 1
+
+        def fn(prev=prev, out=self.lens[idx]):
+            out.copy_(torch.div(prev + (2 * p - d * (k - 1) - 1), s, rounding_mode="floor") + 1)
+        self._lens_fns.append(fn)
+        return idx
+
+    # -- materialisation -------------------------------------------------------------------
+    def _alloc(self, C, T):
+        return ops.alloc_codes(self.B, C, T, self.device)
+
+    def _quantized(self, val, info, first_layer=False):
+        key = (id(val), info.key())
+        qt = self._q.get(key)
+        if qt is not None:
+            return qt
+        if any(k[0] == id(val) for k in self._q):
+            self.stats["rerun"] += 1
+        self._keep.append(val)
+        if isinstance(val, InputVal):
+            qt = self._emit_input(val, info)
+        else:
+            qt = self._emit_requant(val, info)
+        self._q[key] = qt
+        return qt
+
+    def _emit_input(self, val, info):
+        """First layer: SymmetricQuantFunction on the float input (quant_modules.py:180-184)."""
+        if info.bit > 8:
+            raise NotImplementedError("first-layer activation_bit > 8")
+        out = self._alloc(val.C, val.T)
+        scale = torch.tensor([info.scale], dtype=torch.float32, device=self.device)
+        lens = self.lens[0] if info.masked else None
+        x_in, B, C, T, bit = self.x_in, self.B, val.C, val.T, info.bit
+        lib = L.lib()
+
+        def run():
+            L.check(lib.qasr_quantize_f32(L.ptr(x_in), T, L.ptr(scale), bit, L.ptr(out), out.shape[-1], None,
+                                          B, C, T, L.ptr(lens), L.stream_ptr()))
+        self._add("quantize_input", run, nbytes=B * C * T * 5)
+        return QTensor(val, info, out, True, info.scale, info.n)
+
+    def _strip(self, val):
+        relu = False
+        while isinstance(val, ReluOf):
+            relu, val = True, val.base
+        return val, relu
+
+    def _emit_requant(self, val, info):
+        """Run the producer of `val` with an epilogue that ends in QuantAct `info`."""
+        base, relu = self._strip(val)
+        signed = not relu and True
+        qmin, qmax = -info.n - 1, info.n
+        if relu:
+            signed = False
+            if info.n > 255:
+                raise NotImplementedError("activation_bit > 9")
+        elif info.n > 127:
+            raise NotImplementedError("signed activation codes wider than 8 bits")
+        out = self._alloc(base.C, base.T)
+        lens = self.lens[base.stage] if info.masked else None
+        flags = L.F_MASK if info.masked else 0
+        if isinstance(base, ConvVal):
+            cp = ConvParams(base.conv, base.src.scale, base.src.qabs)
+            m, e = dyadic_np(cp.s_out, info.scale)
+            if relu:
+                flags |= L.F_RELU0
+            fast = fast_ok(cp.bound, m, e)
+            self._emit_conv([(base, cp, m, e)], out, flags, fast, dict(qmin=qmin, qmax=qmax), lens,
+                            "conv->act")
+        elif isinstance(base, ResActVal):
+            ra = ActInfo(base.act, False)
+            if ra.n > 127:
+                raise NotImplementedError("res_act wider than 8 bits")
+            m2, e2 = dyadic_np(np.array([ra.scale], F32), info.scale)
+            stage2 = dict(m2=int(m2[0]), e2=int(e2[0]), qmin2=qmin, qmax2=qmax)
+            if relu:
+                flags |= L.F_RELU1
+            flags |= L.F_STAGE2
+            fast2 = fast_ok(ra.n + 1, m2, e2)
+            self._emit_resact(base, ra, out, flags, fast2, stage2, lens)
+        else:
+            raise NotImplementedError(type(base))
+        return QTensor(val, info, out, signed, info.scale, max(abs(qmin), abs(qmax)) if signed else qmax)
+
+    def _plain_resact(self, val):
+        """res_act codes before the block ReLU (input of the next res_act in a dense-residual chain)."""
+        key = (id(val), "plain")
+        qt = self._q.get(key)
+        if qt is None:
+            ra = ActInfo(val.act, False)
+            out = self._alloc(val.C, val.T)
+            self._emit_resact(val, ra, out, 0, True, {}, None)
+            qt = QTensor(val, None, out, True, ra.scale, ra.n + 1)
+            self._q[key] = qt
+            self._keep.append(val)
+        return qt
+
+    def _emit_resact(self, val, ra, out, flags, fast_extra, stage2, lens):
+        main, m_relu = self._strip(val.main)
+        branch, b_relu = self._strip(val.branch)
+        assert not m_relu and not b_relu and isinstance(branch, ConvVal)
+        cpb = ConvParams(branch.conv, branch.src.scale, branch.src.qabs)
+        mb, eb = dyadic_np(cpb.s_out, ra.scale)
+        kw = dict(qmin=-ra.n - 1, qmax=ra.n, **stage2)
+        if isinstance(main, ConvVal):
+            cpm = ConvParams(main.conv, main.src.scale, main.src.qabs)
+            mm, em = dyadic_np(cpm.s_out, ra.scale)
+            fast = fast_extra and fast_ok(cpm.bound, mm, em) and fast_ok(cpb.bound, mb, eb)
+            self._emit_conv([(main, cpm, mm, em), (branch, cpb, mb, eb)], out, flags, fast, kw, lens, "res_act")
+        else:  # chain: previous res_act result (same scale, ratio exactly 1) + this branch
+            assert isinstance(main, ResActVal) and main.act is val.act
+            prev = self._plain_resact(main)
+            fast = fast_extra and fast_ok(cpb.bound, mb, eb)
+            self._emit_conv([(branch, cpb, mb, eb)], out, flags, fast, dict(prev=prev.tensor, **kw), lens,
+                            "res_act_chain")
+
+    def _chan_table(self, cp, m, e):
+        return ops.chan_table(cp.s_out, cp.b_i32(), m, e, self.device)
+
+    def _emit_conv(self, operands, out, flags, fast, epi_kw, lens, name):
+        """One kernel: conv operand 0 (+ operand 1) -> epilogue -> int8 tensor `out`."""
+        tabs = [self._chan_table(cp, m, e) for (_, cp, m, e) in operands]
+        v0, cp0 = operands[0][0], operands[0][1]
+        if not v0.src.signed:
+            pass
+        else:
+            flags |= L.F_B_SIGNED
+        if len(operands) > 1 and operands[1][0].src.signed:
+            flags |= L.F_B1_SIGNED
+        if not fast:
+            flags |= L.F_EXACT_F32 | L.F_EXACT_DYAD
+            if any(cp.bias64 for (_, cp, _, _) in operands):
+                flags |= L.F_BIAS64
+        self.stats["fast" if fast else "exact"] += 1
+        ep = ops.make_epilogue(L.EPI_REQUANT_I8, tabs[0], flags=flags, ch1=tabs[1] if len(tabs) > 1 else None,
+                               out_lens=lens, **epi_kw)
+        self._launch_conv(operands, out, ep, name)
+
+    def _emit_dequant(self, val, name):
+        """float32 output y = f32(acc + b_int) * s_out (decoder logits / encoder API output)."""
+        base, relu = self._strip(val)
+        cp = ConvParams(base.conv, base.src.scale, base.src.qabs)
+        C = base.conv.out_channels
+        one = np.full(C, 2 ** 30, np.int64)
+        tab = ops.chan_table(cp.s_out, cp.b_i32(), one, np.full(C, 30, np.int64), self.device)
+        flags = (L.F_RELU0 if relu else 0) | (L.F_BIAS64 if cp.bias64 else 0) | (L.F_B_SIGNED if base.src.signed else 0)
+        ep = ops.make_epilogue(L.EPI_DEQUANT_F32, tab, flags=flags)
+        out = torch.zeros((self.B, C, ops.round_up(base.T, 16)), dtype=torch.float32, device=self.device)
+        self._launch_conv([(base, cp, None, None)], out, ep, name)
+        sf = torch.from_numpy(cp.s_out.copy()).to(self.device).view(1, -1, 1)
+        setattr(self, name, out)
+        setattr(self, name + "_scale", sf)
+        setattr(self, name + "_T", base.T)
+        return out
+
+    def _launch_conv(self, operands, out, ep, name):
+        v0, cp0 = operands[0][0], operands[0][1]
+        B, lib = self.B, L.lib()
+        C_out, T_out = v0.conv.out_channels, v0.T
+        if cp0.depthwise:
+            assert len(operands) == 1
+            x, T_in = v0.src.tensor, v0.src.val.T
+            w8, k, s, d, p = cp0.w8, cp0.k, cp0.stride, cp0.dil, cp0.pad
+            import ctypes as C
+
+            def run():
+                L.check(lib.qasr_dwconv1d_i8(L.ptr(x), x.shape[-1], L.ptr(w8), L.ptr(out), out.shape[-1], B,
+                                             C_out, T_in, T_out, k, s, d, p, C.byref(ep), L.stream_ptr()))
+            self._add("dw_k%d_%s" % (k, name), run, keep=(ep, w8),
+                      nbytes=B * C_out * (T_in + T_out * out.element_size()), macs=B * C_out * T_out * k)
+        else:
+            gops = []
+            for (v, cp, _, _) in operands:
+                gops.append(ops.gemm_operand(v.src.tensor, v.src.val.T, cp.packed, v.conv.in_channels, cp.k,
+                                             cp.stride, cp.dil, cp.pad))
+            import ctypes as C
+            op1 = C.byref(gops[1]) if len(gops) > 1 else None
+
+            def run():
+                L.check(lib.qasr_conv1d_gemm_i8(C.byref(gops[0]), op1, L.ptr(out), out.shape[-1], B, C_out,
+                                                T_out, C.byref(ep), L.stream_ptr()))
+            nbytes = B * C_out * T_out * out.element_size() + (B * C_out * T_out if ep.prev else 0)
+            macs = 0
+            for (v, cp, _, _) in operands:
+                nbytes += B * v.conv.in_channels * v.src.val.T
+                macs += B * T_out * C_out * v.conv.in_channels * cp.k
+            self._add("gemm_%dx%d_%s" % (v0.conv.in_channels, C_out, name), run, keep=(ep, gops), nbytes=nbytes,
+                      macs=macs)
+
+    def _add(self, name, fn, keep=None, nbytes=0, macs=0):
+        self.ops.append((name, fn))
+        self.op_bytes.append(int(nbytes))
+        self.op_macs.append(int(macs))
+        self._keep.append(keep)
+        self.stats["kernels"] += 1
+
+    # -- execution -------------------------------------------------------------------------
+    def _run_ops(self):
+        for fn in self._lens_fns:
+            fn()
+        for _, fn in self.ops:
+            fn()
+
+    def _replay(self):
+        if not self.use_graph:
+            self._run_ops()
+            return
+        if self.graph is None:
+            # eager warm-up on a side stream (sets kernel attributes, pages code in), then capture
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s):
+                self._run_ops()
+            torch.cuda.current_stream(self.device).wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_ops()
+            self.graph = g
+        self.graph.replay()
+
+    def load_inputs(self, x, lens):
+        if tuple(x.shape) != (self.B, self.C_in, self.T):
+            raise ValueError("plan compiled for input %s, got %s" % ((self.B, self.C_in, self.T), tuple(x.shape)))
+        self.x_in.copy_(x, non_blocking=True)
+        self.lens[0].copy_(lens.to(torch.int32), non_blocking=True)
+
+    def run(self, x=None, lens=None):
+        """Full model forward: returns the float32 logits view (B, V, T') (a static buffer)."""
+        if x is not None:
+            self.load_inputs(x, lens)
+        self._replay()
+        return self.logits[:, :, :self.logits_T] if self.logits is not None else None
+
+    def run_encoder(self, x, lens):
+        """ConvASREncoder.forward contract: (encoded float32 (B,C,T'), encoded_len, scale (1,C,1))."""
+        self.load_inputs(x, lens)
+        self._replay()
+        enc = self.encoded[:, :, :self.encoded_T]
+        if self.encoded.shape[-1] != self.encoded_T:
+            enc = enc.contiguous()
+        else:
+            enc = enc.clone()
+        return enc, self.out_lens().to(torch.long), self.encoded_scale
+
+    def greedy(self):
+        return ops.ctc_argmax(self.logits, self.logits_T)
+
+    def log_probs(self):
+        return ops.log_softmax_tv(self.logits, self.logits_T)
+
+    def out_lens(self):
+        return self.lens[self.enc_stage]
+
+    def codes_of(self, val_key):
+        return self._q[val_key]
+
+
+def _signature(encoder, decoder):
+    from nemo.quantization.utils.quant_modules import QuantAct, QuantConv1d
+    sig = []
+    mods = list(encoder.modules()) + (list(decoder.modules()) if decoder is not None else [])
+    for m in mods:
+        if type(m) is QuantAct:
+            sig.append((m.activation_bit, id(m.x_min), m.x_min._version, id(m.x_max), m.x_max._version))
+        elif type(m) is QuantConv1d:
+            sig.append((m.weight_bit, m.weight._version, id(m.bn), m.quant_mode))
+    return tuple(sig)
+
+
+def get_plan(encoder, decoder, in_shape, device, cache, **kw):
+    key = (tuple(in_shape), str(device), id(decoder))
+    sig = _signature(encoder, decoder)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    plan = FusedPlan(encoder, decoder, in_shape, device, **kw)
+    cache[key] = (sig, plan)
+    return plan

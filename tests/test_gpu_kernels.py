@@ -109,6 +109,10 @@ def test_gemm_raw_i32(case):
     ch = ops.chan_table(np.ones(co, np.float32), bias, np.full(co, 2 ** 30), np.full(co, 30), DEV)
     ep = ops.make_epilogue(L.EPI_RAW_I32, ch, flags=L.F_B_SIGNED if signed else 0)
     out = torch.full((B, co, ops.round_up(T_out, 16)), -777, dtype=torch.int32, device=DEV)
+    if k > 1:  # (B,C,T) layout: TMA cannot fetch unaligned time shifts -> loud refusal, not a fault
+        with pytest.raises(NotImplementedError):
+            ops.conv_gemm(ops.gemm_operand(x, T, wp, ci, k, 1, dil, pad), None, out, B, co, T_out, ep)
+        return
     ops.conv_gemm(ops.gemm_operand(x, T, wp, ci, k, 1, dil, pad), None, out, B, co, T_out, ep)
     torch.cuda.synchronize()
     got = out[:, :, :T_out].cpu().numpy().astype(np.int64)
@@ -116,7 +120,7 @@ def test_gemm_raw_i32(case):
 
 
 @pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
-@pytest.mark.parametrize("case", GEMM_CASES[:5] + GEMM_CASES[5:6], ids=lambda c: c[0])
+@pytest.mark.parametrize("case", GEMM_CASES[:5], ids=lambda c: c[0])
 def test_gemm_requant(case, fast):
     name, B, ci, co, T, k, dil, signed = case
     q, w, bias, pad = _gemm_inputs(case, seed=1)
@@ -184,7 +188,7 @@ def test_gemm_dual_residual(fast):
 
 def test_gemm_dequant_f32_bigacc():
     """|acc| >= 2^24: the f32 round trip of quant_modules.py:305 rounds; dequant output bit-exact."""
-    B, ci, co, T, k = 1, 768, 128, 60, 9
+    B, ci, co, T, k = 1, 7680, 128, 60, 1
     r = rng(4)
     q = r.integers(200, 256, (B, ci, T))
     w = r.integers(90, 127, (co, ci, k))

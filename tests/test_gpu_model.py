@@ -1,0 +1,306 @@
+"""GPU: the drop-in module API and the fused int8 plan against (a) the golden vectors produced by
+the unmodified reference and (b) the oracle on freshly generated QuartzNet15x5 parameters.
+Integer codes bit-exact; dequantised logits within 1e-5 * max|logit| (pure-integer path, see
+SURVEY.md 3.5); log-probs within 1e-5 * max|log-prob|."""
+import copy
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import qasr_oracle as O
+import specio
+from spec_from_modules import spec_from_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NET_CASES = sorted(glob.glob(os.path.join(GOLDEN, "net_*.npz")))
+
+
+def _imports():
+    from nemo.collections.asr.models.ctc_models import EncDecCTCModel
+    import nemo.quantization.utils.quantize_model as qm
+    from nemo.quantization.utils import quant_modules as Q
+    from qasr import topology
+    return EncDecCTCModel, qm, Q, topology
+
+
+def build_from_case(case):
+    EncDecCTCModel, qm, Q, topology = _imports()
+    model = EncDecCTCModel(topology.TOPOLOGIES[case["topology"]](**case["topology_kwargs"]))
+    model.eval()
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in case["state_dict"].items()}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.endswith("conv.conv.weight") or "num_batches" in k for k in missing), missing
+    model.set_quant_bit(case["weight_bit"], "weight")
+    model.set_quant_bit(case["act_bit"], "act")
+    if case["percentile"] is not None:
+        qm.set_percentile(model, case["percentile"])
+    if case["momentum"] is not None:
+        for m in model.modules():
+            if type(m) is Q.QuantAct:
+                m.act_range_momentum = case["momentum"]
+    model.encoder.bn_folding()
+    return model.to(DEV), qm
+
+
+def module_acts(model):
+    from nemo.collections.asr.parts.jasper import MaskedConv1d
+    for b in model.encoder.encoder_layers:
+        for m in b.mconv:
+            if isinstance(m, MaskedConv1d):
+                yield m.act
+        if b.res is not None:
+            for layer in b.res:
+                yield layer[0].act
+        yield b.res_act
+    yield model.decoder.act
+
+
+def set_ranges_from_spec(model, spec):
+    for a, m in zip(O.iter_acts(spec), module_acts(model)):
+        m.x_min = torch.full_like(m.x_min, float(a.x_min))
+        m.x_max = torch.full_like(m.x_max, float(a.x_max))
+
+
+def logit_codes(logits, scale):
+    return torch.round(logits.double() / scale.double().view(1, -1, 1)).to(torch.int64).cpu().numpy()
+
+
+def check_outputs(case_out, logits, logit_scale, log_probs, greedy, enc_lens):
+    assert np.array_equal(enc_lens.cpu().numpy(), case_out["enc_lens"])
+    assert np.array_equal(logit_scale.reshape(-1).cpu().numpy(), case_out["logit_scale"])
+    assert np.array_equal(logit_codes(logits, logit_scale.reshape(-1)), case_out["logit_codes"])
+    lg = logits.cpu().numpy()
+    assert np.abs(lg - case_out["logits"]).max() <= 1e-5 * np.abs(case_out["logits"]).max()
+    lp = log_probs.cpu().numpy()
+    assert np.abs(lp - case_out["log_probs"]).max() <= 1e-5 * np.abs(case_out["log_probs"]).max()
+    assert np.array_equal(greedy.cpu().numpy(), case_out["greedy"])
+
+
+def needs_dense_kernel(case):
+    return "jasper" in case["topology"]
+
+
+@pytest.mark.parametrize("path", NET_CASES, ids=lambda p: os.path.basename(p)[:-4])
+def test_golden_network_module_level(path):
+    case = specio.load(path)
+    if needs_dense_kernel(case):
+        pytest.xfail("dense k>1 convolutions need the channels-last implicit-GEMM kernel (next)")
+    model, qm = build_from_case(case)
+    model.use_fused_plan = model.encoder.use_fused_plan = False
+    x = torch.from_numpy(case["x"]).to(DEV)
+    lens = torch.from_numpy(case["lens"]).to(DEV)
+    if case["mode"] == "static":
+        qm.calibrate(model)
+        for c in case["calib"]:
+            e, l, s = model.encoder(torch.from_numpy(c["x"]).to(DEV), torch.from_numpy(c["lens"]).to(DEV))
+            model.decoder(e, s)
+        # ranges calibrated on the GPU (noise-free integer recipe) vs the reference's (float noise)
+        for a, m in zip(O.iter_acts(case["spec"]), module_acts(model)):
+            for got, want in ((float(m.x_min), float(a.x_min)), (float(m.x_max), float(a.x_max))):
+                assert abs(got - want) <= 1e-5 * max(abs(want), 1e-3)
+        set_ranges_from_spec(model, case["spec"])  # identical calibrated state for the exact comparison
+    qm.evaluate(model)
+    qm.set_dynamic(model, case["mode"] == "dynamic")
+    log_probs, enc_len, greedy = model(processed_signal=x, processed_signal_length=lens)
+    sf = model.decoder.decoder_layers[0].conv_scaling_factor * model.decoder.act.act_scaling_factor
+    check_outputs(case["out"], model.decoder.last_logits, sf, log_probs, greedy, enc_len)
+
+
+@pytest.mark.parametrize("path", [p for p in NET_CASES if "static" in p or "mom" in p],
+                         ids=lambda p: os.path.basename(p)[:-4])
+def test_golden_network_fused_plan(path):
+    case = specio.load(path)
+    if needs_dense_kernel(case):
+        pytest.xfail("dense k>1 convolutions need the channels-last implicit-GEMM kernel (next)")
+    model, qm = build_from_case(case)
+    set_ranges_from_spec(model, case["spec"])
+    qm.evaluate(model)
+    qm.set_dynamic(model, False)
+    x = torch.from_numpy(case["x"]).to(DEV)
+    lens = torch.from_numpy(case["lens"]).to(DEV)
+    for use_graph in (False, True):
+        model._plan_cache = {}
+        from qasr import plan as P
+        plan = P.FusedPlan(model.encoder, model.decoder, x.shape, x.device, use_graph=use_graph)
+        logits = plan.run(x, lens)
+        if use_graph:  # replay twice: static buffers, no stale state
+            logits = plan.run(x, lens)
+        check_outputs(case["out"], logits, plan.logits_scale.reshape(-1), plan.log_probs(), plan.greedy(),
+                      plan.out_lens())
+        # every intermediate int8 tensor against the reference trace
+        checked = 0
+        names = {id(m): n for n, m in model.named_modules()}
+        for (vid, key), qt in plan._q.items():
+            if qt.info is None:
+                continue
+            n = names[id(qt.info.module)].replace("encoder.encoder.", "encoder.")
+            ref = case["trace"][n][0]["codes"]
+            T = ref.shape[2]
+            got = qt.tensor[:, :, :T].cpu().numpy()
+            got = got.astype(np.int64) if qt.signed else got.view(np.uint8).astype(np.int64)
+            assert np.array_equal(got, ref), n
+            checked += 1
+        assert checked > 8
+    # public API path (EncDecCTCModel.forward picks the plan up by itself)
+    log_probs, enc_len, greedy = model(processed_signal=x, processed_signal_length=lens)
+    assert np.array_equal(greedy.cpu().numpy(), case["out"]["greedy"])
+    enc, enc_len, enc_sf = model.encoder(audio_signal=x, length=lens)
+    want = np.round(case["out"]["encoded"] / case["out"]["encoded_scale"].reshape(1, -1, 1))
+    assert np.array_equal(torch.round(enc / enc_sf).cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("case", specio.load(os.path.join(GOLDEN, "ops_act.npz")), ids=lambda c: c["tag"])
+def test_golden_quant_act(case):
+    _, _, Q, _ = _imports()
+    act = Q.QuantAct(case["bit"], quant_mode="symmetric", act_range_momentum=case["momentum"],
+                     dynamic=case["dynamic"], percentile=case["percentile"]).to(DEV)
+    act.running_stat = case["running_stat"]
+    act.x_min = torch.tensor([case["x_min0"]], device=DEV)
+    act.x_max = torch.tensor([case["x_max0"]], device=DEV)
+    for call in case["calls"]:
+        d = lambda a: None if a is None else torch.from_numpy(a).to(DEV)  # noqa: E731
+        pre = None if call["pre_sf"] is None else d(call["pre_sf"]).view(1, -1, 1)
+        isf = None if call["identity_sf"] is None else d(call["identity_sf"]).view(1, -1, 1)
+        out, sf = act(d(call["x"]), pre, d(call["identity"]), isf)
+        assert np.float32(sf.reshape(-1)[0].item()) == call["scale"].reshape(())
+        assert np.array_equal(out.cpu().numpy(), call["out"])
+        assert np.float32(act.x_min.item()) == np.float32(call["x_min"])
+        assert np.float32(act.x_max.item()) == np.float32(call["x_max"])
+
+
+@pytest.mark.parametrize("case", specio.load(os.path.join(GOLDEN, "ops_conv.npz")), ids=lambda c: c["tag"])
+def test_golden_quant_conv(case):
+    _, _, Q, _ = _imports()
+    w = torch.from_numpy(case["weight"])
+    co, cig, k = w.shape
+    conv = torch.nn.Conv1d(cig * case["groups"], co, k, stride=case["stride"], padding=case["pad"],
+                           dilation=case["dil"], groups=case["groups"], bias=case["bias"] is not None)
+    conv.weight.data.copy_(w)
+    if case["bias"] is not None:
+        conv.bias.data.copy_(torch.from_numpy(case["bias"]))
+    qc = Q.QuantConv1d(case["weight_bit"], bias_bit=32, quant_mode="symmetric", per_channel=True)
+    qc.set_param(conv)
+    if case["bn"] is not None:
+        bn = torch.nn.BatchNorm1d(co, eps=case["bn"]["eps"])
+        bn.weight.data.copy_(torch.from_numpy(case["bn"]["weight"]))
+        bn.bias.data.copy_(torch.from_numpy(case["bn"]["bias"]))
+        bn.running_mean.copy_(torch.from_numpy(case["bn"]["mean"]))
+        bn.running_var.copy_(torch.from_numpy(case["bn"]["var"]))
+        bn.eval()
+        qc.bn_folding(bn)
+    qc = qc.to(DEV)
+    s_x = torch.from_numpy(case["s_x"]).to(DEV)
+    x = torch.from_numpy(case["in_codes"]).float().to(DEV) * s_x
+    dense = case["groups"] == 1 and (k > 1 or case["stride"] > 1)
+    if dense:
+        with pytest.raises(NotImplementedError):
+            qc(x, s_x)
+        pytest.xfail("dense k>1 convolutions need the channels-last implicit-GEMM kernel (next)")
+    out, sf = qc(x, s_x)
+    assert np.array_equal(qc.weight_integer.cpu().numpy().astype(np.int32), case["weight_integer"])
+    assert np.array_equal(qc.conv_scaling_factor.cpu().numpy(), case["conv_scaling_factor"])
+    assert np.array_equal(sf.reshape(-1).cpu().numpy(), case["out_scale"])
+    got_acc = torch.round(out.double() / sf.double()).cpu().numpy()
+    assert np.array_equal(got_acc.astype(np.float32), case["acc"].astype(np.float32))
+    assert np.abs(out.cpu().numpy() - case["out"]).max() <= 1e-6 * np.abs(case["out"]).max()
+
+
+# ------------------------------------------------------------------------------------------
+# full-size QuartzNet15x5 against the oracle (parameters generated here, identical inputs)
+# ------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def quartznet():
+    EncDecCTCModel, qm, Q, topology = _imports()
+    from qasr.params import reestimate_bn_, synthetic_features
+    torch.manual_seed(0)
+    model = EncDecCTCModel.from_topology("quartznet15x5")
+    model.eval()
+    reestimate_bn_(model.encoder)
+    model.encoder.bn_folding()
+    return model.to(DEV), qm, synthetic_features
+
+
+@pytest.mark.parametrize("wbit,abit,percentile", [(8, 8, None), (6, 6, 99.996)], ids=["w8a8", "w6a6_pct"])
+def test_quartznet15x5_static_vs_oracle(quartznet, wbit, abit, percentile):
+    model, qm, synthetic_features = quartznet
+    for m in module_acts(model):
+        m.x_min, m.x_max = torch.zeros_like(m.x_min), torch.zeros_like(m.x_max)
+    model.set_quant_bit(wbit, "weight")
+    model.set_quant_bit(abit, "act")
+    qm.set_percentile(model, percentile)
+    spec = spec_from_model(model.encoder, model.decoder)
+    B, T = 2, 200
+    model.use_fused_plan = model.encoder.use_fused_plan = False
+    qm.calibrate(model)
+    O.set_mode(spec, True)
+    for i in range(2):
+        cx, cl = synthetic_features(B, T, seed=100 + i, ragged=(i % 2 == 1))
+        e, l, s = model.encoder(cx.to(DEV), cl.to(DEV))
+        model.decoder(e, s)
+        O.model_forward(spec, cx.numpy(), cl.numpy())
+    qm.evaluate(model)
+    O.set_mode(spec, False)
+    # calibration statistics: both sides run the noise-free integer recipe -> bit-equal ranges
+    for a, m in zip(O.iter_acts(spec), module_acts(model)):
+        assert np.float32(m.x_min.item()) == np.float32(a.x_min)
+        assert np.float32(m.x_max.item()) == np.float32(a.x_max)
+    x, lens = synthetic_features(B, T, seed=5, ragged=True)
+    trace = []
+    want = O.model_forward(spec, x.numpy(), lens.numpy(), trace)
+    assert (want["logit_codes"] != 0).mean() > 0.9
+    # module-level path
+    log_probs, enc_len, greedy = model(processed_signal=x.to(DEV), processed_signal_length=lens.to(DEV))
+    sf = model.decoder.decoder_layers[0].conv_scaling_factor * model.decoder.act.act_scaling_factor
+    assert np.array_equal(logit_codes(model.decoder.last_logits, sf), want["logit_codes"])
+    assert np.array_equal(greedy.cpu().numpy(), want["greedy"])
+    # fused plan
+    model.use_fused_plan = model.encoder.use_fused_plan = True
+    plan = model.plan_for(x.shape, torch.device(DEV))
+    logits = plan.run(x.to(DEV), lens.to(DEV))
+    assert np.array_equal(logit_codes(logits, plan.logits_scale.reshape(-1)), want["logit_codes"])
+    assert np.abs(logits.cpu().numpy() - want["logits"]).max() <= 1e-5 * np.abs(want["logits"]).max()
+    assert np.array_equal(plan.greedy().cpu().numpy(), want["greedy"])
+    assert np.array_equal(plan.out_lens().cpu().numpy(), want["lens"])
+    by_name = {r["name"]: r for r in trace}
+    names = {id(m): n for n, m in model.named_modules()}
+    checked = 0
+    for (vid, key), qt in plan._q.items():
+        if qt.info is None:
+            continue
+        n = names[id(qt.info.module)].replace("encoder.encoder.", "encoder.")
+        if n.endswith(".act") and n[:-4] in by_name:
+            ref = by_name[n[:-4]]["in_codes"]
+        elif n == "decoder.act":
+            ref = by_name["decoder"]["in_codes"]
+        else:
+            continue
+        got = qt.tensor[:, :, :ref.shape[2]].cpu().numpy()
+        got = got.astype(np.int64) if qt.signed else got.view(np.uint8).astype(np.int64)
+        assert np.array_equal(got, ref), n
+        checked += 1
+    assert checked >= 150
+    print("plan stats", plan.stats)
+
+
+def test_quartznet15x5_dynamic_vs_oracle(quartznet):
+    """cfg4's mode: W4A8, dynamic min/max ranges (module-level path; statistics kernels)."""
+    model, qm, synthetic_features = quartznet
+    model.set_quant_bit(4, "weight")
+    model.set_quant_bit(8, "act")
+    qm.set_percentile(model, None)
+    qm.evaluate(model)
+    qm.set_dynamic(model, True)
+    spec = spec_from_model(model.encoder, model.decoder)
+    x, lens = synthetic_features(2, 200, seed=7, ragged=True)
+    want = O.model_forward(spec, x.numpy(), lens.numpy())
+    log_probs, enc_len, greedy = model(processed_signal=x.to(DEV), processed_signal_length=lens.to(DEV))
+    sf = model.decoder.decoder_layers[0].conv_scaling_factor * model.decoder.act.act_scaling_factor
+    assert np.array_equal(logit_codes(model.decoder.last_logits, sf), want["logit_codes"])
+    assert np.array_equal(greedy.cpu().numpy(), want["greedy"])
+    qm.set_dynamic(model, False)
