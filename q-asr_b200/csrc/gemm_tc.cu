@@ -239,8 +239,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ===================== epilogue =====================
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;         // which 64 of the tile's 128 columns
-    const double mult2 = dyad_mult(g.ep.m2, g.ep.e2);
-    const long long half2 = (g.ep.e2 >= 1 && g.ep.e2 <= 62) ? (1ll << (g.ep.e2 - 1)) : 0;
+    const EpiConsts kc = make_epi_consts(g.ep, g.nseg > 1);
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
@@ -282,12 +281,19 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int j = 16 * v + 4 * w4 + i;
-                const int t = tbase + j;
-                const int prev = (int)(int8_t)((pw[w4] >> (8 * i)) & 0xff);
-                q[i] = epilogue_requant<FAST>(g.ep, acc0[j], c0, g.nseg > 1, g.nseg > 1 ? acc1[j] : 0, c1,
-                                              prev, mult2, half2, t < len);
+                const int prev = prow ? (int)(int8_t)((pw[w4] >> (8 * i)) & 0xff) : 0;
+                q[i] = epilogue_requant<FAST>(g.ep, kc, acc0[j], c0, g.nseg > 1, g.nseg > 1 ? acc1[j] : 0, c1,
+                                              prev, true);
               }
               packed[w4] = pack4(q[0], q[1], q[2], q[3]);
+            }
+            if (tv + 16 > len) {  // length mask / row tail: zero the bytes at t >= len
+#pragma unroll
+              for (int w4 = 0; w4 < 4; ++w4) {
+                const int nvalid = len - (tv + 4 * w4);
+                const uint32_t m = nvalid >= 4 ? 0xffffffffu : (nvalid <= 0 ? 0u : (0xffffffffu >> (8 * (4 - nvalid))));
+                packed[w4] &= m;
+              }
             }
             if (row_ok && tv < g.T_out)
               *reinterpret_cast<uint4*>(orow + tv) = make_uint4(packed[0], packed[1], packed[2], packed[3]);

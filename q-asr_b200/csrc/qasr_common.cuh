@@ -85,8 +85,9 @@ struct ChanRegs {
   float s;
   int bias;
   int m, e;
-  double mult;          // exact path
-  long long half;       // fast path: 2^(e-1)
+  double mult;          // exact path: m * 2^-e
+  int sh;               // fast path: e - 32 (host guarantees 32 <= e <= 62)
+  long long add;        // fast path: bias * m + 2^(e-1)
 };
 
 __device__ __forceinline__ ChanRegs load_chan(const qasr_chan* p, int c) {
@@ -97,77 +98,93 @@ __device__ __forceinline__ ChanRegs load_chan(const qasr_chan* p, int c) {
   r.m = v.z;
   r.e = v.w;
   r.mult = dyad_mult(r.m, r.e);
-  r.half = (r.e >= 1 && r.e <= 62) ? (1ll << (r.e - 1)) : 0ll;
+  r.sh = max(r.e - 32, 0);
+  r.add = (long long)r.bias * (long long)r.m + ((r.e >= 1 && r.e <= 62) ? (1ll << (r.e - 1)) : 0ll);
   return r;
 }
 
-// rne(z * m / 2^e) on the all-integer fast path (host guarantees 1 <= e <= 62, no exact tie,
-// |z * m| < 2^53 and a result that fits int32).
-__device__ __forceinline__ int dyad_fast(int z, int m, int e, long long half) {
-  const long long p = (long long)z * (long long)m + half;
-  return (int)(p >> e);
+// All-integer fast path of one conv operand: rne((acc + bias) * m / 2^e) as
+// ((acc * m + (bias * m + 2^(e-1))) >> 32) >> (e - 32): one IMAD.WIDE + one shift.  Valid when the host
+// proved (qasr/plan.py fast_ok): |acc + bias| < 2^22 (the float32 round trip of quant_modules.py:305 /
+// quant_utils.py:187 is the identity and the product is exact in double), 32 <= e <= 62, no in-range
+// value lands on an exact .5 tie (half-up == half-to-even), result fits int32.
+__device__ __forceinline__ int contrib_fast(int acc, const ChanRegs& c) {
+  const long long p = (long long)acc * (long long)c.m + c.add;
+  return (int)(p >> 32) >> c.sh;
 }
 
-template <bool FAST>
-struct Epilogue {
-  // One conv operand: accumulator (without bias) -> integer contribution to the pre-clamp sum.
-  // Returned as double on the exact path (integers, exactly representable), int on the fast path.
-  __device__ __forceinline__ static double contrib_exact(int acc, const ChanRegs& c, bool relu,
-                                                         bool exact_f32, bool bias64) {
-    double z;
-    if (exact_f32) {
-      // INT32_MAX is the sentinel for b_int == 2^31: the reference's float32 clamp bound n-1 =
-      // 2^31-2 rounds to 2^31 (quant_utils.py:76 with k = 32), which no int32 can hold
-      const long long b64 = c.bias == 2147483647 ? 2147483648LL : (long long)c.bias;
-      float a = bias64 ? (float)((long long)acc + b64) : (float)(acc + c.bias);
-      float y = __fmul_rn(a, c.s);                 // quant_modules.py:307
-      if (relu) y = fmaxf(y, 0.0f);                // jasper.py:661
-      z = (double)rintf(__fdiv_rn(y, c.s));        // quant_utils.py:187
-    } else {
-      int zi = acc + c.bias;
-      if (relu) zi = max(zi, 0);
-      z = (double)zi;
-    }
-    return rint(__dmul_rn(z, c.mult));             // quant_utils.py:195-196
+// Literal restatement of the float recipe (any accumulator size, ties, huge biases).
+__device__ __forceinline__ double contrib_exact(int acc, const ChanRegs& c, bool relu, bool exact_f32,
+                                                bool bias64) {
+  double z;
+  if (exact_f32) {
+    // INT32_MAX is the sentinel for b_int == 2^31: the reference's float32 clamp bound n-1 =
+    // 2^31-2 rounds to 2^31 (quant_utils.py:76 with k = 32), which no int32 can hold
+    const long long b64 = c.bias == 2147483647 ? 2147483648LL : (long long)c.bias;
+    float a = bias64 ? (float)((long long)acc + b64) : (float)(acc + c.bias);
+    float y = __fmul_rn(a, c.s);                 // quant_modules.py:307
+    if (relu) y = fmaxf(y, 0.0f);                // jasper.py:661
+    z = (double)rintf(__fdiv_rn(y, c.s));        // quant_utils.py:187
+  } else {
+    int zi = acc + c.bias;
+    if (relu) zi = max(zi, 0);
+    z = (double)zi;
   }
-  __device__ __forceinline__ static int contrib_fast(int acc, const ChanRegs& c, bool relu) {
-    int z = acc + c.bias;
-    if (relu) z = max(z, 0);
-    return dyad_fast(z, c.m, c.e, c.half);
-  }
+  return rint(__dmul_rn(z, c.mult));             // quant_utils.py:195-196
+}
+
+// Kernel-uniform constants of the REQUANT epilogue, derived once per thread.
+struct EpiConsts {
+  int lo1, hi1, lo2, hi2;   // clamps with the ReLUs folded in (fast path)
+  long long half2;
+  double mult2;
 };
 
-// Full per-element REQUANT pipeline.  acc1 / c1 only used when has1; prev is the optional
-// previous res_act code (already loaded).  Returns the final 8-bit code as int.
+__device__ __forceinline__ EpiConsts make_epi_consts(const EpiArgs& ep, bool has1) {
+  EpiConsts k;
+  // ReLU commutes with the monotone requantisation: relu(z) -> clamp lower bound 0 (single operand),
+  // block ReLU after the first clamp -> lower bound 0 as well.
+  const bool relu_lo = (ep.flags & QASR_F_RELU1) || ((ep.flags & QASR_F_RELU0) && !has1 && ep.prev == nullptr);
+  k.lo1 = relu_lo ? max(ep.qmin, 0) : ep.qmin;
+  k.hi1 = ep.qmax;
+  k.lo2 = ep.qmin2;
+  k.hi2 = ep.qmax2;
+  k.half2 = (ep.e2 >= 1 && ep.e2 <= 62) ? (1ll << (ep.e2 - 1)) : 0ll;
+  k.mult2 = dyad_mult(ep.m2, ep.e2);
+  return k;
+}
+
+// Full per-element REQUANT pipeline -> final 8-bit code (as int).  `valid` = false zeroes the code
+// (MaskedConv1d's length mask, jasper.py:177-181).
 template <bool FAST>
-__device__ __forceinline__ int epilogue_requant(const EpiArgs& ep, int acc0, const ChanRegs& c0,
-                                                bool has1, int acc1, const ChanRegs& c1, int prev,
-                                                double mult2, long long half2, bool valid) {
+__device__ __forceinline__ int epilogue_requant(const EpiArgs& ep, const EpiConsts& k, int acc0,
+                                                const ChanRegs& c0, bool has1, int acc1, const ChanRegs& c1,
+                                                int prev, bool valid) {
   int q;
   if (FAST) {
-    int o = Epilogue<true>::contrib_fast(acc0, c0, ep.flags & QASR_F_RELU0);
-    if (has1) o += Epilogue<true>::contrib_fast(acc1, c1, false);
+    int o = contrib_fast(acc0, c0);
+    if (has1) o += contrib_fast(acc1, c1);
     o += prev;
-    q = min(max(o, ep.qmin), ep.qmax);
-    if (ep.flags & QASR_F_RELU1) q = max(q, 0);
+    q = min(max(o, k.lo1), k.hi1);
     if (ep.flags & QASR_F_STAGE2) {
-      q = dyad_fast(q, ep.m2, ep.e2, half2);
-      q = min(max(q, ep.qmin2), ep.qmax2);
+      const long long p = (long long)q * (long long)ep.m2 + k.half2;
+      q = (int)(p >> ep.e2);
+      q = min(max(q, k.lo2), k.hi2);
     }
   } else {
     const bool ex = ep.flags & QASR_F_EXACT_F32, b64 = ep.flags & QASR_F_BIAS64;
-    double o = Epilogue<false>::contrib_exact(acc0, c0, ep.flags & QASR_F_RELU0, ex, b64);
-    if (has1) o += Epilogue<false>::contrib_exact(acc1, c1, false, ex, b64);
+    double o = contrib_exact(acc0, c0, ep.flags & QASR_F_RELU0, ex, b64);
+    if (has1) o += contrib_exact(acc1, c1, false, ex, b64);
     o += (double)prev;
     o = fmin(fmax(o, (double)ep.qmin), (double)ep.qmax);   // quant_utils.py:213-214
     if (ep.flags & QASR_F_RELU1) o = fmax(o, 0.0);          // jasper.py:687
     if (ep.flags & QASR_F_STAGE2) {
-      o = rint(__dmul_rn(o, mult2));
+      o = rint(__dmul_rn(o, k.mult2));
       o = fmin(fmax(o, (double)ep.qmin2), (double)ep.qmax2);
     }
     q = (int)o;
   }
-  return valid ? q : 0;                                       // jasper.py:177-181
+  return valid ? q : 0;
 }
 
 __device__ __forceinline__ float epilogue_dequant(const EpiArgs& ep, int acc, const ChanRegs& c) {
@@ -178,9 +195,11 @@ __device__ __forceinline__ float epilogue_dequant(const EpiArgs& ep, int acc, co
   return y;
 }
 
+// low bytes of four ints -> one word (3 PRMT)
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
-  return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) |
-         ((uint32_t)(d & 0xff) << 24);
+  const uint32_t lo = __byte_perm((uint32_t)a, (uint32_t)b, 0x0040);
+  const uint32_t hi = __byte_perm((uint32_t)c, (uint32_t)d, 0x0040);
+  return __byte_perm(lo, hi, 0x5410);
 }
 
 #endif  // __CUDACC__

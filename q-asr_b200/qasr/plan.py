@@ -63,7 +63,7 @@ def fast_ok(bound, m, e):
     for mi, ei in zip(np.atleast_1d(m).tolist(), np.atleast_1d(e).tolist()):
         if mi == 0:
             continue
-        if ei < 1 or ei > 62:
+        if ei < 32 or ei > 62:     # fast path shifts the high word of the product by e - 32
             return False
         if bound * mi >= 2 ** 53 or (bound * mi) >> ei >= 2 ** 30:
             return False
@@ -71,6 +71,15 @@ def fast_ok(bound, m, e):
         if t < 0 or (1 << t) <= bound:
             return False
     return True
+
+
+def stage2_fast_ok(bound, m, e):
+    """Same proof for the scalar second requantisation (generic 64-bit shift: 1 <= e <= 62)."""
+    mi, ei = int(np.atleast_1d(m)[0]), int(np.atleast_1d(e)[0])
+    if ei < 1 or ei > 62 or bound * mi >= 2 ** 53:
+        return False
+    t = ei - 1 - _tz(mi)
+    return t >= 0 and (1 << t) > bound
 
 
 class ActInfo:
@@ -316,7 +325,7 @@ class FusedPlan:
             if relu:
                 flags |= L.F_RELU1
             flags |= L.F_STAGE2
-            fast2 = fast_ok(ra.n + 1, m2, e2)
+            fast2 = stage2_fast_ok(ra.n + 1, m2, e2)
             self._emit_resact(base, ra, out, flags, fast2, stage2, lens)
         else:
             raise NotImplementedError(type(base))
