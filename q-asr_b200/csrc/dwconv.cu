@@ -14,9 +14,13 @@
 //   K = 32 * KS covers 15 S + d + (k-1) dil + 1 taps; d = (-pad) mod 4 absorbs the misalignment.
 //   * A fragments (KS x 4 registers) are built once per warp from the channel's k int8 taps and
 //     reused for every tile of that channel (several utterances per warp).
-//   * B fragments are plain aligned 32-bit words of the input row: lane L of the warp needs words
-//     (P/4 + 4 S (L>>2) + (L&3) + 8 ks [+4]) -> for S = 1 the 32 lanes read 128 contiguous bytes,
-//     fully coalesced; neighbouring k-steps overlap in L1.  No shared-memory staging of x at all.
+//   * Input rows are staged in shared memory by the bulk-copy engine (cp.async.bulk, one copy per
+//     row, completion on an mbarrier), kBufs rows per warp in flight, with zero halos on both sides
+//     of the row standing in for the conv padding: the HBM read is one coalesced stream per row and
+//     is issued two rows ahead of its use.
+//   * B fragments are plain aligned 32-bit words of the staged row: lane L needs words
+//     (P/4 + 4 S (L>>2) + (L&3) + 8 ks [+4]) -> for S = 1 consecutive lanes read consecutive words
+//     (conflict-free LDS), no bounds checks.
 //   * D (int32, 4 per lane) goes through the fused epilogue, the 4 result bytes are transposed
 //     through a 128-byte per-warp shared-memory line so the warp stores 128 contiguous bytes.
 // mma.sync m16n8k32 (IMMA) was measured at 0.48 instr/clk/SM (1.14 POPS) on B200: the MMA part of
@@ -27,16 +31,21 @@ namespace {
 
 constexpr int kWarps = 4;
 constexpr int kThreads = 32 * kWarps;
-constexpr int kTile = 128;  // outputs per warp tile
+constexpr int kTile = 128;   // outputs per warp tile
+constexpr int kBufs = 3;     // input rows in flight per warp (bulk async copies, 2 ahead)
+constexpr uint32_t kSpinLimit = 1u << 24;
 
 struct DwArgs {
   const uint8_t* x;
   const int8_t* w;
   void* out;
   int x_ld, out_ld, B, C, T_in, T_out, k, stride, dil, pad;
-  int d;        // (-pad) mod 4
-  int bchunk;   // utterances per warp work item
-  int nbg;      // ceil(B / bchunk)
+  int d;          // (-pad) mod 4
+  int bchunk;     // utterances per warp work item
+  int nbg;        // ceil(B / bchunk)
+  int halo;       // zero bytes in front of the row inside a staging buffer (multiple of 16, >= pad + d)
+  int copy_bytes; // T_in rounded up to 16: bytes of one bulk copy
+  int buf_bytes;  // one staging buffer (multiple of 128)
   EpiArgs ep;
 };
 
@@ -52,14 +61,57 @@ __device__ __forceinline__ void imma_16832(int (&acc)[4], const uint32_t (&a)[4]
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spin > kSpinLimit) __trap();
+  }
+}
+// one input row global -> shared through the bulk-copy engine, completion on an mbarrier
+__device__ __forceinline__ void row_copy_async(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 template <int KS, int S, bool XS, bool FAST>
 __global__ void __launch_bounds__(kThreads) dwconv_mma_kernel(const DwArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint32_t stage[kWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, tg = lane & 3;
   const int item = blockIdx.x * kWarps + warp;
-  if (item >= a.C * a.nbg) return;  // whole warps exit together; only __syncwarp below
+  if (item >= a.C * a.nbg) return;  // whole warps exit together; only warp-level sync below
   const int c = item / a.nbg, bg = item - c * a.nbg;
+  const int b_begin = bg * a.bchunk;
+  const int nrows = min(a.B, b_begin + a.bchunk) - b_begin;
+
+  // ---- per-warp staging ring: kBufs x [halo zeros | row | zeros], one mbarrier each
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * kBufs;
+  uint8_t* bufs = smem + 128 + (size_t)warp * kBufs * a.buf_bytes;
+  for (int i = lane; i < kBufs * a.buf_bytes / 16; i += 32)
+    reinterpret_cast<uint4*>(bufs)[i] = make_uint4(0, 0, 0, 0);
+  if (lane == 0) {
+    for (int i = 0; i < kBufs; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bars + i)));
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // zero fill (generic proxy) before the async copies
+  __syncwarp();
+  const uint8_t* xbase = a.x + ((size_t)b_begin * a.C + c) * a.x_ld;
+  const size_t xstep = (size_t)a.C * a.x_ld;  // next utterance, same channel
+  if (lane == 0) {
+    for (int r = 0; r < min(nrows, kBufs - 1); ++r)
+      row_copy_async(smem_addr(bufs + r * a.buf_bytes + a.halo), xbase + r * xstep, a.copy_bytes,
+                     smem_addr(bars + r));
+  }
 
   // ---- banded A fragments of this channel (registers, reused for every tile)
   uint32_t af[KS][4];
@@ -90,39 +142,48 @@ __global__ void __launch_bounds__(kThreads) dwconv_mma_kernel(const DwArgs a) {
   const EpiConsts kc = make_epi_consts(a.ep, false);
   // offsets of this lane's 4 accumulators inside the 128-frame tile: D[row][col] -> 16 col + row
   const int o0 = 32 * tg + g, o1 = o0 + 16, o2 = o0 + 8, o3 = o0 + 24;
-  const int woff = 4 * S * g + tg;  // word offset of b0 inside the tile window
-  const int b_end = min(a.B, (bg + 1) * a.bchunk);
-  const int nwords_in = (a.T_in + 3) >> 2;
+  uint8_t* sb = reinterpret_cast<uint8_t*>(stage[warp]);
+  // word offset of this lane's first B word relative to a tile: window start = halo - pad - d (bytes)
+  const int lane_w = ((a.halo - a.pad - a.d) >> 2) + 4 * S * g + tg;
   const int out_words = ((a.T_out + 15) >> 4) << 2;  // stores cover T_out rounded up to 16 (zero filled)
 
-  for (int b = bg * a.bchunk; b < b_end; ++b) {
+  for (int r = 0; r < nrows; ++r) {
+    const int buf = r % kBufs;
+    // keep kBufs-1 rows in flight: the buffer being refilled was consumed in iteration r-1
+    if (lane == 0 && r + kBufs - 1 < nrows) {
+      const int nb = (r + kBufs - 1) % kBufs;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      row_copy_async(smem_addr(bufs + nb * a.buf_bytes + a.halo), xbase + (size_t)(r + kBufs - 1) * xstep,
+                     a.copy_bytes, smem_addr(bars + nb));
+    }
+    bar_wait(smem_addr(bars + buf), (uint32_t)((r / kBufs) & 1));
+    const uint32_t* xw = reinterpret_cast<const uint32_t*>(bufs + buf * a.buf_bytes) + lane_w;
+    const int b = b_begin + r;
     const size_t row = (size_t)b * a.C + c;
-    const uint32_t* xrow = reinterpret_cast<const uint32_t*>(a.x + row * a.x_ld);
     const int len = (a.ep.flags & QASR_F_MASK) ? min(a.ep.out_lens[b], a.T_out) : a.T_out;
     for (int t0 = 0; t0 < a.T_out; t0 += kTile) {
-      const int pw = (t0 * S - a.pad - a.d) >> 2;  // exact: the numerator is a multiple of 4
+      const uint32_t* tw = xw + ((t0 * S) >> 2);
       int acc[4] = {0, 0, 0, 0};
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const int w0 = pw + woff + 8 * ks, w1 = w0 + 4;
-        const uint32_t b0 = (w0 >= 0 && w0 < nwords_in) ? __ldg(xrow + w0) : 0u;
-        const uint32_t b1 = (w1 >= 0 && w1 < nwords_in) ? __ldg(xrow + w1) : 0u;
-        imma_16832<XS>(acc, af[ks], b0, b1);
-      }
+      for (int ks = 0; ks < KS; ++ks) imma_16832<XS>(acc, af[ks], tw[8 * ks], tw[8 * ks + 4]);
       if (a.ep.mode == QASR_EPI_REQUANT_I8) {
-        const int q0 = epilogue_requant<FAST>(a.ep, kc, acc[0], c0, false, 0, c0, 0, t0 + o0 < len);
-        const int q1 = epilogue_requant<FAST>(a.ep, kc, acc[1], c0, false, 0, c0, 0, t0 + o1 < len);
-        const int q2 = epilogue_requant<FAST>(a.ep, kc, acc[2], c0, false, 0, c0, 0, t0 + o2 < len);
-        const int q3 = epilogue_requant<FAST>(a.ep, kc, acc[3], c0, false, 0, c0, 0, t0 + o3 < len);
-        uint8_t* sb = reinterpret_cast<uint8_t*>(stage[warp]);
-        sb[o0] = (uint8_t)q0;
-        sb[o1] = (uint8_t)q1;
-        sb[o2] = (uint8_t)q2;
-        sb[o3] = (uint8_t)q3;
+        sb[o0] = (uint8_t)(FAST ? epilogue_fast<false, false, false>(a.ep, kc, acc[0], c0, 0, c0, 0)
+                                  : epilogue_exact(a.ep, kc, acc[0], c0, false, 0, c0, 0));
+        sb[o1] = (uint8_t)(FAST ? epilogue_fast<false, false, false>(a.ep, kc, acc[1], c0, 0, c0, 0)
+                                  : epilogue_exact(a.ep, kc, acc[1], c0, false, 0, c0, 0));
+        sb[o2] = (uint8_t)(FAST ? epilogue_fast<false, false, false>(a.ep, kc, acc[2], c0, 0, c0, 0)
+                                  : epilogue_exact(a.ep, kc, acc[2], c0, false, 0, c0, 0));
+        sb[o3] = (uint8_t)(FAST ? epilogue_fast<false, false, false>(a.ep, kc, acc[3], c0, 0, c0, 0)
+                                  : epilogue_exact(a.ep, kc, acc[3], c0, false, 0, c0, 0));
         __syncwarp();
-        const uint32_t word = stage[warp][lane];
+        uint32_t word = stage[warp][lane];
         __syncwarp();
-        const int wi = (t0 >> 2) + lane;
+        const int tl = t0 + 4 * lane;
+        if (tl + 4 > len) {  // length mask / row tail: zero the bytes at t >= len
+          const int nvalid = len - tl;
+          word &= nvalid <= 0 ? 0u : (0xffffffffu >> (8 * (4 - nvalid)));
+        }
+        const int wi = tl >> 2;
         if (wi < out_words)
           reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(a.out) + row * a.out_ld)[wi] = word;
       } else if (a.ep.mode == QASR_EPI_DEQUANT_F32) {
@@ -139,6 +200,7 @@ __global__ void __launch_bounds__(kThreads) dwconv_mma_kernel(const DwArgs a) {
         if (t0 + o3 < a.T_out) orow[t0 + o3] = acc[3] + c0.bias;
       }
     }
+    __syncwarp();  // every lane is done reading this buffer before lane 0 refills it
   }
 }
 
@@ -146,12 +208,25 @@ template <int KS, int S>
 int launch(const DwArgs& a, cudaStream_t stream) {
   const int items = a.C * a.nbg;
   const int grid = (items + kWarps - 1) / kWarps;
+  const size_t smem = 128 + (size_t)kWarps * kBufs * a.buf_bytes;
   const bool xs = a.ep.flags & QASR_F_B_SIGNED;
-  const bool fast = !(a.ep.flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64));
-  if (xs && fast) dwconv_mma_kernel<KS, S, true, true><<<grid, kThreads, 0, stream>>>(a);
-  else if (xs) dwconv_mma_kernel<KS, S, true, false><<<grid, kThreads, 0, stream>>>(a);
-  else if (fast) dwconv_mma_kernel<KS, S, false, true><<<grid, kThreads, 0, stream>>>(a);
-  else dwconv_mma_kernel<KS, S, false, false><<<grid, kThreads, 0, stream>>>(a);
+  const bool fast = !(a.ep.flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64 | QASR_F_STAGE2)) &&
+                    a.ep.prev == nullptr;
+#define QASR_DW_GO(XS_, FAST_)                                                                       \
+  do {                                                                                               \
+    auto kern = dwconv_mma_kernel<KS, S, XS_, FAST_>;                                                \
+    static size_t attr_smem = 0;                                                                     \
+    if (smem > 48 * 1024 && smem > attr_smem) {                                                      \
+      QASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr_smem = smem;                                                                              \
+    }                                                                                                \
+    kern<<<grid, kThreads, smem, stream>>>(a);                                                       \
+  } while (0)
+  if (xs && fast) QASR_DW_GO(true, true);
+  else if (xs) QASR_DW_GO(true, false);
+  else if (fast) QASR_DW_GO(false, true);
+  else QASR_DW_GO(false, false);
+#undef QASR_DW_GO
   return qasr_check_launch("dwconv_mma_kernel");
 }
 
@@ -181,6 +256,26 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
   a.x_ld = x_ld; a.out_ld = out_ld; a.B = B; a.C = C; a.T_in = T_in; a.T_out = T_out;
   a.k = k; a.stride = stride; a.dil = dilation; a.pad = pad;
   a.d = ((-pad) % 4 + 4) % 4;
+  const int span = (k - 1) * dilation + 1;
+  const int ksteps = (15 * stride + a.d + span + 31) / 32;
+  if (ksteps > 6) {
+    qasr_set_error("dwconv: tap span %d (k=%d, dilation=%d, stride=%d) exceeds the supported 6 x 32 window",
+                   span, k, dilation, stride);
+    return QASR_ERR_UNSUPPORTED;
+  }
+  // staging buffer: [halo | row (copy_bytes) | zeros up to the furthest word a tile can touch]
+  a.halo = ((pad + a.d + 15) / 16) * 16;
+  a.copy_bytes = ((T_in + 15) / 16) * 16;
+  const int n_tiles = (T_out + kTile - 1) / kTile;
+  const int reach = a.halo - pad - a.d + n_tiles * kTile * stride + 32 * ksteps + 16;  // bytes read at most
+  int buf = a.halo + a.copy_bytes;
+  if (buf < reach) buf = reach;
+  a.buf_bytes = ((buf + 127) / 128) * 128;
+  const size_t smem = 128 + (size_t)kWarps * kBufs * a.buf_bytes;
+  if (smem > 200 * 1024) {
+    qasr_set_error("dwconv: rows of %d frames need %zu bytes of staging shared memory (limit 200 KiB)", T_in, smem);
+    return QASR_ERR_UNSUPPORTED;
+  }
   // utterances per warp: amortise the A-fragment set-up while keeping >= ~8 warps per SM in flight
   const long long want_items = 8LL * kWarps * qasr_sm_count();
   int bchunk = (int)(((long long)B * C + want_items - 1) / want_items);
@@ -192,8 +287,6 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
   a.ep = make_epi_args(epi);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-  const int span = (k - 1) * dilation + 1;
-  const int ksteps = (15 * stride + a.d + span + 31) / 32;
 #define QASR_DW_CASE(KS_)                                      \
   if (ksteps == KS_) return stride == 1 ? launch<KS_, 1>(a, st) : launch<KS_, 2>(a, st);
   QASR_DW_CASE(1)
@@ -203,7 +296,5 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
   QASR_DW_CASE(5)
   QASR_DW_CASE(6)
 #undef QASR_DW_CASE
-  qasr_set_error("dwconv: tap span %d (k=%d, dilation=%d, stride=%d) exceeds the supported 6 x 32 window", span,
-                 k, dilation, stride);
   return QASR_ERR_UNSUPPORTED;
 }

@@ -134,7 +134,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo, 
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
-template <bool FAST>
+// EPI: bit 0 = all-integer fast epilogue, bits 1..3 (fast path only) = second conv operand,
+// previous-res_act addend, second requantisation stage.  EPI == 0 is the literal (runtime-flag) path.
+constexpr int kEpiFast = 1, kEpiDual = 2, kEpiPrev = 4, kEpiStage2 = 8;
+
+template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
@@ -281,9 +285,14 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int j = 16 * v + 4 * w4 + i;
-                const int prev = prow ? (int)(int8_t)((pw[w4] >> (8 * i)) & 0xff) : 0;
-                q[i] = epilogue_requant<FAST>(g.ep, kc, acc0[j], c0, g.nseg > 1, g.nseg > 1 ? acc1[j] : 0, c1,
-                                              prev, true);
+                if (EPI & kEpiFast) {
+                  const int prev = (EPI & kEpiPrev) ? (int)(int8_t)(pw[w4] >> (8 * i)) : 0;
+                  q[i] = epilogue_fast<(EPI & kEpiDual) != 0, (EPI & kEpiPrev) != 0, (EPI & kEpiStage2) != 0>(
+                      g.ep, kc, acc0[j], c0, (EPI & kEpiDual) ? acc1[j] : 0, c1, prev);
+                } else {
+                  const int prev = prow ? (int)(int8_t)((pw[w4] >> (8 * i)) & 0xff) : 0;
+                  q[i] = epilogue_exact(g.ep, kc, acc0[j], c0, g.nseg > 1, g.nseg > 1 ? acc1[j] : 0, c1, prev);
+                }
               }
               packed[w4] = pack4(q[0], q[1], q[2], q[3]);
             }
@@ -491,19 +500,40 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   g.dbg_align = g_dbg[2] > 0 ? (int)g_dbg[2] : 0;
   g.dbg_nonneg = g_dbg[3] > 0 ? 1 : 0;
 
-  const bool fast = !(epi->flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64));
+  const bool fast = !(epi->flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64)) &&
+                    epi->mode == QASR_EPI_REQUANT_I8;
+  int variant = 0;
+  if (fast)
+    variant = kEpiFast | (op1 ? kEpiDual : 0) | (epi->prev ? kEpiPrev : 0) | ((epi->flags & QASR_F_STAGE2) ? kEpiStage2 : 0);
   int grid = qasr_sm_count();
   if (grid > g.total_tiles) grid = g.total_tiles;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set[2][64] = {};
+  static bool attr_set[16][64] = {};
   int dev = 0;
   QASR_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_set[fast ? 1 : 0][dev]) {  // once per kernel and device (not inside graph replays)
-    if (fast) QASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    else QASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_set[fast ? 1 : 0][dev] = true;
+  const bool need_attr = dev >= 0 && dev < 64 && !attr_set[variant][dev];
+#define QASR_GEMM_CASE(V_)                                                                                     \
+  case V_:                                                                                                     \
+    if (need_attr)                                                                                             \
+      QASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<V_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                           (int)kSmemBytes));                                                  \
+    gemm_i8_kernel<V_><<<grid, kGemmThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);         \
+    break;
+  switch (variant) {
+    QASR_GEMM_CASE(0)
+    QASR_GEMM_CASE(1)
+    QASR_GEMM_CASE(3)
+    QASR_GEMM_CASE(5)
+    QASR_GEMM_CASE(7)
+    QASR_GEMM_CASE(9)
+    QASR_GEMM_CASE(11)
+    QASR_GEMM_CASE(13)
+    QASR_GEMM_CASE(15)
+    default:
+      qasr_set_error("conv1d_gemm: internal: no kernel variant %d", variant);
+      return QASR_ERR_INVALID;
   }
-  if (fast) gemm_i8_kernel<true><<<grid, kGemmThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);
-  else gemm_i8_kernel<false><<<grid, kGemmThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);
+#undef QASR_GEMM_CASE
+  if (need_attr) attr_set[variant][dev] = true;
   return qasr_check_launch("gemm_i8_kernel");
 }

@@ -154,37 +154,37 @@ __device__ __forceinline__ EpiConsts make_epi_consts(const EpiArgs& ep, bool has
   return k;
 }
 
-// Full per-element REQUANT pipeline -> final 8-bit code (as int).  `valid` = false zeroes the code
-// (MaskedConv1d's length mask, jasper.py:177-181).
-template <bool FAST>
-__device__ __forceinline__ int epilogue_requant(const EpiArgs& ep, const EpiConsts& k, int acc0,
-                                                const ChanRegs& c0, bool has1, int acc1, const ChanRegs& c1,
-                                                int prev, bool valid) {
-  int q;
-  if (FAST) {
-    int o = contrib_fast(acc0, c0);
-    if (has1) o += contrib_fast(acc1, c1);
-    o += prev;
-    q = min(max(o, k.lo1), k.hi1);
-    if (ep.flags & QASR_F_STAGE2) {
-      const long long p = (long long)q * (long long)ep.m2 + k.half2;
-      q = (int)(p >> ep.e2);
-      q = min(max(q, k.lo2), k.hi2);
-    }
-  } else {
-    const bool ex = ep.flags & QASR_F_EXACT_F32, b64 = ep.flags & QASR_F_BIAS64;
-    double o = contrib_exact(acc0, c0, ep.flags & QASR_F_RELU0, ex, b64);
-    if (has1) o += contrib_exact(acc1, c1, false, ex, b64);
-    o += (double)prev;
-    o = fmin(fmax(o, (double)ep.qmin), (double)ep.qmax);   // quant_utils.py:213-214
-    if (ep.flags & QASR_F_RELU1) o = fmax(o, 0.0);          // jasper.py:687
-    if (ep.flags & QASR_F_STAGE2) {
-      o = rint(__dmul_rn(o, k.mult2));
-      o = fmin(fmax(o, (double)ep.qmin2), (double)ep.qmax2);
-    }
-    q = (int)o;
+// Full per-element REQUANT pipeline -> final 8-bit code (as int), all-integer fast path.  The
+// operand / stage structure is a compile-time property of the kernel instantiation.
+template <bool DUAL, bool PREV, bool STAGE2>
+__device__ __forceinline__ int epilogue_fast(const EpiArgs& ep, const EpiConsts& k, int acc0, const ChanRegs& c0,
+                                             int acc1, const ChanRegs& c1, int prev) {
+  int o = contrib_fast(acc0, c0);
+  if (DUAL) o += contrib_fast(acc1, c1);
+  if (PREV) o += prev;
+  int q = min(max(o, k.lo1), k.hi1);
+  if (STAGE2) {
+    const long long p = (long long)q * (long long)ep.m2 + k.half2;
+    q = (int)(p >> ep.e2);
+    q = min(max(q, k.lo2), k.hi2);
   }
-  return valid ? q : 0;
+  return q;
+}
+
+// Literal float recipe (runtime flags; any accumulator size, exact ties, 64-bit bias).
+__device__ __forceinline__ int epilogue_exact(const EpiArgs& ep, const EpiConsts& k, int acc0, const ChanRegs& c0,
+                                              bool has1, int acc1, const ChanRegs& c1, int prev) {
+  const bool ex = ep.flags & QASR_F_EXACT_F32, b64 = ep.flags & QASR_F_BIAS64;
+  double o = contrib_exact(acc0, c0, ep.flags & QASR_F_RELU0, ex, b64);
+  if (has1) o += contrib_exact(acc1, c1, false, ex, b64);
+  o += (double)prev;
+  o = fmin(fmax(o, (double)ep.qmin), (double)ep.qmax);   // quant_utils.py:213-214
+  if (ep.flags & QASR_F_RELU1) o = fmax(o, 0.0);          // jasper.py:687
+  if (ep.flags & QASR_F_STAGE2) {
+    o = rint(__dmul_rn(o, k.mult2));
+    o = fmin(fmax(o, (double)ep.qmin2), (double)ep.qmax2);
+  }
+  return (int)o;
 }
 
 __device__ __forceinline__ float epilogue_dequant(const EpiArgs& ep, int acc, const ChanRegs& c) {
