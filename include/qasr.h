@@ -108,10 +108,15 @@ typedef struct {
  * quant_modules.py:301-305 for groups == C_in == C_out, k in {33..87}, stride 1|2,
  * dilation 1|2, plus the fused epilogue above.
  *   x      [B][C][x_ld]  8-bit codes (signed iff QASR_F_B_SIGNED), already masked
- *   w      [C][k]        int8 weight codes W_int (quant_utils.py:74-76)
+ *   wp     packed weights from qasr_pack_dw_weights(): the int8 codes W_int [C][k]
+ *          (quant_utils.py:74-76) laid out as the banded tensor-core A fragments the kernel
+ *          consumes; packing depends on (k, stride, dilation, pad) and is done once per layer
  *   out    [B][C][out_ld] int8 (REQUANT), float (DEQUANT) or int32 (RAW); pitch in elems
  * ---------------------------------------------------------------------------------- */
-int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, void* out, int32_t out_ld,
+int64_t qasr_dw_packed_bytes(int32_t C, int32_t k, int32_t stride, int32_t dilation, int32_t pad);
+int qasr_pack_dw_weights(const int8_t* w, void* wp, int32_t C, int32_t k, int32_t stride,
+                         int32_t dilation, int32_t pad, void* stream);
+int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* wp, void* out, int32_t out_ld,
                      int32_t B, int32_t C, int32_t T_in, int32_t T_out, int32_t k,
                      int32_t stride, int32_t dilation, int32_t pad,
                      const qasr_epilogue* epi, void* stream);

@@ -12,8 +12,9 @@
 //       A[16 x K],  A[i][kk] = w[(kk - S i - d) / dil]      (banded; depends on the channel only)
 //       B[K  x 8],  B[kk][j] = x[P + 16 S j + kk],  P = S t0 - pad - d   (4-byte aligned)
 //   K = 32 * KS covers 15 S + d + (k-1) dil + 1 taps; d = (-pad) mod 4 absorbs the misalignment.
-//   * A fragments (KS x 4 registers) are built once per warp from the channel's k int8 taps and
-//     reused for every tile of that channel (several utterances per warp).
+//   * A fragments (KS x 4 registers per lane) are packed once per layer by qasr_pack_dw_weights and
+//     loaded with KS*4 coalesced words per warp, then reused for every tile of that channel
+//     (several utterances per warp).
 //   * Input rows are staged in shared memory by the bulk-copy engine (cp.async.bulk, one copy per
 //     row, completion on an mbarrier), kBufs rows per warp in flight, with zero halos on both sides
 //     of the row standing in for the conv padding: the HBM read is one coalesced stream per row and
@@ -82,7 +83,8 @@ __device__ __forceinline__ void row_copy_async(uint32_t dst, const void* src, ui
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <int KS, int S, bool XS, bool FAST>
+// EK: 0 = REQUANT all-integer fast path, 1 = REQUANT literal path, 2 = DEQUANT_F32 / RAW_I32
+template <int KS, int S, bool XS, int EK>
 __global__ void __launch_bounds__(kThreads) dwconv_mma_kernel(const DwArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint32_t stage[kWarps][32];
@@ -113,29 +115,14 @@ __global__ void __launch_bounds__(kThreads) dwconv_mma_kernel(const DwArgs a) {
                      smem_addr(bars + r));
   }
 
-  // ---- banded A fragments of this channel (registers, reused for every tile)
+  // ---- banded A fragments of this channel: pre-packed per lane by qasr_pack_dw_weights
   uint32_t af[KS][4];
   {
-    const int8_t* wr = a.w + (size_t)c * a.k;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.w) + (size_t)c * KS * 128 + lane;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int row = g + 8 * (r & 1);
-        const int kk0 = 32 * ks + 16 * (r >> 1) + 4 * tg;
-        uint32_t word = 0;
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-          const int u = kk0 + bb - S * row - a.d;
-          int v = 0;
-          if (u >= 0) {
-            const int tap = u / a.dil;
-            if (tap * a.dil == u && tap < a.k) v = __ldg(wr + tap);
-          }
-          word |= (uint32_t)(v & 0xff) << (8 * bb);
-        }
-        af[ks][r] = word;
-      }
+      for (int r = 0; r < 4; ++r) af[ks][r] = __ldg(wp + (ks * 4 + r) * 32);
     }
   }
   const ChanRegs c0 = load_chan(a.ep.ch0, c);
@@ -166,14 +153,14 @@ __global__ void __launch_bounds__(kThreads) dwconv_mma_kernel(const DwArgs a) {
       int acc[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) imma_16832<XS>(acc, af[ks], tw[8 * ks], tw[8 * ks + 4]);
-      if (a.ep.mode == QASR_EPI_REQUANT_I8) {
-        sb[o0] = (uint8_t)(FAST ? epilogue_fast<false, false, false>(a.ep, kc, acc[0], c0, 0, c0, 0)
+      if (EK < 2) {
+        sb[o0] = (uint8_t)(EK == 0 ? epilogue_fast<false, false, false>(a.ep, kc, acc[0], c0, 0, c0, 0)
                                   : epilogue_exact(a.ep, kc, acc[0], c0, false, 0, c0, 0));
-        sb[o1] = (uint8_t)(FAST ? epilogue_fast<false, false, false>(a.ep, kc, acc[1], c0, 0, c0, 0)
+        sb[o1] = (uint8_t)(EK == 0 ? epilogue_fast<false, false, false>(a.ep, kc, acc[1], c0, 0, c0, 0)
                                   : epilogue_exact(a.ep, kc, acc[1], c0, false, 0, c0, 0));
-        sb[o2] = (uint8_t)(FAST ? epilogue_fast<false, false, false>(a.ep, kc, acc[2], c0, 0, c0, 0)
+        sb[o2] = (uint8_t)(EK == 0 ? epilogue_fast<false, false, false>(a.ep, kc, acc[2], c0, 0, c0, 0)
                                   : epilogue_exact(a.ep, kc, acc[2], c0, false, 0, c0, 0));
-        sb[o3] = (uint8_t)(FAST ? epilogue_fast<false, false, false>(a.ep, kc, acc[3], c0, 0, c0, 0)
+        sb[o3] = (uint8_t)(EK == 0 ? epilogue_fast<false, false, false>(a.ep, kc, acc[3], c0, 0, c0, 0)
                                   : epilogue_exact(a.ep, kc, acc[3], c0, false, 0, c0, 0));
         __syncwarp();
         uint32_t word = stage[warp][lane];
@@ -212,9 +199,10 @@ int launch(const DwArgs& a, cudaStream_t stream) {
   const bool xs = a.ep.flags & QASR_F_B_SIGNED;
   const bool fast = !(a.ep.flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64 | QASR_F_STAGE2)) &&
                     a.ep.prev == nullptr;
-#define QASR_DW_GO(XS_, FAST_)                                                                       \
+  const int ek = a.ep.mode != QASR_EPI_REQUANT_I8 ? 2 : (fast ? 0 : 1);
+#define QASR_DW_GO(XS_, EK_)                                                                         \
   do {                                                                                               \
-    auto kern = dwconv_mma_kernel<KS, S, XS_, FAST_>;                                                \
+    auto kern = dwconv_mma_kernel<KS, S, XS_, EK_>;                                                  \
     static size_t attr_smem = 0;                                                                     \
     if (smem > 48 * 1024 && smem > attr_smem) {                                                      \
       QASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -222,20 +210,69 @@ int launch(const DwArgs& a, cudaStream_t stream) {
     }                                                                                                \
     kern<<<grid, kThreads, smem, stream>>>(a);                                                       \
   } while (0)
-  if (xs && fast) QASR_DW_GO(true, true);
-  else if (xs) QASR_DW_GO(true, false);
-  else if (fast) QASR_DW_GO(false, true);
-  else QASR_DW_GO(false, false);
+  if (xs) {
+    if (ek == 0) QASR_DW_GO(true, 0); else if (ek == 1) QASR_DW_GO(true, 1); else QASR_DW_GO(true, 2);
+  } else {
+    if (ek == 0) QASR_DW_GO(false, 0); else if (ek == 1) QASR_DW_GO(false, 1); else QASR_DW_GO(false, 2);
+  }
 #undef QASR_DW_GO
   return qasr_check_launch("dwconv_mma_kernel");
 }
 
+// [C][k] int8 taps -> [C][KS][4 regs][32 lanes] A-fragment words of the banded matrix
+__global__ void pack_dw_kernel(const int8_t* __restrict__ w, uint32_t* __restrict__ wp, int C, int k, int S,
+                               int dil, int d, int KS) {
+  const int total = C * KS * 128;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int lane = i & 31, r = (i >> 5) & 3, ks = (i >> 7) % KS, c = i / (KS * 128);
+    const int g = lane >> 2, tg = lane & 3;
+    const int row = g + 8 * (r & 1);
+    const int kk0 = 32 * ks + 16 * (r >> 1) + 4 * tg;
+    uint32_t word = 0;
+    for (int bb = 0; bb < 4; ++bb) {
+      const int u = kk0 + bb - S * row - d;
+      int v = 0;
+      if (u >= 0) {
+        const int tap = u / dil;
+        if (tap * dil == u && tap < k) v = w[(size_t)c * k + tap];
+      }
+      word |= (uint32_t)(v & 0xff) << (8 * bb);
+    }
+    wp[i] = word;
+  }
+}
+
+int dw_ksteps(int k, int stride, int dilation, int pad) {
+  const int d = ((-pad) % 4 + 4) % 4;
+  return (15 * stride + d + (k - 1) * dilation + 1 + 31) / 32;
+}
+
 }  // namespace
+
+extern "C" int64_t qasr_dw_packed_bytes(int32_t C, int32_t k, int32_t stride, int32_t dilation, int32_t pad) {
+  if (C <= 0 || k <= 0 || (stride != 1 && stride != 2) || dilation < 1 || pad < 0) return -1;
+  const int ks = dw_ksteps(k, stride, dilation, pad);
+  if (ks > 6) return -1;
+  return (int64_t)C * ks * 128 * 4;
+}
+
+extern "C" int qasr_pack_dw_weights(const int8_t* w, void* wp, int32_t C, int32_t k, int32_t stride,
+                                    int32_t dilation, int32_t pad, void* stream) {
+  QASR_CHECK_ARG(w && wp && qasr_aligned16(wp), "pack_dw_weights: null / unaligned pointer");
+  QASR_CHECK_ARG(qasr_dw_packed_bytes(C, k, stride, dilation, pad) > 0,
+                 "pack_dw_weights: unsupported shape (k=%d stride=%d dilation=%d pad=%d)", k, stride, dilation, pad);
+  const int ks = dw_ksteps(k, stride, dilation, pad);
+  const int total = C * ks * 128;
+  pack_dw_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      w, static_cast<uint32_t*>(wp), C, k, stride, dilation, ((-pad) % 4 + 4) % 4, ks);
+  return qasr_check_launch("pack_dw_kernel");
+}
 
 extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, void* out, int32_t out_ld,
                                 int32_t B, int32_t C, int32_t T_in, int32_t T_out, int32_t k, int32_t stride,
                                 int32_t dilation, int32_t pad, const qasr_epilogue* epi, void* stream) {
   QASR_CHECK_ARG(x && w && out && epi, "dwconv: null pointer");
+  QASR_CHECK_ARG(qasr_aligned16(w), "dwconv: packed weights (qasr_pack_dw_weights) must be 16-byte aligned");
   QASR_CHECK_ARG(B > 0 && C > 0 && T_in > 0 && T_out > 0 && k > 0, "dwconv: bad shape");
   QASR_CHECK_ARG(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2 (got %d)", stride);
   QASR_CHECK_ARG(dilation >= 1 && pad >= 0, "dwconv: bad dilation/pad");

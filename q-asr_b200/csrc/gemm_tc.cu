@@ -15,9 +15,10 @@
 //               tile i+1.  An optional second operand pair (the block's residual 1x1 conv,
 //               jasper.py:667-672) accumulates into a second TMEM tile and both meet in the
 //               res_act epilogue (jasper.py:681) without an int32 round trip through HBM.
-// Warp roles (384 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (640 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0: TMA producer (one elected lane)      warp 1: MMA issuer (one elected lane)
-//   warp 2: TMEM allocator                        warps 4..11: epilogue (TMEM -> regs -> HBM)
+//   warp 2: TMEM allocator                        warps 4..19: epilogue (TMEM -> regs -> HBM),
+//   four per scheduler so TMEM-load / store latencies of one warp hide behind the others
 #include <cuda.h>
 
 #include "qasr_common.cuh"
@@ -26,7 +27,7 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 128;
 constexpr int kStages = 5;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
 constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = BM * BK, kBBytes = BK * BN;
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
@@ -114,6 +115,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }
@@ -242,19 +252,26 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;         // which 64 of the tile's 128 columns
+    const int cgroup = (warp - 4) >> 2;       // which 32 of the tile's 128 columns
     const EpiConsts kc = make_epi_consts(g.ep, g.nseg > 1);
     int as = 0;
     uint32_t aphase = 0;
+    int last_mt = -1;
+    bool row_ok = false;
+    int cc = 0;
+    ChanRegs c0, c1;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
       const int mt = tile % g.m_tiles;
       const int rest = tile / g.m_tiles;
       const int nt = rest % g.n_tiles, b = rest / g.n_tiles;
-      const int c = mt * BM + quarter * 32 + lane;
-      const bool row_ok = c < g.C_out;
-      const int cc = row_ok ? c : 0;
-      const ChanRegs c0 = load_chan(g.ep.ch0, cc);
-      const ChanRegs c1 = g.nseg > 1 ? load_chan(g.ep.ch1, cc) : c0;
+      if (mt != last_mt) {  // per-channel parameters change only with the M tile
+        const int c = mt * BM + quarter * 32 + lane;
+        row_ok = c < g.C_out;
+        cc = row_ok ? c : 0;
+        c0 = load_chan(g.ep.ch0, cc);
+        c1 = g.nseg > 1 ? load_chan(g.ep.ch1, cc) : c0;
+        last_mt = mt;
+      }
       const int len = (g.ep.flags & QASR_F_MASK) ? min(g.ep.out_lens[b], g.T_out) : g.T_out;
       const size_t row = (size_t)b * g.C_out + cc;
 
@@ -262,61 +279,57 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       tc_fence_after();
 #pragma unroll 1
       for (int ch = 0; ch < 2; ++ch) {
-        const int col0 = half * 64 + ch * 32;
+        const int col0 = cgroup * 32 + ch * 16;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * 2 * BN + col0);
-        int acc0[32], acc1[32];
-        tmem_ld32(taddr, acc0);
-        if (g.nseg > 1) tmem_ld32(taddr + BN, acc1);
+        int acc0[16], acc1[16];
+        tmem_ld16(taddr, acc0);
+        if (g.nseg > 1) tmem_ld16(taddr + BN, acc1);
         tmem_ld_wait();
-        const int tbase = nt * BN + col0;
+        const int tv = nt * BN + col0;   // first frame of this 16-column vector
         if (g.ep.mode == QASR_EPI_REQUANT_I8) {
           uint8_t* orow = reinterpret_cast<uint8_t*>(g.out) + row * g.out_ld;
-          const int8_t* prow = g.ep.prev ? g.ep.prev + row * g.ep.prev_ld : nullptr;
+          uint4 pv = make_uint4(0, 0, 0, 0);
+          if ((EPI == 0 || (EPI & kEpiPrev)) && g.ep.prev != nullptr && row_ok && tv < g.T_out)
+            pv = *reinterpret_cast<const uint4*>(g.ep.prev + row * g.ep.prev_ld + tv);
+          const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+          uint32_t packed[4];
 #pragma unroll
-          for (int v = 0; v < 2; ++v) {   // two 16-byte vectors per 32 columns
-            const int tv = tbase + 16 * v;
-            uint4 pv = make_uint4(0, 0, 0, 0);
-            if (prow && row_ok && tv < g.T_out) pv = *reinterpret_cast<const uint4*>(prow + tv);
-            const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
-            uint32_t packed[4];
+          for (int w4 = 0; w4 < 4; ++w4) {
+            int q[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j = 4 * w4 + i;
+              if (EPI & kEpiFast) {
+                const int prev = (EPI & kEpiPrev) ? (int)(int8_t)(pw[w4] >> (8 * i)) : 0;
+                q[i] = epilogue_fast<(EPI & kEpiDual) != 0, (EPI & kEpiPrev) != 0, (EPI & kEpiStage2) != 0>(
+                    g.ep, kc, acc0[j], c0, (EPI & kEpiDual) ? acc1[j] : 0, c1, prev);
+              } else {
+                const int prev = (int)(int8_t)((pw[w4] >> (8 * i)) & 0xff);
+                q[i] = epilogue_exact(g.ep, kc, acc0[j], c0, g.nseg > 1, g.nseg > 1 ? acc1[j] : 0, c1, prev);
+              }
+            }
+            packed[w4] = pack4(q[0], q[1], q[2], q[3]);
+          }
+          if (tv + 16 > len) {  // length mask / row tail: zero the bytes at t >= len
 #pragma unroll
             for (int w4 = 0; w4 < 4; ++w4) {
-              int q[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int j = 16 * v + 4 * w4 + i;
-                if (EPI & kEpiFast) {
-                  const int prev = (EPI & kEpiPrev) ? (int)(int8_t)(pw[w4] >> (8 * i)) : 0;
-                  q[i] = epilogue_fast<(EPI & kEpiDual) != 0, (EPI & kEpiPrev) != 0, (EPI & kEpiStage2) != 0>(
-                      g.ep, kc, acc0[j], c0, (EPI & kEpiDual) ? acc1[j] : 0, c1, prev);
-                } else {
-                  const int prev = prow ? (int)(int8_t)((pw[w4] >> (8 * i)) & 0xff) : 0;
-                  q[i] = epilogue_exact(g.ep, kc, acc0[j], c0, g.nseg > 1, g.nseg > 1 ? acc1[j] : 0, c1, prev);
-                }
-              }
-              packed[w4] = pack4(q[0], q[1], q[2], q[3]);
+              const int nvalid = len - (tv + 4 * w4);
+              const uint32_t m = nvalid >= 4 ? 0xffffffffu : (nvalid <= 0 ? 0u : (0xffffffffu >> (8 * (4 - nvalid))));
+              packed[w4] &= m;
             }
-            if (tv + 16 > len) {  // length mask / row tail: zero the bytes at t >= len
-#pragma unroll
-              for (int w4 = 0; w4 < 4; ++w4) {
-                const int nvalid = len - (tv + 4 * w4);
-                const uint32_t m = nvalid >= 4 ? 0xffffffffu : (nvalid <= 0 ? 0u : (0xffffffffu >> (8 * (4 - nvalid))));
-                packed[w4] &= m;
-              }
-            }
-            if (row_ok && tv < g.T_out)
-              *reinterpret_cast<uint4*>(orow + tv) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
           }
+          if (row_ok && tv < g.T_out)
+            *reinterpret_cast<uint4*>(orow + tv) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         } else if (g.ep.mode == QASR_EPI_DEQUANT_F32) {
           float* orow = reinterpret_cast<float*>(g.out) + row * g.out_ld;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (row_ok && tbase + j < g.T_out) orow[tbase + j] = epilogue_dequant(g.ep, acc0[j], c0);
+          for (int j = 0; j < 16; ++j)
+            if (row_ok && tv + j < g.T_out) orow[tv + j] = epilogue_dequant(g.ep, acc0[j], c0);
         } else {
           int32_t* orow = reinterpret_cast<int32_t*>(g.out) + row * g.out_ld;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (row_ok && tbase + j < g.T_out) orow[tbase + j] = acc0[j] + c0.bias;
+          for (int j = 0; j < 16; ++j)
+            if (row_ok && tv + j < g.T_out) orow[tv + j] = acc0[j] + c0.bias;
         }
       }
       tc_fence_before();

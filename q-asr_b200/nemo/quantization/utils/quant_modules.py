@@ -275,8 +275,10 @@ class QuantConv1d(Module):
                 if self.groups != 1:
                     raise NotImplementedError("grouped (non-depthwise) quantised convolution")
                 packed = _ops.pack_weights(w8)
-            self._prep = dict(s_w=s_w, w_int=w_int, w8=w8.reshape(self.out_channels, -1) if depthwise else w8,
-                              packed=packed, bias=bias, depthwise=depthwise)
+            if depthwise:
+                w8 = _ops.pack_dw_weights(w8.reshape(self.out_channels, -1), self.stride[0], self.dilation[0],
+                                          self.padding[0])
+            self._prep = dict(s_w=s_w, w_int=w_int, w8=w8, packed=packed, bias=bias, depthwise=depthwise)
             self._prep_key = key
             self.weight_integer = w_int
             self.conv_scaling_factor = s_w

@@ -50,6 +50,8 @@ _SIGS = {
     "qasr_sm_count": (C.c_int, []),
     "qasr_dwconv1d_i8": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                    _i32, C.POINTER(Epilogue), _vp]),
+    "qasr_dw_packed_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32]),
+    "qasr_pack_dw_weights": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "qasr_conv1d_gemm_i8": (C.c_int, [C.POINTER(GemmOperand), C.POINTER(GemmOperand), _vp, _i32, _i32,
                                       _i32, _i32, C.POINTER(Epilogue), _vp]),
     "qasr_packed_weight_bytes": (_i64, [_i32, _i32, _i32]),

@@ -52,6 +52,19 @@ def dwconv(x, T_in, w, out, T_out, k, stride, dilation, pad, ep):
     return out
 
 
+def pack_dw_weights(w_int8, stride, dilation, pad):
+    """w_int8: [C][k] int8 cuda -> banded A-fragment table for qasr_dwconv1d_i8."""
+    Cn, k = w_int8.shape
+    nbytes = int(L.load_library().qasr_dw_packed_bytes(Cn, k, stride, dilation, pad))
+    if nbytes <= 0:
+        raise NotImplementedError("qasr: depthwise conv k=%d stride=%d dilation=%d pad=%d exceeds the supported "
+                                  "tap window" % (k, stride, dilation, pad))
+    wp = torch.empty(nbytes, dtype=torch.int8, device=w_int8.device)
+    L.check(L.lib().qasr_pack_dw_weights(L.ptr(w_int8.contiguous()), L.ptr(wp), Cn, k, stride, dilation, pad,
+                                         L.stream_ptr()))
+    return wp
+
+
 def packed_weight_bytes(c_out, c_in, k):
     return int(L.load_library().qasr_packed_weight_bytes(c_out, c_in, k))
 

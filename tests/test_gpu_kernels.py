@@ -253,7 +253,7 @@ def test_dwconv_requant(case, fast):
     lens = r.integers(T_out // 2, T_out + 1, B).astype(np.int32)
     want = expected_requant(acc, m, e, -128, 127, lens=lens)
     x = to_codes_tensor(q, signed)
-    wd = torch.from_numpy(w[:, 0, :].astype(np.int8)).to(DEV).contiguous()
+    wd = ops.pack_dw_weights(torch.from_numpy(w[:, 0, :].astype(np.int8)).to(DEV).contiguous(), stride, dil, pad)
     ch = ops.chan_table(r.uniform(1e-5, 1e-3, Cn).astype(np.float32), None, m, e, DEV)
     flags = L.F_MASK | (L.F_B_SIGNED if signed else 0)
     if not fast:
@@ -275,7 +275,7 @@ def test_dwconv_raw_and_dequant():
     w = r.integers(-127, 127, (Cn, 1, k))
     acc = O.conv1d_int(q, w, None, 1, k // 2, 1, Cn)
     x = to_codes_tensor(q, False)
-    wd = torch.from_numpy(w[:, 0, :].astype(np.int8)).to(DEV).contiguous()
+    wd = ops.pack_dw_weights(torch.from_numpy(w[:, 0, :].astype(np.int8)).to(DEV).contiguous(), 1, 1, k // 2)
     s_out = r.uniform(1e-5, 1e-3, Cn).astype(np.float32)
     ch = ops.chan_table(s_out, None, np.full(Cn, 2 ** 30), np.full(Cn, 30), DEV)
     out = torch.zeros((B, Cn, ops.round_up(T, 16)), dtype=torch.int32, device=DEV)
@@ -385,7 +385,7 @@ def test_error_paths():
     x = ops.alloc_codes(1, 8, 32, DEV)
     ch = ops.chan_table(np.ones(8, np.float32), None, np.full(8, 2 ** 30), np.full(8, 30), DEV)
     with pytest.raises(ValueError):
-        ops.dwconv(x, 32, torch.zeros((8, 5), dtype=torch.int8, device=DEV), x, 32, 5, 3, 1, 2,
+        ops.dwconv(x, 32, torch.zeros(8 * 128 * 4, dtype=torch.int8, device=DEV), x, 32, 5, 3, 1, 2,
                    ops.make_epilogue(L.EPI_REQUANT_I8, ch))
     with pytest.raises(ValueError):
         ops.quantile2_f32(torch.zeros((1, 1, 8), device=DEV), 1.5, 0.5)
