@@ -130,6 +130,16 @@ def kernel_breakdown(plan, flush, iters=3):
     return classes
 
 
+def apply_debug_knobs():
+    """QASR_DEBUG="4=1,5=1" -> qasr_debug_set(4, 1), (5, 1): schedule experiments only."""
+    spec = os.environ.get("QASR_DEBUG")
+    if spec:
+        from qasr import _lib
+        for kv in spec.split(","):
+            k, v = kv.split("=")
+            _lib.lib().qasr_debug_set(int(k), int(v))
+
+
 def run_ours(args):
     distributed = "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1
     rank = int(os.environ.get("RANK", "0"))
@@ -144,6 +154,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     wl = WORKLOAD
     from qasr.params import synthetic_features
+    apply_debug_knobs()
     model = build_model(device, wl)
     B, T = wl["batch"], wl["frames"]
     x_host, lens_host = synthetic_features(B, T, seed=1000 + rank)

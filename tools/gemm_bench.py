@@ -1,0 +1,42 @@
+"""Micro-benchmark of the tensor-core GEMM kernel on the benchmark workload's layer shapes, with the
+bring-up knobs (qasr_debug_set) to separate load / MMA / epilogue / store costs."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "q-asr_b200")]
+import numpy as np, torch
+from qasr import _lib as L, ops
+dev = "cuda:0"
+lib = L.lib()
+B, T = 64, 800
+FLUSH = False
+def run(ci, co, dual, knobs, iters=20, ld=None):
+    ld = ld or T
+    x = torch.randint(0, 127, (B, ci, ld), dtype=torch.int8, device=dev)
+    x1 = torch.randint(0, 127, (B, ci, ld), dtype=torch.int8, device=dev)
+    w = torch.randint(-30, 30, (co, ci, 1), dtype=torch.int8, device=dev)
+    wp, wp1 = ops.pack_weights(w), ops.pack_weights(w)
+    m = np.full(co, (1 << 30) + 12345); e = np.full(co, 44)
+    ch = ops.chan_table(np.full(co, 1e-4, np.float32), np.zeros(co), m, e, dev)
+    flags = L.F_RELU1 | (L.F_STAGE2 if dual else 0) | L.F_RELU0 * (not dual)
+    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=flags, ch1=ch if dual else None, qmin=-128, qmax=127,
+                           m2=(1 << 30) + 777, e2=30, qmin2=-256, qmax2=255)
+    out = torch.zeros((B, co, ld), dtype=torch.int8, device=dev)
+    op0 = ops.gemm_operand(x, T, wp, ci, 1); op1 = ops.gemm_operand(x1, T, wp1, ci, 1) if dual else None
+    for k, v in knobs.items(): lib.qasr_debug_set(k, v)
+    for _ in range(3): ops.conv_gemm(op0, op1, out, B, co, T, ep)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters): ops.conv_gemm(op0, op1, out, B, co, T, ep)
+    g.replay(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g.replay(); b.record(); b.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3 / iters)
+    for k in knobs: lib.qasr_debug_set(k, -1)
+    return np.median(ts)
+for (ci, co, dual) in ((512, 512, False), (512, 512, True), (256, 256, False)):
+    for name, knobs in (("default", {}), ("MT=1", {5: 1}), ("stream", {4: 1}), ("stream MT=1", {4: 1, 5: 1}),
+                        ("no-epilogue", {6: 1}), ("no-mma", {6: 2}), ("no-store", {6: 4}), ("no-epi no-mma", {6: 3})):
+        print("%4dx%4d dual=%d %-14s %7.1f us" % (ci, co, dual, name, run(ci, co, dual, knobs)), flush=True)
