@@ -143,6 +143,27 @@ int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm_operand* o
                         void* out, int32_t out_ld, int32_t B, int32_t C_out, int32_t T_out,
                         const qasr_epilogue* epi, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * K2b  the same convolution on CHANNELS-LAST codes [B][T][ld] (ld = channel pitch, % 16 == 0):
+ *      any k / dilation, stride 1|2 -- Jasper's dense k = 11..29 convs and strided head
+ *      (quant_modules.py:301-305).  TMA cannot fetch time-shifted boxes from the (B,C,T) layout
+ *      (16-byte alignment of the contiguous coordinate), so networks with dense k > 1 convs keep
+ *      their int8 activations channels-last.  Same packed weights, same epilogue; `prev` and a
+ *      REQUANT output are channels-last [B][T_out][ld], DEQUANT_F32 / RAW_I32 outputs are written
+ *      in the reference's (B, C_out, T_out) layout (out_ld = time pitch).
+ * ---------------------------------------------------------------------------------- */
+int qasr_conv1d_ntc_i8(const qasr_gemm_operand* op0, const qasr_gemm_operand* op1,
+                       void* out, int32_t out_ld, int32_t B, int32_t C_out, int32_t T_out,
+                       const qasr_epilogue* epi, void* stream);
+
+/* (B,C,T) float32 -> channels-last int8 codes [B][T][c_ld].
+ *   mode 0: first-layer SymmetricQuantFunction clamp(rne((1/s)*x), -n, n-1) (quant_modules.py:180-184)
+ *   mode 1: codes of an already quantised tensor rne(x / s)                 (quant_modules.py:301)
+ *   t >= lens[b] -> code 0 when lens != NULL. */
+int qasr_quantize_f32_ntc(const float* x, int32_t x_ld, const float* scale, int32_t mode, int32_t bit,
+                          int8_t* codes, int32_t c_ld, int32_t B, int32_t C, int32_t T,
+                          const int32_t* lens, void* stream);
+
 /* Bytes of the packed weight buffer for (C_out, C_in, k). */
 int64_t qasr_packed_weight_bytes(int32_t C_out, int32_t C_in, int32_t k);
 /* w [C_out][C_in][k] int8 (torch Conv1d layout) -> packed.  Device to device. */

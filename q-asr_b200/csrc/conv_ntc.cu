@@ -1,0 +1,445 @@
+// K2b: dense 1-D convolution (any k, stride, dilation; groups == 1) on channels-last 8-bit codes
+// [B][T][C] as an implicit int8 GEMM on tcgen05 -- Jasper's k = 11..29 convs, its strided head, and any
+// 1x1 conv of a channels-last network.  Restates F.conv1d(x_int.double(), w_int.double(), bias) of
+// QuantConv1d.int_conv (nemo/quantization/utils/quant_modules.py:301-305).
+//
+// Why a second layout: TMA needs a 16-byte aligned box start along the contiguous axis (measured: an
+// unaligned inner coordinate faults), so in the reference's (B,C,T) layout the conv taps cannot be fetched
+// as time-shifted boxes.  With channels contiguous the tap shift moves the NON-contiguous (time)
+// coordinate, which may be any integer, negative or past the end (zero filled = the conv padding), and a
+// strided conv is a TMA traversal stride on that axis.
+//
+// GEMM view per utterance:  D[T_out, C_out] = sum_tap X[T_out*s + tap*d - pad, C_in] * W_tap[C_in, C_out]
+//   A operand = activation box 128 frames x 128 channels, K-major, 128B swizzle (3-D TMA, time coordinate
+//               shifted per tap)
+//   B operand = packed weights [tap][C_out_pad][C_in_pad] (same packing as K2), K-major, 128B swizzle
+//   D         = int32 in TMEM: lanes = frames, columns = output channels; epilogue threads own one frame
+//               and walk 16 channels at a time -> 16-byte stores into the channels-last output.  Per-channel
+//               epilogue parameters sit in a shared-memory table (broadcast reads).
+// Pipeline / warp roles as in gemm_tc.cu (TMA producer, MMA issuer, TMEM allocator, 16 epilogue warps,
+// double-buffered TMEM, optional second operand pair for the residual 1x1 conv + res_act).
+#include <cuda.h>
+
+#include "qasr_common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace qasr_tc;
+
+constexpr int BM = 128, BN = 128, BK = 128;
+constexpr int kStages = 5;
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = 128 + 32 * kEpiWarps;
+constexpr uint32_t kABytes = BM * BK, kBBytes = BN * BK;
+constexpr uint32_t kStageBytes = kABytes + kBBytes;
+constexpr uint32_t kTabBytes = 2 /*operands*/ * 2 /*fast, exact*/ * BN * 16;
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kTabBytes;
+constexpr uint32_t kTmemCols = 512;
+
+struct Seg {
+  int taps, cblocks, stride, dil, pad, c_out_pad;
+  uint32_t idesc;
+};
+
+struct Args {
+  void* out;
+  int out_ld, out_nct, B, C_out, T_out;
+  int nseg, t_tiles, c_tiles, total_tiles;
+  Seg seg[2];
+  EpiArgs ep;
+};
+
+// shared-memory per-channel records (two uint4 per operand and channel)
+__device__ __forceinline__ void store_chan(uint4* fast, uint4* exact, const qasr_chan* tab, int c, int C_out) {
+  int4 v = make_int4(0, 0, 0, 1);
+  if (c < C_out) v = __ldg(reinterpret_cast<const int4*>(tab) + c);
+  const int m = v.z, e = v.w;
+  const long long add = (long long)v.y * (long long)m + ((e >= 1 && e <= 62) ? (1ll << (e - 1)) : 0ll);
+  const double mult = dyad_mult(m, e);
+  *fast = make_uint4((uint32_t)m, (uint32_t)max(e - 32, 0), (uint32_t)(add & 0xffffffffll), (uint32_t)(add >> 32));
+  const long long mb = __double_as_longlong(mult);
+  *exact = make_uint4((uint32_t)v.x, (uint32_t)v.y, (uint32_t)(mb & 0xffffffffll), (uint32_t)(mb >> 32));
+}
+__device__ __forceinline__ ChanRegs load_chan_smem(const uint4* fast, const uint4* exact, bool need_exact) {
+  ChanRegs r;
+  const uint4 f = *fast;
+  r.m = (int)f.x;
+  r.sh = (int)f.y;
+  r.add = (long long)(((unsigned long long)f.w << 32) | f.z);
+  r.e = r.sh + 32;
+  r.s = 0.f;
+  r.bias = 0;
+  r.mult = 0.0;
+  if (need_exact) {
+    const uint4 x = *exact;
+    r.s = __uint_as_float(x.x);
+    r.bias = (int)x.y;
+    r.mult = __longlong_as_double((long long)(((unsigned long long)x.w << 32) | x.z));
+  }
+  return r;
+}
+
+// EPI as in gemm_tc.cu: bit0 fast, bit1 dual, bit2 prev, bit3 stage2; 0 = literal path
+constexpr int kEpiFast = 1, kEpiDual = 2, kEpiPrev = 4, kEpiStage2 = 8;
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmW0,
+                const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmW1, const Args g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + kStages * kStageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+  uint4* tab = reinterpret_cast<uint4*>(gen_base + kStages * kStageBytes + 256);  // [op][fast|exact][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW0) : "memory");
+    if (g.nseg > 1) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX1) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 32 * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const int ct = tile % g.c_tiles;
+        const int rest = tile / g.c_tiles;
+        const int tt = rest % g.t_tiles, b = rest / g.t_tiles;
+        for (int sg = 0; sg < g.nseg; ++sg) {
+          const Seg& s = g.seg[sg];
+          const CUtensorMap* mX = sg == 0 ? &tmX0 : &tmX1;
+          const CUtensorMap* mW = sg == 0 ? &tmW0 : &tmW1;
+          for (int tap = 0; tap < s.taps; ++tap) {
+            const int tcoord = tt * BM * s.stride + tap * s.dil - s.pad;
+            for (int cb = 0; cb < s.cblocks; ++cb) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+              mbar_expect_tx(full_bar(stage), kStageBytes);
+              tma_load_3d(sa, mX, cb * BK, tcoord, b, full_bar(stage));
+              tma_load_2d(sb, mW, cb * BK, tap * s.c_out_pad + ct * BN, full_bar(stage));
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        for (int sg = 0; sg < g.nseg; ++sg) {
+          const Seg& s = g.seg[sg];
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * 2 * BN + sg * BN);
+          const int slabs = s.taps * s.cblocks;
+          for (int it = 0; it < slabs; ++it) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+#pragma unroll
+            for (int kk = 0; kk < BK / 32; ++kk) {
+              const uint64_t adesc = make_smem_desc(sa + kk * 32, 0, 1024);
+              const uint64_t bdesc = make_smem_desc(sb + kk * 32, 0, 1024);
+              tc_mma_i8(d_tmem, adesc, bdesc, s.idesc, (it | kk) != 0 ? 1u : 0u);
+            }
+            tc_commit(empty_bar(stage));
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        tc_commit(tfull_bar(as));
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;          // TMEM lane quarter = 32 frames
+    const int cgroup = (warp - 4) >> 2;    // 32 of the tile's 128 output channels
+    const int etid = threadIdx.x - 128;    // 0..511
+    const EpiConsts kc = make_epi_consts(g.ep, g.nseg > 1);
+    const bool need_exact = !(EPI & kEpiFast);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      const int ct = tile % g.c_tiles;
+      const int rest = tile / g.c_tiles;
+      const int tt = rest % g.t_tiles, b = rest / g.t_tiles;
+      // per-channel parameter table of this channel tile
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");  // previous tile's readers are done
+      if (etid < BN) {
+        store_chan(tab + etid, tab + BN + etid, g.ep.ch0, ct * BN + etid, g.C_out);
+        if (g.nseg > 1) store_chan(tab + 2 * BN + etid, tab + 3 * BN + etid, g.ep.ch1, ct * BN + etid, g.C_out);
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");
+      const int t = tt * BM + quarter * 32 + lane;
+      const bool t_ok = t < g.T_out;
+      const int len = (g.ep.flags & QASR_F_MASK) ? min(g.ep.out_lens[b], g.T_out) : g.T_out;
+      const size_t trow = (size_t)b * g.T_out + (t_ok ? t : 0);
+
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        const int col0 = cgroup * 32 + ch * 16;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * 2 * BN + col0);
+        int acc0[16], acc1[16];
+        tmem_ld16(taddr, acc0);
+        if (g.nseg > 1) tmem_ld16(taddr + BN, acc1);
+        tmem_ld_wait();
+        const int c_first = ct * BN + col0;
+        if (g.ep.mode == QASR_EPI_REQUANT_I8) {
+          uint4 pv = make_uint4(0, 0, 0, 0);
+          if ((EPI == 0 || (EPI & kEpiPrev)) && g.ep.prev != nullptr && t_ok && c_first < g.C_out)
+            pv = *reinterpret_cast<const uint4*>(g.ep.prev + trow * g.ep.prev_ld + c_first);
+          const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+          uint32_t packed[4];
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) {
+            int q[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j = 4 * w4 + i;
+              const ChanRegs c0 = load_chan_smem(tab + col0 + j, tab + BN + col0 + j, need_exact);
+              ChanRegs c1 = c0;
+              if (EPI == 0 ? g.nseg > 1 : (EPI & kEpiDual) != 0)
+                c1 = load_chan_smem(tab + 2 * BN + col0 + j, tab + 3 * BN + col0 + j, need_exact);
+              const int prev = (int)(int8_t)((pw[w4] >> (8 * i)) & 0xff);
+              if (EPI & kEpiFast)
+                q[i] = epilogue_fast<(EPI & kEpiDual) != 0, (EPI & kEpiPrev) != 0, (EPI & kEpiStage2) != 0>(
+                    g.ep, kc, acc0[j], c0, (EPI & kEpiDual) ? acc1[j] : 0, c1, prev);
+              else
+                q[i] = epilogue_exact(g.ep, kc, acc0[j], c0, g.nseg > 1, g.nseg > 1 ? acc1[j] : 0, c1, prev);
+            }
+            packed[w4] = pack4(q[0], q[1], q[2], q[3]);
+          }
+          if (t >= len) packed[0] = packed[1] = packed[2] = packed[3] = 0u;  // jasper.py:177-181
+          if (t_ok && c_first < g.C_out) {
+            uint8_t* orow = reinterpret_cast<uint8_t*>(g.out) + trow * g.out_ld;
+            *reinterpret_cast<uint4*>(orow + c_first) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          }
+        } else {
+          // float32 / int32 outputs go to the reference's (B, C, T) layout: consecutive lanes = consecutive
+          // frames of one channel -> coalesced
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c = c_first + j;
+            if (!t_ok || c >= g.C_out) continue;
+            const ChanRegs c0 = load_chan_smem(tab + col0 + j, tab + BN + col0 + j, true);
+            const size_t o = ((size_t)b * g.C_out + c) * g.out_ld + t;
+            if (g.ep.mode == QASR_EPI_DEQUANT_F32)
+              reinterpret_cast<float*>(g.out)[o] = epilogue_dequant(g.ep, acc0[j], c0);
+            else
+              reinterpret_cast<int32_t*>(g.out)[o] = acc0[j] + c0.bias;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+int make_map_weights(CUtensorMap* map, const int8_t* wp, int rows, int c_in_pad) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { qasr_set_error("cuTensorMapEncodeTiled entry point not available"); return QASR_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)c_in_pad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)c_in_pad};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(wp), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { qasr_set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return QASR_ERR_CUDA; }
+  return QASR_OK;
+}
+
+// activations [B][T][ld]: dims (C, T, B); the time axis carries the conv stride as a traversal stride
+int make_map_acts(CUtensorMap* map, const void* x, int C, int T, int B, int ld, int stride) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { qasr_set_error("cuTensorMapEncodeTiled entry point not available"); return QASR_ERR_CUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)ld * (cuuint64_t)T};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(BM * stride), 1};
+  cuuint32_t estr[3] = {1, (cuuint32_t)stride, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { qasr_set_error("cuTensorMapEncodeTiled(activations, channels-last) failed: %d", (int)r); return QASR_ERR_CUDA; }
+  return QASR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// (B,C,T) float32 -> channels-last int8 codes, tile transpose through shared memory
+//   mode 0: first-layer SymmetricQuantFunction  clamp(rne((1/s) * x), -n, n-1)   (quant_modules.py:180-184)
+//   mode 1: codes of an already quantised tensor  rne(x / s)                      (quant_modules.py:301)
+// ---------------------------------------------------------------------------------------------
+__global__ void quantize_ntc_kernel(const float* __restrict__ x, int x_ld, const float* scale, int mode, int n,
+                                    int8_t* __restrict__ codes, int c_ld, int B, int C, int T,
+                                    const int32_t* lens) {
+  __shared__ int8_t tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const float s = scale[0];
+  const float inv = __fdiv_rn(1.0f, s);
+  const int len = lens ? lens[b] : T;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    float v = 0.f;
+    if (c < C && t < T && t < len) v = x[((size_t)b * C + c) * x_ld + t];
+    float r;
+    if (mode == 0) r = fminf(fmaxf(rintf(__fmul_rn(inv, v)), (float)(-n)), (float)(n - 1));
+    else r = rintf(__fdiv_rn(v, s));
+    tile[i][threadIdx.x] = (int8_t)(int)r;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T && c < c_ld) codes[((size_t)b * T + t) * c_ld + c] = c < C ? tile[threadIdx.x][i] : (int8_t)0;
+  }
+}
+
+}  // namespace
+
+extern "C" int qasr_quantize_f32_ntc(const float* x, int32_t x_ld, const float* scale, int32_t mode, int32_t bit,
+                                     int8_t* codes, int32_t c_ld, int32_t B, int32_t C, int32_t T,
+                                     const int32_t* lens, void* stream) {
+  QASR_CHECK_ARG(x && scale && codes, "quantize_f32_ntc: null pointer");
+  QASR_CHECK_ARG(B > 0 && C > 0 && T > 0 && x_ld >= T && c_ld >= C && c_ld % 16 == 0, "quantize_f32_ntc: bad shape / pitch");
+  QASR_CHECK_ARG(mode == 0 || mode == 1, "quantize_f32_ntc: mode");
+  QASR_CHECK_ARG(mode == 1 || (bit >= 2 && bit <= 8), "quantize_f32_ntc: activation_bit %d not in [2, 8]", bit);
+  QASR_CHECK_ARG(B <= 65535, "quantize_f32_ntc: B too large");
+  dim3 grid((T + 31) / 32, (c_ld + 31) / 32, B), block(32, 8);
+  quantize_ntc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, x_ld, scale, mode, (1 << (bit - 1)) - 1, codes,
+                                                               c_ld, B, C, T, lens);
+  return qasr_check_launch("quantize_ntc_kernel");
+}
+
+extern "C" int qasr_conv1d_ntc_i8(const qasr_gemm_operand* op0, const qasr_gemm_operand* op1, void* out,
+                                  int32_t out_ld, int32_t B, int32_t C_out, int32_t T_out,
+                                  const qasr_epilogue* epi, void* stream) {
+  QASR_CHECK_ARG(op0 && out && epi, "conv1d_ntc: null pointer");
+  QASR_CHECK_ARG(B > 0 && C_out > 0 && T_out > 0, "conv1d_ntc: bad shape");
+  int rc = qasr_validate_epilogue(epi, true);
+  if (rc) return rc;
+  QASR_CHECK_ARG((op1 != nullptr) == (epi->ch1 != nullptr), "conv1d_ntc: second operand and epi->ch1 must come together");
+  QASR_CHECK_ARG(!op1 || epi->mode == QASR_EPI_REQUANT_I8, "conv1d_ntc: second operand needs REQUANT mode");
+  if (epi->mode == QASR_EPI_REQUANT_I8) {
+    QASR_CHECK_ARG(qasr_aligned16(out) && out_ld % 16 == 0 && out_ld >= round_up(C_out, 16),
+                   "conv1d_ntc: channels-last output pitch must be a multiple of 16 covering C_out");
+  } else {
+    QASR_CHECK_ARG(out_ld >= T_out, "conv1d_ntc: (B,C,T) output pitch must cover T_out");
+  }
+  Args g;
+  memset(&g, 0, sizeof(g));
+  CUtensorMap maps[4];
+  memset(maps, 0, sizeof(maps));
+  const qasr_gemm_operand* ops[2] = {op0, op1};
+  g.nseg = op1 ? 2 : 1;
+  for (int i = 0; i < g.nseg; ++i) {
+    const qasr_gemm_operand* o = ops[i];
+    QASR_CHECK_ARG(o->x && o->wp && o->C_in > 0 && o->T_in > 0 && o->k > 0, "conv1d_ntc: operand %d bad", i);
+    QASR_CHECK_ARG(o->stride >= 1 && o->stride <= 2 && o->dilation >= 1 && o->pad >= 0, "conv1d_ntc: stride/dilation/pad");
+    QASR_CHECK_ARG((o->T_in + 2 * o->pad - o->dilation * (o->k - 1) - 1) / o->stride + 1 == T_out,
+                   "conv1d_ntc: operand %d: T_out %d inconsistent with T_in %d", i, T_out, o->T_in);
+    QASR_CHECK_ARG(o->x_ld % 16 == 0 && o->x_ld >= o->C_in && qasr_aligned16(o->x) && qasr_aligned16(o->wp),
+                   "conv1d_ntc: operand %d channel pitch / alignment", i);
+    Seg& s = g.seg[i];
+    s.taps = o->k;
+    s.cblocks = (o->C_in + BK - 1) / BK;
+    s.stride = o->stride;
+    s.dil = o->dilation;
+    s.pad = o->pad;
+    s.c_out_pad = round_up(C_out, BN);
+    const uint32_t a_signed = (epi->flags & (i == 0 ? QASR_F_B_SIGNED : QASR_F_B1_SIGNED)) ? 1u : 0u;
+    // D=S32, A = activations (un)signed K-major, B = weights signed K-major, N=128, M=128
+    s.idesc = (2u << 4) | (a_signed << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    rc = make_map_acts(&maps[2 * i], o->x, o->C_in, o->T_in, B, o->x_ld, o->stride);
+    if (rc) return rc;
+    rc = make_map_weights(&maps[2 * i + 1], o->wp, o->k * s.c_out_pad, round_up(o->C_in, BK));
+    if (rc) return rc;
+  }
+  if (g.nseg == 1) { maps[2] = maps[0]; maps[3] = maps[1]; }
+  g.out = out;
+  g.out_ld = out_ld;
+  g.B = B;
+  g.C_out = C_out;
+  g.T_out = T_out;
+  g.t_tiles = (T_out + BM - 1) / BM;
+  g.c_tiles = (C_out + BN - 1) / BN;
+  g.total_tiles = g.t_tiles * g.c_tiles * B;
+  g.ep = make_epi_args(epi);
+  const bool fast = !(epi->flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64)) &&
+                    epi->mode == QASR_EPI_REQUANT_I8;
+  int variant = 0;
+  if (fast)
+    variant = kEpiFast | (op1 ? kEpiDual : 0) | (epi->prev ? kEpiPrev : 0) | ((epi->flags & QASR_F_STAGE2) ? kEpiStage2 : 0);
+  int grid = qasr_sm_count();
+  if (grid > g.total_tiles) grid = g.total_tiles;
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr_set[16][64] = {};
+  int dev = 0;
+  QASR_CHECK_CUDA(cudaGetDevice(&dev));
+  const bool need_attr = dev >= 0 && dev < 64 && !attr_set[variant][dev];
+#define QASR_NTC_CASE(V_)                                                                                      \
+  case V_:                                                                                                     \
+    if (need_attr)                                                                                             \
+      QASR_CHECK_CUDA(cudaFuncSetAttribute(conv_ntc_kernel<V_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                           (int)kSmemBytes));                                                  \
+    conv_ntc_kernel<V_><<<grid, kThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);            \
+    break;
+  switch (variant) {
+    QASR_NTC_CASE(0)
+    QASR_NTC_CASE(1)
+    QASR_NTC_CASE(3)
+    QASR_NTC_CASE(5)
+    QASR_NTC_CASE(7)
+    QASR_NTC_CASE(9)
+    QASR_NTC_CASE(11)
+    QASR_NTC_CASE(13)
+    QASR_NTC_CASE(15)
+    default:
+      qasr_set_error("conv1d_ntc: internal: no kernel variant %d", variant);
+      return QASR_ERR_INVALID;
+  }
+#undef QASR_NTC_CASE
+  if (need_attr) attr_set[variant][dev] = true;
+  return qasr_check_launch("conv_ntc_kernel");
+}

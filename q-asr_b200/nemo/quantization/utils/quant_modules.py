@@ -301,9 +301,10 @@ class QuantConv1d(Module):
         B, Cin, T = x.shape
         if input_unsigned is None:
             input_unsigned = bool((x.min() >= 0).item())                # auto mode: one host sync
-        codes = _ops.codes_from_f32(x, s_x)
         k, stride, dil, pad = self.kernel_size[0], self.stride[0], self.dilation[0], self.padding[0]
         T_out = (T + 2 * pad - dil * (k - 1) - 1) // stride + 1
+        channels_last = not p["depthwise"] and (k > 1 or stride > 1)
+        codes = _ops.quantize_f32_ntc(x, s_x, 1) if channels_last else _ops.codes_from_f32(x, s_x)
         tab = torch.stack([s_out.contiguous().view(torch.int32), b_i32,
                            torch.full_like(b_i32, 1 << 30), torch.full_like(b_i32, 30)], dim=1).contiguous()
         flags = _L.F_BIAS64 | (0 if input_unsigned else _L.F_B_SIGNED)
@@ -312,6 +313,9 @@ class QuantConv1d(Module):
                           device=x.device)
         if p["depthwise"]:
             _ops.dwconv(codes, T, p["w8"], out, T_out, k, stride, dil, pad, ep)
+        elif channels_last:  # dense k > 1 / strided conv: channels-last implicit GEMM, (B,C,T) float out
+            _ops.conv_ntc(_ops.gemm_operand(codes, T, p["packed"], Cin, k, stride, dil, pad), None, out, B,
+                          self.out_channels, T_out, ep)
         else:
             _ops.conv_gemm(_ops.gemm_operand(codes, T, p["packed"], Cin, k, stride, dil, pad), None, out, B,
                            self.out_channels, T_out, ep)

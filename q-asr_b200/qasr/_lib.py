@@ -54,6 +54,9 @@ _SIGS = {
     "qasr_pack_dw_weights": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "qasr_conv1d_gemm_i8": (C.c_int, [C.POINTER(GemmOperand), C.POINTER(GemmOperand), _vp, _i32, _i32,
                                       _i32, _i32, C.POINTER(Epilogue), _vp]),
+    "qasr_conv1d_ntc_i8": (C.c_int, [C.POINTER(GemmOperand), C.POINTER(GemmOperand), _vp, _i32, _i32,
+                                     _i32, _i32, C.POINTER(Epilogue), _vp]),
+    "qasr_quantize_f32_ntc": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "qasr_packed_weight_bytes": (_i64, [_i32, _i32, _i32]),
     "qasr_pack_conv_weights": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "qasr_quantize_f32": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp]),

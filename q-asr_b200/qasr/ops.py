@@ -94,6 +94,29 @@ def conv_gemm(op0, op1, out, B, c_out, T_out, ep):
     return out
 
 
+def conv_ntc(op0, op1, out, B, c_out, T_out, ep):
+    """Channels-last implicit GEMM (any k / stride / dilation); operands are [B][T][ld] code tensors."""
+    L.check(L.lib().qasr_conv1d_ntc_i8(C.byref(op0), C.byref(op1) if op1 is not None else None,
+                                       L.ptr(out), out.shape[-1], B, c_out, T_out, C.byref(ep),
+                                       L.stream_ptr()))
+    return out
+
+
+def alloc_codes_ntc(B, Cn, T, device):
+    """Zero-initialised channels-last code tensor [B][T][ld], ld = C rounded up to 16."""
+    return torch.zeros((B, T, round_up(Cn, 16)), dtype=torch.int8, device=device)
+
+
+def quantize_f32_ntc(x, scale, mode, bit=8, lens=None):
+    """(B,C,T) float -> channels-last codes; mode 0 = first-layer quantiser, 1 = rne(x / s)."""
+    B, Cn, T = x.shape
+    x = x.contiguous()
+    codes = alloc_codes_ntc(B, Cn, T, x.device)
+    L.check(L.lib().qasr_quantize_f32_ntc(L.ptr(x), T, L.ptr(scale), mode, bit, L.ptr(codes), codes.shape[-1],
+                                          B, Cn, T, L.ptr(lens), L.stream_ptr()))
+    return codes
+
+
 def quantize_f32(x, scale, bit, lens=None, want_codes=True, want_float=True):
     B, Cn, T = x.shape
     x = x.contiguous()

@@ -137,10 +137,18 @@ class ReluOf(Val):
 
 
 class QTensor:
-    """A materialised int8 tensor: value `val` quantised by `info` (None: plain res_act codes)."""
+    """A materialised int8 tensor: value `val` quantised by `info` (None: plain res_act codes).
+    Layout [B][C][ld] (time contiguous) or, in channels-last plans, [B][T][ld]."""
 
-    def __init__(self, val, info, tensor, signed, scale, qabs):
+    def __init__(self, val, info, tensor, signed, scale, qabs, ntc=False):
         self.val, self.info, self.tensor, self.signed, self.scale, self.qabs = val, info, tensor, signed, scale, qabs
+        self.ntc = ntc
+
+    def codes_bct(self):
+        """Integer codes as a (B, C, T) int64 numpy array (tests / debugging)."""
+        t = self.tensor
+        a = (t[:, :self.val.T, :self.val.C].permute(0, 2, 1) if self.ntc else t[:, :, :self.val.T]).cpu().numpy()
+        return a.astype(np.int64) if self.signed else a.view(np.uint8).astype(np.int64)
 
 
 class ConvParams:
@@ -184,6 +192,7 @@ class FusedPlan:
         self._keep = []
         self.verbose = verbose
         B = self.B
+        self.ntc = self._needs_channels_last()
         self.x_in = torch.zeros((B, self.C_in, self.T), dtype=torch.float32, device=self.device)
         self.lens = [torch.zeros(B, dtype=torch.int32, device=self.device)]   # per length stage
         self._lens_fns = []
@@ -191,6 +200,20 @@ class FusedPlan:
         self.graph = None
         self.use_graph = use_graph
         self._warm = False
+
+    def _needs_channels_last(self):
+        """Dense k > 1 / strided convs (Jasper) run on the channels-last implicit-GEMM kernel; such a
+        network keeps all its int8 activations channels-last."""
+        from nemo.quantization.utils.quant_modules import QuantConv1d
+        dense = depthwise = False
+        for m in self.encoder.modules():
+            if type(m) is QuantConv1d:
+                dw = m.groups == m.in_channels == m.out_channels and m.groups > 1
+                depthwise |= dw
+                dense |= (not dw) and (m.kernel_size[0] > 1 or m.stride[0] > 1)
+        if dense and depthwise:
+            raise NotImplementedError("networks mixing depthwise and dense k>1 convolutions")
+        return dense
 
     # -- symbolic walk (conv_asr.py:194-206, jasper.py:641-692) ----------------------------
     def _build(self):
@@ -255,6 +278,8 @@ class FusedPlan:
 
     # -- materialisation -------------------------------------------------------------------
     def _alloc(self, C, T):
+        if self.ntc:
+            return ops.alloc_codes_ntc(self.B, C, T, self.device)
         return ops.alloc_codes(self.B, C, T, self.device)
 
     def _quantized(self, val, info, first_layer=False):
@@ -282,11 +307,16 @@ class FusedPlan:
         x_in, B, C, T, bit = self.x_in, self.B, val.C, val.T, info.bit
         lib = L.lib()
 
-        def run():
-            L.check(lib.qasr_quantize_f32(L.ptr(x_in), T, L.ptr(scale), bit, L.ptr(out), out.shape[-1], None,
-                                          B, C, T, L.ptr(lens), L.stream_ptr()))
+        if self.ntc:
+            def run():
+                L.check(lib.qasr_quantize_f32_ntc(L.ptr(x_in), T, L.ptr(scale), 0, bit, L.ptr(out), out.shape[-1],
+                                                  B, C, T, L.ptr(lens), L.stream_ptr()))
+        else:
+            def run():
+                L.check(lib.qasr_quantize_f32(L.ptr(x_in), T, L.ptr(scale), bit, L.ptr(out), out.shape[-1], None,
+                                              B, C, T, L.ptr(lens), L.stream_ptr()))
         self._add("quantize_input", run, nbytes=B * C * T * 5)
-        return QTensor(val, info, out, True, info.scale, info.n)
+        return QTensor(val, info, out, True, info.scale, info.n, self.ntc)
 
     def _strip(self, val):
         relu = False
@@ -329,7 +359,7 @@ class FusedPlan:
             self._emit_resact(base, ra, out, flags, fast2, stage2, lens)
         else:
             raise NotImplementedError(type(base))
-        return QTensor(val, info, out, signed, info.scale, max(abs(qmin), abs(qmax)) if signed else qmax)
+        return QTensor(val, info, out, signed, info.scale, max(abs(qmin), abs(qmax)) if signed else qmax, self.ntc)
 
     def _plain_resact(self, val):
         """res_act codes before the block ReLU (input of the next res_act in a dense-residual chain)."""
@@ -339,7 +369,7 @@ class FusedPlan:
             ra = ActInfo(val.act, False)
             out = self._alloc(val.C, val.T)
             self._emit_resact(val, ra, out, 0, True, {}, None)
-            qt = QTensor(val, None, out, True, ra.scale, ra.n + 1)
+            qt = QTensor(val, None, out, True, ra.scale, ra.n + 1, self.ntc)
             self._q[key] = qt
             self._keep.append(val)
         return qt
@@ -407,7 +437,7 @@ class FusedPlan:
         B, lib = self.B, L.lib()
         C_out, T_out = v0.conv.out_channels, v0.T
         if cp0.depthwise:
-            assert len(operands) == 1
+            assert len(operands) == 1 and not self.ntc
             x, T_in = v0.src.tensor, v0.src.val.T
             w8, k, s, d, p = cp0.w8, cp0.k, cp0.stride, cp0.dil, cp0.pad
             import ctypes as C
@@ -424,10 +454,11 @@ class FusedPlan:
                                              cp.stride, cp.dil, cp.pad))
             import ctypes as C
             op1 = C.byref(gops[1]) if len(gops) > 1 else None
+            entry = lib.qasr_conv1d_ntc_i8 if self.ntc else lib.qasr_conv1d_gemm_i8
 
             def run():
-                L.check(lib.qasr_conv1d_gemm_i8(C.byref(gops[0]), op1, L.ptr(out), out.shape[-1], B, C_out,
-                                                T_out, C.byref(ep), L.stream_ptr()))
+                L.check(entry(C.byref(gops[0]), op1, L.ptr(out), out.shape[-1], B, C_out, T_out, C.byref(ep),
+                              L.stream_ptr()))
             nbytes = B * C_out * T_out * out.element_size() + (B * C_out * T_out if ep.prev else 0)
             macs = 0
             for (v, cp, _, _) in operands:

@@ -33,6 +33,20 @@ def to_codes_tensor(q, signed):
     return t
 
 
+def to_ntc_tensor(q, signed):
+    """int array (B,C,T) -> channels-last zero padded device tensor [B][T][ld]."""
+    B, Cn, T = q.shape
+    t = ops.alloc_codes_ntc(B, Cn, T, DEV)
+    arr = q.astype(np.int8) if signed else q.astype(np.uint8).view(np.int8)
+    t[:, :, :Cn] = torch.from_numpy(np.ascontiguousarray(arr.transpose(0, 2, 1))).to(DEV)
+    return t
+
+
+def from_ntc_tensor(t, Cn, signed):
+    a = t[:, :, :Cn].permute(0, 2, 1).cpu().numpy()
+    return a.astype(np.int64) if signed else a.view(np.uint8).astype(np.int64)
+
+
 def from_codes_tensor(t, T, signed):
     a = t[:, :, :T].cpu().numpy()
     return a.astype(np.int64) if signed else a.view(np.uint8).astype(np.int64)
@@ -112,6 +126,12 @@ def test_gemm_raw_i32(case):
     if k > 1:  # (B,C,T) layout: TMA cannot fetch unaligned time shifts -> loud refusal, not a fault
         with pytest.raises(NotImplementedError):
             ops.conv_gemm(ops.gemm_operand(x, T, wp, ci, k, 1, dil, pad), None, out, B, co, T_out, ep)
+        # ... and the channels-last implicit GEMM computes it (int32 out in (B,C,T))
+        xn = to_ntc_tensor(q, signed)
+        ops.conv_ntc(ops.gemm_operand(xn, T, wp, ci, k, 1, dil, pad), None, out, B, co, T_out, ep)
+        torch.cuda.synchronize()
+        got = out[:, :, :T_out].cpu().numpy().astype(np.int64)
+        assert np.array_equal(got, want), "ntc mismatches: %d / %d" % ((got != want).sum(), want.size)
         return
     ops.conv_gemm(ops.gemm_operand(x, T, wp, ci, k, 1, dil, pad), None, out, B, co, T_out, ep)
     torch.cuda.synchronize()
@@ -184,6 +204,75 @@ def test_gemm_dual_residual(fast):
     torch.cuda.synchronize()
     got = from_codes_tensor(out, T, signed=False)
     assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
+
+
+NTC_CASES = [
+    # name, B, C_in, C_out, T, k, stride, dil, signed
+    ("ntc_k11_s2_c64", 2, 64, 256, 301, 11, 2, 1, True),
+    ("ntc_k13_c384", 1, 384, 384, 200, 13, 1, 1, False),
+    ("ntc_k29_dil2", 2, 128, 160, 150, 29, 1, 2, False),
+    ("ntc_k1_1024_29", 2, 1024, 29, 77, 1, 1, 1, True),
+    ("ntc_tiny_k5", 3, 32, 48, 40, 5, 1, 1, False),
+]
+
+
+@pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
+@pytest.mark.parametrize("case", NTC_CASES, ids=lambda c: c[0])
+def test_conv_ntc_requant_dual_prev(case, fast):
+    """Channels-last implicit GEMM: main conv (any k / stride / dilation) + residual 1x1 operand + previous
+    res_act codes + block ReLU + second requantisation + length mask, against the oracle arithmetic."""
+    name, B, ci, co, T, k, stride, dil, signed = case
+    r = rng(20)
+    q = r.integers(-128, 128, (B, ci, T)) if signed else r.integers(0, 256, (B, ci, T))
+    w = r.integers(-20, 20, (co, ci, k))
+    bias = r.integers(-3000, 3000, co)
+    pad = (dil * k) // 2 - 1 if dil > 1 else k // 2
+    acc0 = O.conv1d_int(q, w, bias, stride, pad, dil, 1)
+    T_out = acc0.shape[2]
+    ci1 = 64
+    q1 = r.integers(0, 256, (B, ci1, T_out))
+    w1 = r.integers(-60, 60, (co, ci1, 1))
+    acc1 = O.conv1d_int(q1, w1, None, 1, 0, 1, 1)
+    prev = r.integers(-128, 128, (B, co, T_out))
+    m0, e0 = norm_me(*rand_dyadic(r, co, 1e-5, 1e-4))
+    m1, e1 = norm_me(*rand_dyadic(r, co, 1e-5, 2e-4))
+    m2, e2 = norm_me(*O.batch_frexp(np.array([2.01])))
+    lens = r.integers(T_out // 2, T_out + 1, B).astype(np.int32)
+    want = expected_requant(acc0, m0, e0, -128, 127, acc1=acc1, m1=m1, e1=e1, prev=prev, relu1=True,
+                            stage2=(m2[0], e2[0], -256, 255), lens=lens)
+    wp = ops.pack_weights(torch.from_numpy(w.astype(np.int8)).to(DEV))
+    wp1 = ops.pack_weights(torch.from_numpy(w1.astype(np.int8)).to(DEV))
+    one = np.full(co, 1e-4, np.float32)
+    ch0 = ops.chan_table(one, bias, m0, e0, DEV)
+    ch1 = ops.chan_table(one, None, m1, e1, DEV)
+    flags = L.F_RELU1 | L.F_STAGE2 | L.F_MASK | (L.F_B_SIGNED if signed else 0)
+    if not fast:
+        flags |= L.F_EXACT_F32 | L.F_EXACT_DYAD
+    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch0, flags=flags, ch1=ch1, prev=to_ntc_tensor(prev, True), qmin=-128,
+                           qmax=127, m2=m2[0], e2=e2[0], qmin2=-256, qmax2=255,
+                           out_lens=torch.from_numpy(lens).to(DEV))
+    out = ops.alloc_codes_ntc(B, co, T_out, DEV)
+    ops.conv_ntc(ops.gemm_operand(to_ntc_tensor(q, signed), T, wp, ci, k, stride, dil, pad),
+                 ops.gemm_operand(to_ntc_tensor(q1, False), T_out, wp1, ci1, 1), out, B, co, T_out, ep)
+    torch.cuda.synchronize()
+    got = from_ntc_tensor(out, co, signed=False)
+    assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
+
+
+def test_quantize_f32_ntc():
+    r = rng(21)
+    B, Cn, T = 3, 40, 70
+    x = (r.standard_normal((B, Cn, T)) * 2).astype(np.float32)
+    lens = np.array([70, 33, 64], np.int32)
+    s = O.sym_scale(8, -3.3, 2.9).reshape(())
+    xm = np.where(np.arange(T)[None, None, :] < lens[:, None, None], x, 0).astype(np.float32)
+    codes = ops.quantize_f32_ntc(torch.from_numpy(x).to(DEV), torch.tensor([s], device=DEV), 0, 8,
+                                 lens=torch.from_numpy(lens).to(DEV))
+    assert np.array_equal(from_ntc_tensor(codes, Cn, True), O.sym_quantize(xm, 8, s).astype(np.int64))
+    assert int(codes[:, :, Cn:].abs().sum()) == 0
+    z = r.integers(0, 256, (B, Cn, T))
+    codes = ops.quantize_f32_ntc(torch.from_numpy((z * s).astype(np.float32)).to(DEV), torch.tensor([s], device=DEV), 1)
+    assert np.array_equal(from_ntc_tensor(codes, Cn, False), z)
 
 
 def test_gemm_dequant_f32_bigacc():

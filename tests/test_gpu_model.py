@@ -89,8 +89,6 @@ def needs_dense_kernel(case):
 @pytest.mark.parametrize("path", NET_CASES, ids=lambda p: os.path.basename(p)[:-4])
 def test_golden_network_module_level(path):
     case = specio.load(path)
-    if needs_dense_kernel(case):
-        pytest.xfail("dense k>1 convolutions need the channels-last implicit-GEMM kernel (next)")
     model, qm = build_from_case(case)
     model.use_fused_plan = model.encoder.use_fused_plan = False
     x = torch.from_numpy(case["x"]).to(DEV)
@@ -116,8 +114,6 @@ def test_golden_network_module_level(path):
                          ids=lambda p: os.path.basename(p)[:-4])
 def test_golden_network_fused_plan(path):
     case = specio.load(path)
-    if needs_dense_kernel(case):
-        pytest.xfail("dense k>1 convolutions need the channels-last implicit-GEMM kernel (next)")
     model, qm = build_from_case(case)
     set_ranges_from_spec(model, case["spec"])
     qm.evaluate(model)
@@ -141,10 +137,7 @@ def test_golden_network_fused_plan(path):
                 continue
             n = names[id(qt.info.module)].replace("encoder.encoder.", "encoder.")
             ref = case["trace"][n][0]["codes"]
-            T = ref.shape[2]
-            got = qt.tensor[:, :, :T].cpu().numpy()
-            got = got.astype(np.int64) if qt.signed else got.view(np.uint8).astype(np.int64)
-            assert np.array_equal(got, ref), n
+            assert np.array_equal(qt.codes_bct(), ref), n
             checked += 1
         assert checked > 8
     # public API path (EncDecCTCModel.forward picks the plan up by itself)
@@ -197,11 +190,6 @@ def test_golden_quant_conv(case):
     qc = qc.to(DEV)
     s_x = torch.from_numpy(case["s_x"]).to(DEV)
     x = torch.from_numpy(case["in_codes"]).float().to(DEV) * s_x
-    dense = case["groups"] == 1 and (k > 1 or case["stride"] > 1)
-    if dense:
-        with pytest.raises(NotImplementedError):
-            qc(x, s_x)
-        pytest.xfail("dense k>1 convolutions need the channels-last implicit-GEMM kernel (next)")
     out, sf = qc(x, s_x)
     assert np.array_equal(qc.weight_integer.cpu().numpy().astype(np.int32), case["weight_integer"])
     assert np.array_equal(qc.conv_scaling_factor.cpu().numpy(), case["conv_scaling_factor"])
@@ -280,9 +268,7 @@ def test_quartznet15x5_static_vs_oracle(quartznet, wbit, abit, percentile):
             ref = by_name["decoder"]["in_codes"]
         else:
             continue
-        got = qt.tensor[:, :, :ref.shape[2]].cpu().numpy()
-        got = got.astype(np.int64) if qt.signed else got.view(np.uint8).astype(np.int64)
-        assert np.array_equal(got, ref), n
+        assert np.array_equal(qt.codes_bct(), ref), n
         checked += 1
     assert checked >= 150
     print("plan stats", plan.stats)
