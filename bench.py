@@ -30,6 +30,9 @@ import torch  # noqa: E402
 WORKLOAD = dict(name="quartznet15x5_w6a6_percentile99.996_static_b64_t1600", topology="quartznet15x5",
                 weight_bit=6, act_bit=6, percentile=99.996, batch=64, frames=1600,
                 calib_batches=4, calib_shape=(8, 64, 500))
+# BASELINE.json configs[2] (parity-test network; `--workload jasper` measures it for DESIGN.md only)
+WORKLOAD_JASPER = dict(name="jasper10x5dr_w8a8_static_b32_t1600", topology="jasper10x5dr", weight_bit=8, act_bit=8,
+                       percentile=None, batch=32, frames=1600, calib_batches=2, calib_shape=(4, 64, 500))
 FRAMES_PER_AUDIO_SECOND = 100.0  # 10 ms hop
 
 
@@ -122,7 +125,8 @@ def kernel_breakdown(plan, flush, iters=3):
             per_op[i] += a.elapsed_time(b) / iters
     classes = {}
     for (name, _), ms, nbytes in zip(plan.ops, per_op, plan.op_bytes):
-        cls = "dwconv" if name.startswith("dw_") else ("gemm_i8_tc" if name.startswith("gemm_") else "quantize")
+        cls = "dwconv" if name.startswith("dw_") else (
+            ("conv_ntc_tc" if plan.ntc else "gemm_i8_tc") if name.startswith("gemm_") else "quantize")
         c = classes.setdefault(cls, dict(ms=0.0, bytes=0, launches=0))
         c["ms"] += ms
         c["bytes"] += nbytes
@@ -152,7 +156,7 @@ def run_ours(args):
     if distributed:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
-    wl = WORKLOAD
+    wl = WORKLOAD_JASPER if args.workload == "jasper" else WORKLOAD
     from qasr.params import synthetic_features
     apply_debug_knobs()
     model = build_model(device, wl)
@@ -238,12 +242,14 @@ def run_ours(args):
     dom = max(classes, key=lambda k: classes[k]["ms"])
     peak, peak_src = peaks()
     achieved = classes[dom]["bytes"] / (classes[dom]["ms"] / 1e3) / 1e9
+    macs = sum(m for (n, _), m in zip(plan.ops, plan.op_macs) if n.startswith("gemm_"))
     roofline = dict(bound="hbm", kernel=dom, achieved=round(achieved, 1), peak=peak, unit="GB/s",
                     frac=round(achieved / peak, 4), traffic=None, peak_source=peak_src,
                     launches_per_step=classes[dom]["launches"],
                     algorithmic_bytes_per_step=classes[dom]["bytes"],
                     kernel_ms_per_step=round(classes[dom]["ms"], 4),
                     share_of_step=round(classes[dom]["ms"] / step_ms, 3),
+                    tensor_tops=round(2 * macs / (sum(v["ms"] for k, v in classes.items() if "tc" in k) / 1e3) / 1e12, 1),
                     classes={k: dict(ms=round(v["ms"], 4), gbs=round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1),
                                      launches=v["launches"]) for k, v in classes.items()})
     cpu = cpu_baseline(model, wl, seconds_budget=20.0)
@@ -351,6 +357,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="quartznet", choices=["quartznet", "jasper"],
+                    help="quartznet = BASELINE configs[1] (the metric's configuration, default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

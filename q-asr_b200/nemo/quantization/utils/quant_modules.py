@@ -19,6 +19,7 @@ import torch.nn.functional as F
 from torch.nn import Module, Parameter
 
 from qasr import _lib as _L
+from qasr import dist as _dist
 from qasr import ops as _ops
 
 from .quant_utils import *  # noqa: F401,F403  (the reference star-exports these too)
@@ -86,6 +87,15 @@ class QuantAct(Module):
 
     # -- range statistics (reference :113-125 / :150-167) ---------------------------------
     def _batch_range(self, x, identity, percentile):
+        """Range of this batch; under data parallelism (qasr.dist) min / max are all-reduced so every rank
+        sees the full-batch range the reference computes."""
+        if _dist.is_enabled() and percentile is not None:
+            raise NotImplementedError("percentile statistics over a data-parallel (sharded) batch need a "
+                                      "distributed selection; calibrate on one rank or use min/max")
+        x_min, x_max = self._local_batch_range(x, identity, percentile)
+        return _dist.allreduce_range(x_min, x_max)
+
+    def _local_batch_range(self, x, identity, percentile):
         if x.is_cuda:
             x3 = x if x.dim() == 3 else x.reshape(1, -1, x.shape[-1])
             id3 = None if identity is None else identity.reshape(x3.shape)

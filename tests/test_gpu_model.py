@@ -290,3 +290,53 @@ def test_quartznet15x5_dynamic_vs_oracle(quartznet):
     assert np.array_equal(logit_codes(model.decoder.last_logits, sf), want["logit_codes"])
     assert np.array_equal(greedy.cpu().numpy(), want["greedy"])
     qm.set_dynamic(model, False)
+
+
+def test_jasper10x5dr_static_vs_oracle():
+    """BASELINE config 3's network: dense k = 11..29 convs (channels-last implicit GEMM), strided head,
+    dense residual chains of up to 10 res_act applications, accumulators beyond 2^24."""
+    EncDecCTCModel, qm, Q, topology = _imports()
+    from qasr.params import reestimate_bn_, synthetic_features
+    torch.manual_seed(0)
+    model = EncDecCTCModel.from_topology("jasper10x5dr")
+    model.eval()
+    reestimate_bn_(model.encoder)
+    model.encoder.bn_folding()
+    model = model.to(DEV)
+    spec = spec_from_model(model.encoder, model.decoder)
+    B, T = 1, 120
+    model.use_fused_plan = model.encoder.use_fused_plan = False
+    qm.calibrate(model)
+    O.set_mode(spec, True)
+    cx, cl = synthetic_features(B, T, seed=100)
+    e, l, s = model.encoder(cx.to(DEV), cl.to(DEV))
+    model.decoder(e, s)
+    O.model_forward(spec, cx.numpy(), cl.numpy())
+    qm.evaluate(model)
+    O.set_mode(spec, False)
+    for a, m in zip(O.iter_acts(spec), module_acts(model)):
+        assert np.float32(m.x_min.item()) == np.float32(a.x_min)
+        assert np.float32(m.x_max.item()) == np.float32(a.x_max)
+    x, lens = synthetic_features(B, T, seed=5)
+    trace = []
+    want = O.model_forward(spec, x.numpy(), lens.numpy(), trace)
+    model.use_fused_plan = model.encoder.use_fused_plan = True
+    plan = model.plan_for(x.shape, torch.device(DEV))
+    assert plan.ntc
+    logits = plan.run(x.to(DEV), lens.to(DEV))
+    assert np.array_equal(logit_codes(logits, plan.logits_scale.reshape(-1)), want["logit_codes"])
+    assert np.array_equal(plan.greedy().cpu().numpy(), want["greedy"])
+    by_name = {}
+    for r in trace:
+        by_name.setdefault(r["name"], []).append(r)
+    names = {id(m): n for n, m in model.named_modules()}
+    checked = 0
+    for (vid, key), qt in plan._q.items():
+        if qt.info is None:
+            continue
+        n = names[id(qt.info.module)].replace("encoder.encoder.", "encoder.")
+        if n.endswith(".act") and n[:-4] in by_name:
+            assert np.array_equal(qt.codes_bct(), by_name[n[:-4]][0]["in_codes"]), n
+            checked += 1
+    assert checked >= 100
+    print("jasper plan stats", plan.stats)
