@@ -242,6 +242,31 @@ int qasr_ctc_argmax(const float* logits, int32_t ld, int32_t B, int32_t V, int32
 int qasr_log_softmax_tv(const float* logits, int32_t ld, int32_t B, int32_t V, int32_t T,
                         float* log_probs, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * K6  mel-spectrogram featurizer (n_fft = 512)
+ * qasr_melspec_f32 replaces FilterbankFeatures.forward up to the log
+ * (nemo/collections/asr/parts/features.py:347-368): pre-emphasis, torch.stft framing (center,
+ * reflect padding), |X|^2, mel filterbank (non-zero bands: fb_w / fb_start / fb_off), log(x + guard).
+ *   audio [B][audio_ld] float, L samples per row;  feat [B][n_mels][feat_ld], n_frames = 1 + L/hop
+ *   window512: window zero-padded to 512;  twiddle256: exp(-2 pi i k/512) as (re, im) pairs
+ * qasr_normalize_features_f32 replaces normalize_batch 'per_feature' (:53-68) + the length mask and
+ * zero padding (:383-395), in place: seq_len[b] valid frames, T_pad total frames.
+ * ---------------------------------------------------------------------------------- */
+int qasr_melspec_f32(const float* audio, int32_t audio_ld, int32_t B, int32_t L, int32_t hop,
+                     const float* window512, const float* twiddle256, const float* fb_w,
+                     const int32_t* fb_start, const int32_t* fb_off, int32_t n_mels, float preemph,
+                     float log_guard, float* feat, int32_t feat_ld, int32_t n_frames, void* stream);
+int qasr_normalize_features_f32(float* feat, int32_t feat_ld, int32_t B, int32_t n_mels, int32_t n_frames,
+                                int32_t T_pad, const int32_t* seq_len, int32_t do_normalize, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K5b  greedy CTC collapse on device (metrics/wer.py:117-136): merge repeats, drop blanks.
+ *   labels [B][T] int32 -> tokens [B][T] int32 (compacted, -1 filled), counts [B] int32;
+ *   only the first lens[b] frames of each row are decoded when lens != NULL.
+ * ---------------------------------------------------------------------------------- */
+int qasr_ctc_collapse(const int32_t* labels, int32_t B, int32_t T, const int32_t* lens, int32_t blank_id,
+                      int32_t* tokens, int32_t* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -368,7 +368,36 @@ __global__ void log_softmax_tv_kernel(const float* __restrict__ logits, int ld, 
   }
 }
 
+// greedy CTC collapse: one warp per utterance, ballot + prefix popcount compaction
+__global__ void ctc_collapse_kernel(const int32_t* __restrict__ labels, int B, int T, const int32_t* lens,
+                                    int blank, int32_t* __restrict__ tokens, int32_t* __restrict__ counts) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int n = lens ? min(lens[b], T) : T;
+  const int32_t* row = labels + (size_t)b * T;
+  int32_t* out = tokens + (size_t)b * T;
+  int count = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    const int p = t < n ? row[t] : blank;
+    const int prev = (t > 0 && t < n) ? row[t - 1] : blank;          // previous = blank_id at the start
+    const bool keep = t < n && p != blank && (p != prev || prev == blank);
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (keep) out[count + __popc(mask & ((1u << lane) - 1))] = p;
+    count += __popc(mask);
+  }
+  for (int t = count + lane; t < T; t += 32) out[t] = -1;
+  if (lane == 0) counts[b] = count;
+}
+
 }  // namespace
+
+extern "C" int qasr_ctc_collapse(const int32_t* labels, int32_t B, int32_t T, const int32_t* lens, int32_t blank_id,
+                                 int32_t* tokens, int32_t* counts, void* stream) {
+  QASR_CHECK_ARG(labels && tokens && counts && B > 0 && T > 0, "ctc_collapse: bad arguments");
+  ctc_collapse_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(labels, B, T, lens, blank_id, tokens, counts);
+  return qasr_check_launch("ctc_collapse_kernel");
+}
 
 // ---------------------------------------------------------------------------------------------
 // C ABI

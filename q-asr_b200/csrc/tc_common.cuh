@@ -5,6 +5,9 @@
 
 namespace qasr_tc {
 
+#ifndef QASR_SUSPEND_HINT_NS
+#define QASR_SUSPEND_HINT_NS 2000u
+#endif
 constexpr uint32_t kSpinLimit = 1u << 22;  // a wedged pipeline traps instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -27,7 +30,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(2000u)
+        : "r"(bar), "r"(parity), "r"(QASR_SUSPEND_HINT_NS)
         : "memory");
     if (spin > kSpinLimit) __trap();
   }

@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqasr.so")
+LIB_PATH = os.environ.get("QASR_LIB_PATH", os.path.join(_HERE, "libqasr.so"))  # override: kernel experiments
 
 EPI_REQUANT_I8, EPI_DEQUANT_F32, EPI_RAW_I32 = 0, 1, 2
 F_RELU0, F_RELU1, F_STAGE2, F_MASK = 1, 2, 4, 8
@@ -72,6 +72,10 @@ _SIGS = {
     "qasr_quantile2_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _f32, _f32, _vp, _vp, _vp]),
     "qasr_ctc_argmax": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "qasr_log_softmax_tv": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "qasr_melspec_f32": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _vp,
+                                   _i32, _i32, _vp]),
+    "qasr_normalize_features_f32": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "qasr_ctc_collapse": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
     "qasr_debug_set": (C.c_int, [C.c_int, C.c_longlong]),
 }
 

