@@ -213,6 +213,9 @@ class QuantConv1d(Module):
             self.weight_function = SymmetricQuantFunction.apply
         self._prep_key = None
         self._prep = None
+        # module-level calls reproduce the reference's float outputs bit for bit (costs a second integer
+        # conv per call; the fused static plan does not need it).  False = noise-free integer recipe.
+        self.exact_float_noise = True
 
     def set_param(self, conv):
         self.in_channels = conv.in_channels
@@ -315,21 +318,48 @@ class QuantConv1d(Module):
         T_out = (T + 2 * pad - dil * (k - 1) - 1) // stride + 1
         channels_last = not p["depthwise"] and (k > 1 or stride > 1)
         codes = _ops.quantize_f32_ntc(x, s_x, 1) if channels_last else _ops.codes_from_f32(x, s_x)
-        tab = torch.stack([s_out.contiguous().view(torch.int32), b_i32,
-                           torch.full_like(b_i32, 1 << 30), torch.full_like(b_i32, 30)], dim=1).contiguous()
-        flags = _L.F_BIAS64 | (0 if input_unsigned else _L.F_B_SIGNED)
-        ep = _ops.make_epilogue(_L.EPI_DEQUANT_F32, tab, flags=flags)
-        out = torch.empty((B, self.out_channels, _ops.round_up(T_out, 16)), dtype=torch.float32,
-                          device=x.device)
-        if p["depthwise"]:
-            _ops.dwconv(codes, T, p["w8"], out, T_out, k, stride, dil, pad, ep)
-        elif channels_last:  # dense k > 1 / strided conv: channels-last implicit GEMM, (B,C,T) float out
-            _ops.conv_ntc(_ops.gemm_operand(codes, T, p["packed"], Cin, k, stride, dil, pad), None, out, B,
-                          self.out_channels, T_out, ep)
+
+        def run_conv(inp, signed, table, mode, out_t):
+            ep = _ops.make_epilogue(mode, table, flags=_L.F_BIAS64 | (_L.F_B_SIGNED if signed else 0))
+            if p["depthwise"]:
+                _ops.dwconv(inp, T, p["w8"], out_t, T_out, k, stride, dil, pad, ep)
+            elif channels_last:  # dense k > 1 / strided conv: channels-last implicit GEMM, (B,C,T) out
+                _ops.conv_ntc(_ops.gemm_operand(inp, T, p["packed"], Cin, k, stride, dil, pad), None, out_t, B,
+                              self.out_channels, T_out, ep)
+            else:
+                _ops.conv_gemm(_ops.gemm_operand(inp, T, p["packed"], Cin, k, stride, dil, pad), None, out_t, B,
+                               self.out_channels, T_out, ep)
+            return out_t
+
+        ld = _ops.round_up(T_out, 16)
+        one, thirty = torch.full_like(b_i32, 1 << 30), torch.full_like(b_i32, 30)
+        if not self.exact_float_noise:
+            tab = torch.stack([s_out.contiguous().view(torch.int32), b_i32, one, thirty], dim=1).contiguous()
+            out = run_conv(codes, not input_unsigned, tab, _L.EPI_DEQUANT_F32,
+                           torch.empty((B, self.out_channels, ld), dtype=torch.float32, device=x.device))
+            conv_output = out[:, :, :T_out]
         else:
-            _ops.conv_gemm(_ops.gemm_operand(codes, T, p["packed"], Cin, k, stride, dil, pad), None, out, B,
-                           self.out_channels, T_out, ep)
-        conv_output = out[:, :, :T_out]
+            # The reference never rounds x_int = x / s_x (:301): code q enters its float64 conv as
+            # q + eps(q), eps = f64(f32(q * s_x) / s_x) - q in {0, +-ulp_f32(q)}, so the accumulator it
+            # converts to float32 (:305) is acc + delta, delta = sum w * eps.  eps * 2^22 is a small integer
+            # (|.| <= 64): delta is one more integer conv over LUT-mapped codes.  Reproducing it makes the
+            # float outputs -- and every range statistic taken on them in calibration / dynamic mode --
+            # bit-identical to the reference.
+            q = torch.arange(-256, 256, device=x.device, dtype=torch.float32)
+            eps = ((q * s_x) / s_x).double() - q.double()
+            lut = torch.round(eps * float(2 ** 22)).to(torch.int8)
+            idx = (codes.view(torch.uint8).to(torch.int64) if input_unsigned else codes.to(torch.int64)) + 256
+            rcodes = lut[idx]
+            tab0 = torch.stack([s_out.contiguous().view(torch.int32), torch.zeros_like(b_i32), one, thirty],
+                               dim=1).contiguous()
+            acc = run_conv(codes, not input_unsigned, tab0, _L.EPI_RAW_I32,
+                           torch.empty((B, self.out_channels, ld), dtype=torch.int32, device=x.device))
+            dacc = run_conv(rcodes, True, tab0, _L.EPI_RAW_I32,
+                            torch.empty((B, self.out_channels, ld), dtype=torch.int32, device=x.device))
+            bias64 = self.bias_integer.double() if p["bias"] is not None else torch.zeros_like(s_out).double()
+            tot = acc[:, :, :T_out].double() + bias64.view(1, -1, 1) + dacc[:, :, :T_out].double() * (2.0 ** -22)
+            conv_output = tot.float() * s_out.view(1, -1, 1)            # .type(torch.float) :305, rescale :307
+            return conv_output, s_out.view(1, -1, 1)
         if out.shape[-1] != T_out:
             conv_output = conv_output.contiguous()
         return conv_output, s_out.view(1, -1, 1)

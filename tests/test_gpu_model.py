@@ -98,16 +98,20 @@ def test_golden_network_module_level(path):
         for c in case["calib"]:
             e, l, s = model.encoder(torch.from_numpy(c["x"]).to(DEV), torch.from_numpy(c["lens"]).to(DEV))
             model.decoder(e, s)
-        # ranges calibrated on the GPU (noise-free integer recipe) vs the reference's (float noise)
+        # the module-level path reproduces the reference's float noise (QuantConv1d.exact_float_noise): the
+        # ranges calibrated on the GPU are bit-equal to the reference's, percentile mode included
         for a, m in zip(O.iter_acts(case["spec"]), module_acts(model)):
-            for got, want in ((float(m.x_min), float(a.x_min)), (float(m.x_max), float(a.x_max))):
-                assert abs(got - want) <= 1e-5 * max(abs(want), 1e-3)
-        set_ranges_from_spec(model, case["spec"])  # identical calibrated state for the exact comparison
+            assert np.float32(m.x_min.item()) == np.float32(a.x_min)
+            assert np.float32(m.x_max.item()) == np.float32(a.x_max)
     qm.evaluate(model)
     qm.set_dynamic(model, case["mode"] == "dynamic")
     log_probs, enc_len, greedy = model(processed_signal=x, processed_signal_length=lens)
     sf = model.decoder.decoder_layers[0].conv_scaling_factor * model.decoder.act.act_scaling_factor
     check_outputs(case["out"], model.decoder.last_logits, sf, log_probs, greedy, enc_len)
+    # bit-identical dequantised logits and encoder output floats
+    assert np.array_equal(model.decoder.last_logits.cpu().numpy(), case["out"]["logits"])
+    enc, _, enc_sf = model.encoder(audio_signal=x, length=lens)
+    assert np.array_equal(enc.cpu().numpy(), case["out"]["encoded"])
 
 
 @pytest.mark.parametrize("path", [p for p in NET_CASES if "static" in p or "mom" in p],
@@ -196,7 +200,10 @@ def test_golden_quant_conv(case):
     assert np.array_equal(sf.reshape(-1).cpu().numpy(), case["out_scale"])
     got_acc = torch.round(out.double() / sf.double()).cpu().numpy()
     assert np.array_equal(got_acc.astype(np.float32), case["acc"].astype(np.float32))
-    assert np.abs(out.cpu().numpy() - case["out"]).max() <= 1e-6 * np.abs(case["out"]).max()
+    assert np.array_equal(out.cpu().numpy(), case["out"])          # bit-identical floats (delta reproduced)
+    qc.exact_float_noise = False                                   # the noise-free integer recipe
+    out2, _ = qc(x, s_x)
+    assert np.abs(out2.cpu().numpy() - case["out"]).max() <= 1e-6 * np.abs(case["out"]).max()
 
 
 # ------------------------------------------------------------------------------------------
@@ -225,6 +232,7 @@ def test_quartznet15x5_static_vs_oracle(quartznet, wbit, abit, percentile):
     spec = spec_from_model(model.encoder, model.decoder)
     B, T = 2, 200
     model.use_fused_plan = model.encoder.use_fused_plan = False
+    O.LITERAL_NOISE = True     # the module-level path reproduces the reference's float noise
     qm.calibrate(model)
     O.set_mode(spec, True)
     for i in range(2):
@@ -234,18 +242,20 @@ def test_quartznet15x5_static_vs_oracle(quartznet, wbit, abit, percentile):
         O.model_forward(spec, cx.numpy(), cl.numpy())
     qm.evaluate(model)
     O.set_mode(spec, False)
-    # calibration statistics: both sides run the noise-free integer recipe -> bit-equal ranges
+    # calibration statistics (min/max and percentile): bit-equal ranges
     for a, m in zip(O.iter_acts(spec), module_acts(model)):
         assert np.float32(m.x_min.item()) == np.float32(a.x_min)
         assert np.float32(m.x_max.item()) == np.float32(a.x_max)
     x, lens = synthetic_features(B, T, seed=5, ragged=True)
     trace = []
     want = O.model_forward(spec, x.numpy(), lens.numpy(), trace)
+    O.LITERAL_NOISE = False
     assert (want["logit_codes"] != 0).mean() > 0.9
     # module-level path
     log_probs, enc_len, greedy = model(processed_signal=x.to(DEV), processed_signal_length=lens.to(DEV))
     sf = model.decoder.decoder_layers[0].conv_scaling_factor * model.decoder.act.act_scaling_factor
     assert np.array_equal(logit_codes(model.decoder.last_logits, sf), want["logit_codes"])
+    assert np.array_equal(model.decoder.last_logits.cpu().numpy(), want["logits"])   # bit-identical floats
     assert np.array_equal(greedy.cpu().numpy(), want["greedy"])
     # fused plan
     model.use_fused_plan = model.encoder.use_fused_plan = True
@@ -284,7 +294,11 @@ def test_quartznet15x5_dynamic_vs_oracle(quartznet):
     qm.set_dynamic(model, True)
     spec = spec_from_model(model.encoder, model.decoder)
     x, lens = synthetic_features(2, 200, seed=7, ragged=True)
-    want = O.model_forward(spec, x.numpy(), lens.numpy())
+    O.LITERAL_NOISE = True     # dynamic ranges are taken on floats that carry the reference's noise
+    try:
+        want = O.model_forward(spec, x.numpy(), lens.numpy())
+    finally:
+        O.LITERAL_NOISE = False
     log_probs, enc_len, greedy = model(processed_signal=x.to(DEV), processed_signal_length=lens.to(DEV))
     sf = model.decoder.decoder_layers[0].conv_scaling_factor * model.decoder.act.act_scaling_factor
     assert np.array_equal(logit_codes(model.decoder.last_logits, sf), want["logit_codes"])
@@ -306,6 +320,7 @@ def test_jasper10x5dr_static_vs_oracle():
     spec = spec_from_model(model.encoder, model.decoder)
     B, T = 1, 120
     model.use_fused_plan = model.encoder.use_fused_plan = False
+    O.LITERAL_NOISE = True
     qm.calibrate(model)
     O.set_mode(spec, True)
     cx, cl = synthetic_features(B, T, seed=100)
@@ -319,6 +334,7 @@ def test_jasper10x5dr_static_vs_oracle():
         assert np.float32(m.x_max.item()) == np.float32(a.x_max)
     x, lens = synthetic_features(B, T, seed=5)
     trace = []
+    O.LITERAL_NOISE = False    # the fused plan is the noise-free integer recipe
     want = O.model_forward(spec, x.numpy(), lens.numpy(), trace)
     model.use_fused_plan = model.encoder.use_fused_plan = True
     plan = model.plan_for(x.shape, torch.device(DEV))
