@@ -38,3 +38,31 @@ def run(ci, co, dual, knobs, iters=20, ld=None):
     return np.median(ts)
 for (ci, co, dual) in ((512, 512, False), (512, 512, True), (256, 256, False), (256, 512, False), (512, 1024, False)):
     print("%4dx%4d dual=%d %7.1f us" % (ci, co, dual, run(ci, co, dual, {})), flush=True)
+
+
+def run_ntc(ci, co, dual, iters=20):
+    x = torch.randint(0, 127, (B, T, ci), dtype=torch.int8, device=dev)
+    w = torch.randint(-30, 30, (co, ci, 1), dtype=torch.int8, device=dev)
+    wp = ops.pack_weights(w)
+    m = np.full(co, (1 << 30) + 12345); e = np.full(co, 44)
+    ch = ops.chan_table(np.full(co, 1e-4, np.float32), np.zeros(co), m, e, dev)
+    flags = L.F_RELU1 | (L.F_STAGE2 if dual else 0) | L.F_RELU0 * (not dual)
+    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=flags, ch1=ch if dual else None, qmin=-128, qmax=127,
+                           m2=(1 << 30) + 777, e2=30, qmin2=-256, qmax2=255)
+    out = torch.zeros((B, T, co), dtype=torch.int8, device=dev)
+    op0 = ops.gemm_operand(x, T, wp, ci, 1); op1 = ops.gemm_operand(x, T, wp, ci, 1) if dual else None
+    for _ in range(3): ops.conv_ntc(op0, op1, out, B, co, T, ep)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters): ops.conv_ntc(op0, op1, out, B, co, T, ep)
+    g.replay(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g.replay(); b.record(); b.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3 / iters)
+    return np.median(ts)
+
+for (ci, co, dual) in ((512, 512, False), (512, 512, True), (256, 256, False), (512, 1024, False)):
+    print("NTC %4dx%4d dual=%d %7.1f us" % (ci, co, dual, run_ntc(ci, co, dual)), flush=True)
