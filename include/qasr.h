@@ -86,6 +86,11 @@ enum {
 #define QASR_F_B_SIGNED   64  /* conv-0 input codes are signed (else unsigned)              */
 #define QASR_F_B1_SIGNED  128 /* conv-1 (residual branch) input codes are signed            */
 #define QASR_F_BIAS64     256 /* add the bias in 64-bit (|b_int| close to 2^31)             */
+#define QASR_F_FAST_F32   512 /* single-operand REQUANT only: the host proved that
+                                 clamp(rint(f32(acc+bias) * f32(m*2^-e))), one float FMA
+                                 with a single rounding, equals the dyadic result for every
+                                 reachable accumulator (|acc+bias| < 2^22); kernels then run
+                                 the epilogue on the FP32 pipe (2x the IMAD.HI rate on B200) */
 
 typedef struct {
   int32_t mode;              /* QASR_EPI_*                                               */

@@ -5,7 +5,18 @@
 
 namespace {
 thread_local char g_err[512] = "";
+// bring-up / benchmarking knobs (qasr_debug_set; not part of the public header): -1 = unset
+//   0,1: B-operand descriptor strides   2,3: TMA coordinate experiments   4: force streaming weights
+//   5: M tiles per CTA   6: skip epilogue (1) / MMA (2) / stores (4)   8: depthwise path (0 = IMMA, 1 = tcgen05)
+long long g_dbg[16] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
 }
+
+extern "C" int qasr_debug_set(int key, long long value) {
+  if (key < 0 || key >= 16) return QASR_ERR_INVALID;
+  g_dbg[key] = value;
+  return QASR_OK;
+}
+long long qasr_debug_get(int key) { return key >= 0 && key < 16 ? g_dbg[key] : -1; }
 
 void qasr_set_error(const char* fmt, ...) {
   va_list ap;
@@ -52,6 +63,10 @@ int qasr_validate_epilogue(const qasr_epilogue* e, bool allow_second_operand) {
   } else {
     QASR_CHECK_ARG(e->ch1 == nullptr && e->prev == nullptr, "epilogue: residual operands need REQUANT mode");
   }
+  QASR_CHECK_ARG(!(e->flags & QASR_F_FAST_F32) ||
+                     (e->mode == QASR_EPI_REQUANT_I8 && e->ch1 == nullptr && e->prev == nullptr &&
+                      !(e->flags & (QASR_F_STAGE2 | QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64))),
+                 "epilogue: FAST_F32 is a single-operand, single-stage REQUANT fast path");
   QASR_CHECK_ARG(!(e->flags & QASR_F_BIAS64) || (e->flags & QASR_F_EXACT_F32) || e->mode != QASR_EPI_REQUANT_I8,
                  "epilogue: BIAS64 requires EXACT_F32");
   return QASR_OK;

@@ -83,7 +83,8 @@ __device__ __forceinline__ void row_copy_async(uint32_t dst, const void* src, ui
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// EK: 0 = REQUANT all-integer fast path, 1 = REQUANT literal path, 2 = DEQUANT_F32 / RAW_I32
+// EK: 0 = REQUANT all-integer fast path, 1 = REQUANT literal path, 2 = DEQUANT_F32 / RAW_I32,
+//     3 = REQUANT float fast path (QASR_F_FAST_F32)
 template <int KS, int S, bool XS, int EK>
 __global__ void __launch_bounds__(kThreads) dwconv_mma_kernel(const DwArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -153,15 +154,16 @@ __global__ void __launch_bounds__(kThreads) dwconv_mma_kernel(const DwArgs a) {
       int acc[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) imma_16832<XS>(acc, af[ks], tw[8 * ks], tw[8 * ks + 4]);
-      if (EK < 2) {
-        sb[o0] = (uint8_t)(EK == 0 ? epilogue_fast<false, false, false>(a.ep, kc, acc[0], c0, 0, c0, 0)
-                                  : epilogue_exact(a.ep, kc, acc[0], c0, false, 0, c0, 0));
-        sb[o1] = (uint8_t)(EK == 0 ? epilogue_fast<false, false, false>(a.ep, kc, acc[1], c0, 0, c0, 0)
-                                  : epilogue_exact(a.ep, kc, acc[1], c0, false, 0, c0, 0));
-        sb[o2] = (uint8_t)(EK == 0 ? epilogue_fast<false, false, false>(a.ep, kc, acc[2], c0, 0, c0, 0)
-                                  : epilogue_exact(a.ep, kc, acc[2], c0, false, 0, c0, 0));
-        sb[o3] = (uint8_t)(EK == 0 ? epilogue_fast<false, false, false>(a.ep, kc, acc[3], c0, 0, c0, 0)
-                                  : epilogue_exact(a.ep, kc, acc[3], c0, false, 0, c0, 0));
+      if (EK != 2) {
+        auto code = [&](int acc_v) -> uint8_t {
+          if (EK == 3) return (uint8_t)epilogue_f32_bits(kc, acc_v, c0);
+          return (uint8_t)(EK == 0 ? epilogue_fast<false, false, false>(a.ep, kc, acc_v, c0, 0, c0, 0)
+                                   : epilogue_exact(a.ep, kc, acc_v, c0, false, 0, c0, 0));
+        };
+        sb[o0] = code(acc[0]);
+        sb[o1] = code(acc[1]);
+        sb[o2] = code(acc[2]);
+        sb[o3] = code(acc[3]);
         __syncwarp();
         uint32_t word = stage[warp][lane];
         __syncwarp();
@@ -199,7 +201,7 @@ int launch(const DwArgs& a, cudaStream_t stream) {
   const bool xs = a.ep.flags & QASR_F_B_SIGNED;
   const bool fast = !(a.ep.flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64 | QASR_F_STAGE2)) &&
                     a.ep.prev == nullptr;
-  const int ek = a.ep.mode != QASR_EPI_REQUANT_I8 ? 2 : (fast ? 0 : 1);
+  const int ek = a.ep.mode != QASR_EPI_REQUANT_I8 ? 2 : ((a.ep.flags & QASR_F_FAST_F32) ? 3 : (fast ? 0 : 1));
 #define QASR_DW_GO(XS_, EK_)                                                                         \
   do {                                                                                               \
     auto kern = dwconv_mma_kernel<KS, S, XS_, EK_>;                                                  \
@@ -211,9 +213,9 @@ int launch(const DwArgs& a, cudaStream_t stream) {
     kern<<<grid, kThreads, smem, stream>>>(a);                                                       \
   } while (0)
   if (xs) {
-    if (ek == 0) QASR_DW_GO(true, 0); else if (ek == 1) QASR_DW_GO(true, 1); else QASR_DW_GO(true, 2);
+    if (ek == 0) QASR_DW_GO(true, 0); else if (ek == 1) QASR_DW_GO(true, 1); else if (ek == 2) QASR_DW_GO(true, 2); else QASR_DW_GO(true, 3);
   } else {
-    if (ek == 0) QASR_DW_GO(false, 0); else if (ek == 1) QASR_DW_GO(false, 1); else QASR_DW_GO(false, 2);
+    if (ek == 0) QASR_DW_GO(false, 0); else if (ek == 1) QASR_DW_GO(false, 1); else if (ek == 2) QASR_DW_GO(false, 2); else QASR_DW_GO(false, 3);
   }
 #undef QASR_DW_GO
   return qasr_check_launch("dwconv_mma_kernel");
@@ -249,11 +251,23 @@ int dw_ksteps(int k, int stride, int dilation, int pad) {
 
 }  // namespace
 
+// tensor-core variant (dwconv_tc.cu)
+bool qasr_dwconv_tc_supported(int B, int C, int T_in, int T_out, int k, int stride, int dilation, int pad);
+int qasr_dwconv_tc_launch(const void* x, int x_ld, const int8_t* taps, void* out, int out_ld, int B, int C, int T_in,
+                          int T_out, int k, int stride, int dilation, int pad, const qasr_epilogue* epi, void* stream);
+
+// packed layout: [IMMA A-fragment table (absent when the tap window exceeds 6 x 32)] [raw taps [C][k], for the
+// tcgen05 kernel which builds its banded matrices on the fly]
+static int64_t dw_table_bytes(int C, int k, int stride, int dilation, int pad) {
+  const int ks = dw_ksteps(k, stride, dilation, pad);
+  return ks > 6 ? 0 : (int64_t)C * ks * 128 * 4;
+}
+
 extern "C" int64_t qasr_dw_packed_bytes(int32_t C, int32_t k, int32_t stride, int32_t dilation, int32_t pad) {
   if (C <= 0 || k <= 0 || (stride != 1 && stride != 2) || dilation < 1 || pad < 0) return -1;
-  const int ks = dw_ksteps(k, stride, dilation, pad);
-  if (ks > 6) return -1;
-  return (int64_t)C * ks * 128 * 4;
+  const int64_t table = dw_table_bytes(C, k, stride, dilation, pad);
+  if (table == 0 && !qasr_dwconv_tc_supported(1, C, 1, 1, k, stride, dilation, pad)) return -1;
+  return table + (((int64_t)C * k + 15) / 16) * 16;
 }
 
 extern "C" int qasr_pack_dw_weights(const int8_t* w, void* wp, int32_t C, int32_t k, int32_t stride,
@@ -262,6 +276,10 @@ extern "C" int qasr_pack_dw_weights(const int8_t* w, void* wp, int32_t C, int32_
   QASR_CHECK_ARG(qasr_dw_packed_bytes(C, k, stride, dilation, pad) > 0,
                  "pack_dw_weights: unsupported shape (k=%d stride=%d dilation=%d pad=%d)", k, stride, dilation, pad);
   const int ks = dw_ksteps(k, stride, dilation, pad);
+  const int64_t table = dw_table_bytes(C, k, stride, dilation, pad);
+  QASR_CHECK_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(wp) + table, w, (size_t)C * k, cudaMemcpyDeviceToDevice,
+                                  (cudaStream_t)stream));
+  if (table == 0) return QASR_OK;
   const int total = C * ks * 128;
   pack_dw_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       w, static_cast<uint32_t*>(wp), C, k, stride, dilation, ((-pad) % 4 + 4) % 4, ks);
@@ -285,6 +303,26 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
   QASR_CHECK_ARG(epi->mode != QASR_EPI_REQUANT_I8 || out_ld % 16 == 0, "dwconv: out pitch % 16");
   int rc = qasr_validate_epilogue(epi, false);
   if (rc) return rc;
+
+  // engine choice (tools/dw_bench.py, batch 64 x 800 frames x 512 channels): the IMMA kernel wins for the
+  // short windows (k = 33..75: 25-27 us against 28 us), the tcgen05 kernel for the long dilated ones whose
+  // banded A fragments need 6 IMMA k-steps (k = 87, dilation 2: 32 us against 35 us) and it alone covers
+  // windows beyond 6 x 32 taps.  Bring-up knob 8 forces one engine (0 = IMMA, 1 = tcgen05).
+  const int64_t table_bytes = dw_table_bytes(C, k, stride, dilation, pad);
+  const bool tc_ok = qasr_dwconv_tc_supported(B, C, T_in, T_out, k, stride, dilation, pad);
+  const long long knob = qasr_debug_get(8);
+  bool use_tc = tc_ok && B >= 16 && (long long)B * C * T_out >= (1 << 20) && dw_ksteps(k, stride, dilation, pad) >= 6;
+  if (knob == 0 && table_bytes > 0) use_tc = false;
+  if (knob == 1 && tc_ok) use_tc = true;
+  if (table_bytes == 0) use_tc = true;   // only the tensor-core kernel covers this tap window
+  if (use_tc) {
+    if (!tc_ok) {
+      qasr_set_error("dwconv: tap span (k=%d, dilation=%d, stride=%d) exceeds both kernels' windows", k, dilation, stride);
+      return QASR_ERR_UNSUPPORTED;
+    }
+    return qasr_dwconv_tc_launch(x, x_ld, w + table_bytes, out, out_ld, B, C, T_in, T_out, k, stride, dilation, pad,
+                                 epi, stream);
+  }
 
   DwArgs a;
   a.x = static_cast<const uint8_t*>(x);

@@ -73,6 +73,8 @@ static inline EpiArgs make_epi_args(const qasr_epilogue* e) {
 }
 
 int qasr_validate_epilogue(const qasr_epilogue* e, bool allow_second_operand);
+long long qasr_debug_get(int key);   // bring-up knobs, see api.cu
+extern "C" int qasr_debug_set(int key, long long value);
 
 #ifdef __CUDACC__
 
@@ -88,6 +90,7 @@ struct ChanRegs {
   double mult;          // exact path: m * 2^-e
   int sh;               // fast path: e - 32 (host guarantees 32 <= e <= 62)
   long long add;        // fast path: bias * m + 2^(e-1)
+  float r;              // float fast path: f32(m * 2^-e)
 };
 
 __device__ __forceinline__ ChanRegs load_chan(const qasr_chan* p, int c) {
@@ -100,6 +103,7 @@ __device__ __forceinline__ ChanRegs load_chan(const qasr_chan* p, int c) {
   r.mult = dyad_mult(r.m, r.e);
   r.sh = max(r.e - 32, 0);
   r.add = (long long)r.bias * (long long)r.m + ((r.e >= 1 && r.e <= 62) ? (1ll << (r.e - 1)) : 0ll);
+  r.r = __double2float_rn(r.mult);
   return r;
 }
 
@@ -134,10 +138,13 @@ __device__ __forceinline__ double contrib_exact(int acc, const ChanRegs& c, bool
 }
 
 // Kernel-uniform constants of the REQUANT epilogue, derived once per thread.
+constexpr float kF32Magic = 12582912.0f;   // 1.5 * 2^23: float(kF32Magic + n) has n in its low mantissa bits
+
 struct EpiConsts {
   int lo1, hi1, lo2, hi2;   // clamps with the ReLUs folded in (fast path)
   long long half2;
   double mult2;
+  float flo, fhi;           // float fast path: kF32Magic + lo1 / hi1
 };
 
 __device__ __forceinline__ EpiConsts make_epi_consts(const EpiArgs& ep, bool has1) {
@@ -151,6 +158,8 @@ __device__ __forceinline__ EpiConsts make_epi_consts(const EpiArgs& ep, bool has
   k.hi2 = ep.qmax2;
   k.half2 = (ep.e2 >= 1 && ep.e2 <= 62) ? (1ll << (ep.e2 - 1)) : 0ll;
   k.mult2 = dyad_mult(ep.m2, ep.e2);
+  k.flo = kF32Magic + (float)k.lo1;
+  k.fhi = kF32Magic + (float)k.hi1;
   return k;
 }
 
@@ -169,6 +178,16 @@ __device__ __forceinline__ int epilogue_fast(const EpiArgs& ep, const EpiConsts&
     q = min(max(q, k.lo2), k.hi2);
   }
   return q;
+}
+
+// Float fast path (QASR_F_FAST_F32, single operand, single stage): I2F + FFMA + 2 FMNMX on the 128-lane FP32
+// pipe instead of IMAD.HI (32 lanes/clk/SM measured on B200) + SHF + 2 VIMNMX.  The FMA rounds the exact
+// product plus 1.5 * 2^23 once, to an integer (ties to even); the code is the low byte of the result's bit
+// pattern, so the caller packs the returned words directly.  Equality with the dyadic for every reachable
+// accumulator and this clamp is proved on the host (qasr/plan.py f32_ok).
+__device__ __forceinline__ uint32_t epilogue_f32_bits(const EpiConsts& k, int acc, const ChanRegs& c) {
+  const float y = fmaf((float)(acc + c.bias), c.r, kF32Magic);
+  return __float_as_uint(fminf(fmaxf(y, k.flo), k.fhi));
 }
 
 // Literal float recipe (runtime flags; any accumulator size, exact ties, 64-bit bias).

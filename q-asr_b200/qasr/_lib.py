@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("QASR_LIB_PATH", os.path.join(_HERE, "libqasr.so"))  #
 EPI_REQUANT_I8, EPI_DEQUANT_F32, EPI_RAW_I32 = 0, 1, 2
 F_RELU0, F_RELU1, F_STAGE2, F_MASK = 1, 2, 4, 8
 F_EXACT_F32, F_EXACT_DYAD, F_B_SIGNED, F_B1_SIGNED, F_BIAS64 = 16, 32, 64, 128, 256
+F_FAST_F32 = 512
 
 
 class QasrError(RuntimeError):

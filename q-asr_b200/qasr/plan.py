@@ -73,6 +73,33 @@ def fast_ok(bound, m, e):
     return True
 
 
+def f32_ok(bound, m, e, lo, hi):
+    """May the one-FMA float epilogue clamp(rint(f32(z) * f32(m * 2^-e)), lo, hi) (QASR_F_FAST_F32) replace the
+    dyadic rne(z * m / 2^e) for every integer |z| <= bound?  Call only when fast_ok() already holds (so the
+    dyadic has no ties and equals (z*m + 2^(e-1)) >> e).  Both functions are non-decreasing in z, so they agree
+    everywhere iff they agree on both sides of every jump of the exact one inside the clamp window (and at the
+    ends of the range): at most hi - lo + 2 jumps per channel, checked with exact int64 / float64 arithmetic."""
+    if bound >= 2 ** 22:
+        return False
+    m = np.atleast_1d(m).astype(np.int64).reshape(-1, 1)
+    e = np.atleast_1d(e).astype(np.int64).reshape(-1, 1)
+    if (m <= 0).any() or (e < 1).any() or (e > 62).any():
+        return False
+    r64 = m.astype(F64) * np.exp2(-e.astype(F64))          # exact: 31-bit integer times a power of two
+    r32 = r64.astype(F32).astype(F64)
+    if bound * float(r64.max()) >= 2 ** 21:
+        return False
+    h = np.arange(lo - 1, hi + 1, dtype=F64).reshape(1, -1) + 0.5     # exact jumps happen where z*r crosses h
+    z0 = np.floor(h / r64)
+    cand = np.concatenate([z0 + d for d in (-1.0, 0.0, 1.0, 2.0)] +
+                          [np.full((m.shape[0], 1), -float(bound)), np.full((m.shape[0], 1), float(bound))], axis=1)
+    cand = np.clip(cand, -float(bound), float(bound))
+    zi = cand.astype(np.int64)
+    exact = (zi * m + (np.int64(1) << (e - 1))) >> e          # |z*m| < 2^53, e <= 62: fits int64
+    fl = np.rint(cand * r32)                                  # z * f32(r): exact in double, one rounding
+    return bool(np.array_equal(np.clip(exact, lo, hi), np.clip(fl, lo, hi).astype(np.int64)))
+
+
 def stage2_fast_ok(bound, m, e):
     """Same proof for the scalar second requantisation (generic 64-bit shift: 1 <= e <= 62)."""
     mi, ei = int(np.atleast_1d(m)[0]), int(np.atleast_1d(e)[0])
@@ -187,7 +214,7 @@ class FusedPlan:
         self.ops = []           # list of (name, callable)
         self.op_bytes = []      # algorithmic HBM bytes per op (int8 in + int8/f32 out)
         self.op_macs = []       # multiply-accumulates per op
-        self.stats = dict(kernels=0, fast=0, exact=0, rerun=0)
+        self.stats = dict(kernels=0, fast=0, exact=0, rerun=0, f32=0)
         self._q = {}            # materialised QTensors
         self._keep = []
         self.verbose = verbose
@@ -344,6 +371,8 @@ class FusedPlan:
             if relu:
                 flags |= L.F_RELU0
             fast = fast_ok(cp.bound, m, e)
+            if fast and f32_ok(cp.bound, m, e, max(qmin, 0) if relu else qmin, qmax):
+                flags |= L.F_FAST_F32
             self._emit_conv([(base, cp, m, e)], out, flags, fast, dict(qmin=qmin, qmax=qmax), lens,
                             "conv->act")
         elif isinstance(base, ResActVal):
@@ -411,6 +440,8 @@ class FusedPlan:
             if any(cp.bias64 for (_, cp, _, _) in operands):
                 flags |= L.F_BIAS64
         self.stats["fast" if fast else "exact"] += 1
+        if flags & L.F_FAST_F32:
+            self.stats["f32"] += 1
         ep = ops.make_epilogue(L.EPI_REQUANT_I8, tabs[0], flags=flags, ch1=tabs[1] if len(tabs) > 1 else None,
                                out_lens=lens, **epi_kw)
         self._launch_conv(operands, out, ep, name)

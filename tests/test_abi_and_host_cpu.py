@@ -127,3 +127,42 @@ def test_plan_host_math_matches_oracle():
         z = np.arange(-bound, bound + 1)
         fast = (z.astype(object) * m + (1 << (e - 1))) >> e
         assert np.array_equal(np.array(fast, dtype=np.int64), O.dyadic_mul(z, m, e).astype(np.int64))
+
+
+def test_f32_ok_brute_force():
+    """The host proof behind QASR_F_FAST_F32: whenever f32_ok() says yes, the one-FMA float epilogue (emulated
+    here in float32 arithmetic exactly as the kernel computes it) equals the oracle's dyadic for EVERY reachable
+    accumulator; and it says no for multipliers whose float32 rounding moves a rounding boundary."""
+    import qasr_oracle as O
+    from qasr import plan as P
+    rng = np.random.default_rng(1)
+    magic = np.float32(12582912.0)
+    accepted = refused = 0
+    for trial in range(400):
+        m = int(rng.integers(2 ** 30, 2 ** 31))
+        e = int(rng.integers(36, 50))
+        bound = int(rng.integers(100, 300000))
+        lo, hi = [(-32, 31), (0, 63), (-128, 127), (0, 255)][trial % 4]
+        ma, ea = np.array([m]), np.array([e])
+        if not P.fast_ok(bound, ma, ea):
+            continue
+        ok = P.f32_ok(bound, ma, ea, lo, hi)
+        z = np.arange(-bound, bound + 1)
+        want = np.clip(O.dyadic_mul(z, m, e).astype(np.int64), lo, hi)
+        r = np.float32(m * 2.0 ** -e)
+        # fmaf(f32(z), r, magic): exact product and sum, one rounding to float32 (float64 holds both exactly enough:
+        # |z * r| < 2^21 with a 48-bit product; the sum is rounded to an integer, which rint reproduces)
+        y = (np.rint(z.astype(np.float64) * np.float64(r)) + np.float64(magic)).astype(np.float32)
+        y = np.minimum(np.maximum(y, magic + np.float32(lo)), magic + np.float32(hi))
+        got = (y.view(np.int32) - np.int32(0x4B400000)).astype(np.int64)
+        same = np.array_equal(got, want)
+        if ok:
+            accepted += 1
+            assert same, (m, e, bound, lo, hi)
+        else:
+            refused += 1
+            assert not same or bound * r >= 2 ** 21, "f32_ok refused a multiplier that is exact on the whole range"
+    assert accepted > 50
+    # low byte of the float bit pattern is the two's complement code byte
+    y = (magic + np.arange(-128, 128).astype(np.float32)).astype(np.float32)
+    assert np.array_equal((y.view(np.uint32) & 0xff).astype(np.uint8), np.arange(-128, 128).astype(np.int8).view(np.uint8))

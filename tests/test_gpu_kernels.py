@@ -57,6 +57,20 @@ def rand_dyadic(r, n, lo=2e-5, hi=3e-3):
     return O.batch_frexp(ratio)
 
 
+def f32_dyadic(r, n, bound, lo, hi, rlo=2e-5, rhi=3e-3):
+    """Per-channel dyadics for which the host proves the float fast path (plan.f32_ok), resampling the others."""
+    from qasr import plan as P
+    m, e = norm_me(*rand_dyadic(r, n, rlo, rhi))
+    for _ in range(200):
+        bad = [i for i in range(n) if not (P.fast_ok(bound, m[i:i + 1], e[i:i + 1]) and
+                                           P.f32_ok(bound, m[i:i + 1], e[i:i + 1], lo, hi))]
+        if not bad:
+            return m, e
+        mm, ee = norm_me(*rand_dyadic(r, len(bad), rlo, rhi))
+        m[bad], e[bad] = mm, ee
+    raise AssertionError("could not find float-exact dyadics")
+
+
 def norm_me(m, e):
     m = np.asarray(m, np.int64).copy()
     e = np.asarray(e, np.int64).copy()
@@ -168,6 +182,32 @@ def test_gemm_requant(case, fast):
     got = from_codes_tensor(out, T_out, signed=False)
     assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
     assert int(out[:, :, T_out:].abs().sum()) == 0  # pitch padding stays zero
+
+
+@pytest.mark.parametrize("case", GEMM_CASES[:5], ids=lambda c: c[0])
+def test_gemm_requant_f32(case):
+    """Float fast path (QASR_F_FAST_F32): single operand, ReLU folded into the clamp, host-proved dyadics."""
+    name, B, ci, co, T, k, dil, signed = case
+    q, w, bias, pad = _gemm_inputs(case, seed=1)
+    acc = O.conv1d_int(q, w, bias, 1, pad, dil, 1)
+    T_out = acc.shape[2]
+    r = rng(12)
+    bound = int(np.abs(acc).max())
+    assert bound < 2 ** 22
+    m, e = f32_dyadic(r, co, bound, 0, 63, 1e-6, 2e-4)
+    lens = r.integers(T_out // 2, T_out + 1, B).astype(np.int32)
+    want = expected_requant(acc, m, e, -64, 63, relu0=True, lens=lens)
+    x = to_codes_tensor(q, signed)
+    wp = ops.pack_weights(torch.from_numpy(w.astype(np.int8)).to(DEV))
+    ch = ops.chan_table(r.uniform(1e-5, 1e-3, co).astype(np.float32), bias, m, e, DEV)
+    flags = L.F_RELU0 | L.F_MASK | L.F_FAST_F32 | (L.F_B_SIGNED if signed else 0)
+    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=flags, qmin=-64, qmax=63, out_lens=torch.from_numpy(lens).to(DEV))
+    out = ops.alloc_codes(B, co, T_out, DEV)
+    ops.conv_gemm(ops.gemm_operand(x, T, wp, ci, k, 1, dil, pad), None, out, B, co, T_out, ep)
+    torch.cuda.synchronize()
+    got = from_codes_tensor(out, T_out, signed=False)
+    assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
+    assert int(out[:, :, T_out:].abs().sum()) == 0
 
 
 @pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
@@ -325,12 +365,26 @@ DW_CASES = [
     ("k9_s2_tiny", 3, 64, 64, 9, 2, 1, True),
     ("k13_dil2_tiny", 2, 32, 40, 13, 1, 2, False),
     ("k5_T17", 2, 8, 17, 5, 1, 1, True),
+    # batches that fill the tensor-core kernel's row tiles (several utterance chunks / time-block groups)
+    ("k33_b20", 20, 24, 330, 33, 1, 1, False),
+    ("k75_b70", 70, 8, 200, 75, 1, 1, True),
+    ("k87_dil2_b16", 16, 16, 420, 87, 1, 2, False),
+    ("k11_s2_b33", 33, 16, 321, 11, 2, 1, False),
+    ("k33_b130", 130, 4, 170, 33, 1, 1, False),
 ]
 
 
-@pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
+@pytest.fixture(params=[0, 1], ids=["imma", "tcgen05"])
+def dw_engine(request):
+    """Forces one of the two depthwise engines (bring-up knob 8) so both are checked on every case."""
+    L.lib().qasr_debug_set(8, request.param)
+    yield request.param
+    L.lib().qasr_debug_set(8, -1)
+
+
+@pytest.mark.parametrize("fast", [False, True, "f32"], ids=["exact", "fast", "f32"])
 @pytest.mark.parametrize("case", DW_CASES, ids=lambda c: c[0])
-def test_dwconv_requant(case, fast):
+def test_dwconv_requant(case, fast, dw_engine):
     name, B, Cn, T, k, stride, dil, signed = case
     r = rng(5)
     q = r.integers(-128, 128, (B, Cn, T)) if signed else r.integers(0, 256, (B, Cn, T))
@@ -338,7 +392,10 @@ def test_dwconv_requant(case, fast):
     pad = (dil * k) // 2 - 1 if dil > 1 else k // 2
     acc = O.conv1d_int(q, w, None, stride, pad, dil, Cn)
     T_out = acc.shape[2]
-    m, e = norm_me(*rand_dyadic(r, Cn, 1e-4, 2e-3))
+    if fast == "f32":
+        m, e = f32_dyadic(r, Cn, int(np.abs(acc).max()), -128, 127, 1e-4, 2e-3)
+    else:
+        m, e = norm_me(*rand_dyadic(r, Cn, 1e-4, 2e-3))
     lens = r.integers(T_out // 2, T_out + 1, B).astype(np.int32)
     want = expected_requant(acc, m, e, -128, 127, lens=lens)
     x = to_codes_tensor(q, signed)
@@ -347,6 +404,8 @@ def test_dwconv_requant(case, fast):
     flags = L.F_MASK | (L.F_B_SIGNED if signed else 0)
     if not fast:
         flags |= L.F_EXACT_F32 | L.F_EXACT_DYAD
+    if fast == "f32":
+        flags |= L.F_FAST_F32
     ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=flags, qmin=-128, qmax=127,
                            out_lens=torch.from_numpy(lens).to(DEV))
     out = ops.alloc_codes(B, Cn, T_out, DEV)
@@ -357,7 +416,7 @@ def test_dwconv_requant(case, fast):
     assert int(out[:, :, T_out:].abs().sum()) == 0
 
 
-def test_dwconv_raw_and_dequant():
+def test_dwconv_raw_and_dequant(dw_engine):
     B, Cn, T, k = 2, 48, 100, 33
     r = rng(6)
     q = r.integers(0, 256, (B, Cn, T))

@@ -1,0 +1,44 @@
+"""Micro-benchmark of the two depthwise-conv engines on the benchmark workload's layer shapes, with the
+bring-up knobs (qasr_debug_set 6) to separate load / MMA / epilogue / store / Tc-build costs of the tcgen05 one."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "q-asr_b200")]
+import numpy as np, torch
+from qasr import _lib as L, ops
+dev = "cuda:0"
+lib = L.lib()
+B, T = 64, 800
+
+
+def run(C, k, dil, knobs, iters=20):
+    pad = (dil * k) // 2 - 1 if dil > 1 else k // 2
+    x = torch.randint(0, 64, (B, C, T), dtype=torch.int8, device=dev)
+    w = torch.randint(-31, 32, (C, k), dtype=torch.int8, device=dev)
+    wd = ops.pack_dw_weights(w, 1, dil, pad)
+    m = np.full(C, (1 << 30) + 12345); e = np.full(C, 40)
+    ch = ops.chan_table(np.full(C, 1e-4, np.float32), np.zeros(C), m, e, dev)
+    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=0, qmin=-32, qmax=31)
+    out = torch.zeros((B, C, T), dtype=torch.int8, device=dev)
+    for kk, v in knobs.items(): lib.qasr_debug_set(kk, v)
+    for _ in range(3): ops.dwconv(x, T, wd, out, T, k, 1, dil, pad, ep)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters): ops.dwconv(x, T, wd, out, T, k, 1, dil, pad, ep)
+    g.replay(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g.replay(); b.record(); b.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3 / iters)
+    for kk in knobs: lib.qasr_debug_set(kk, -1)
+    return np.median(ts)
+
+
+for (C, k, dil) in ((512, 33, 1), (512, 75, 1), (256, 33, 1), (512, 87, 2)):
+    print("C=%d k=%d dil=%d: imma %6.1f us   tcgen05 %6.1f us" % (C, k, dil, run(C, k, dil, {8: 0}), run(C, k, dil, {8: 1})), flush=True)
+if len(sys.argv) > 1 and sys.argv[1] == "knobs":
+    for name, kn in (("full", {}), ("no-epilogue", {6: 1}), ("no-mma", {6: 2}), ("no-stores", {6: 4}), ("no-rebuild", {6: 8}),
+                     ("loads only", {6: 3 + 8}), ("loads+mma", {6: 1 + 8}), ("loads+epi", {6: 2 + 8})):
+        kn = dict(kn); kn[8] = 1
+        print("C=512 k=33 %-12s %6.1f us" % (name, run(512, 33, 1, kn)), flush=True)

@@ -36,6 +36,13 @@ def run(ci, co, dual, knobs, iters=20, ld=None):
         ts.append(a.elapsed_time(b) * 1e3 / iters)
     for k in knobs: lib.qasr_debug_set(k, -1)
     return np.median(ts)
+if len(sys.argv) > 1 and sys.argv[1] == "knobs":
+    # qasr_debug_set 6: 1 = epilogue does nothing, 2 = no MMA issue, 4 = no stores; 5: M tiles per CTA; 4: streaming A
+    for (ci, co, dual) in ((512, 512, False), (512, 512, True)):
+        for name, knobs in (("full", {}), ("no-epilogue", {6: 1}), ("no-mma", {6: 2}), ("no-stores", {6: 4}),
+                            ("loads only", {6: 3}), ("MT=1", {5: 1}), ("streaming A", {4: 1})):
+            print("%4dx%4d dual=%d %-12s %7.1f us" % (ci, co, dual, name, run(ci, co, dual, knobs)), flush=True)
+    sys.exit(0)
 for (ci, co, dual) in ((512, 512, False), (512, 512, True), (256, 256, False), (256, 512, False), (512, 1024, False)):
     print("%4dx%4d dual=%d %7.1f us" % (ci, co, dual, run(ci, co, dual, {})), flush=True)
 
