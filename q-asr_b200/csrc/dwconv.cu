@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(kThreads) dwconv_mma_kernel(const DwArgs a) {
   __shared__ uint32_t stage[kWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, tg = lane & 3;
+  pdl_trigger();
   const int item = blockIdx.x * kWarps + warp;
   if (item >= a.C * a.nbg) return;  // whole warps exit together; only warp-level sync below
   const int c = item / a.nbg, bg = item - c * a.nbg;
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(kThreads) dwconv_mma_kernel(const DwArgs a) {
   __syncwarp();
   const uint8_t* xbase = a.x + ((size_t)b_begin * a.C + c) * a.x_ld;
   const size_t xstep = (size_t)a.C * a.x_ld;  // next utterance, same channel
+  pdl_wait();   // activations (and the output buffer) belong to the stream order; everything above is set-up
   if (lane == 0) {
     for (int r = 0; r < min(nrows, kBufs - 1); ++r)
       row_copy_async(smem_addr(bufs + r * a.buf_bytes + a.halo), xbase + r * xstep, a.copy_bytes,
@@ -210,7 +212,7 @@ int launch(const DwArgs& a, cudaStream_t stream) {
       QASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       attr_smem = smem;                                                                              \
     }                                                                                                \
-    kern<<<grid, kThreads, smem, stream>>>(a);                                                       \
+    QASR_CHECK_CUDA(qasr_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, a));             \
   } while (0)
   if (xs) {
     if (ek == 0) QASR_DW_GO(true, 0); else if (ek == 1) QASR_DW_GO(true, 1); else if (ek == 2) QASR_DW_GO(true, 2); else QASR_DW_GO(true, 3);

@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
   if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
     const bool leader = elect_one();
+    pdl_wait();   // the activation rows come from the previous kernel
     const int tiles_per_ch = a.tiles_per_ch, ntbg = a.ntbg, tbpt = a.tb_per_tile, n_tblk = a.n_tblk;
     const int slabs = a.slabs, bbox = a.bbox, stages = a.stages;
     const int tstep = a.N * a.stride, tshift = a.pad + a.o;
@@ -232,7 +234,8 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
     };
 
     int chan_idx = 0;
-    if (u0 < u1) build(u0 / tiles_per_ch, 0);
+    if (u0 < u1) build(u0 / tiles_per_ch, 0);   // taps are constants of the plan: built before the dependency wait
+    pdl_wait();
     int as = 0;
     uint32_t aphase = 0;
     int cur_c = -1;
@@ -401,7 +404,7 @@ int qasr_dwconv_tc_launch(const void* x, int x_ld, const int8_t* taps, void* out
     if (need_attr)                                                                                              \
       QASR_CHECK_CUDA(cudaFuncSetAttribute(dwconv_tc_kernel<EK_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                            (int)kSmemBudget));                                                  \
-    dwconv_tc_kernel<EK_><<<grid, kThreads, smem_bytes, st>>>(map, a);                                          \
+    QASR_CHECK_CUDA(qasr_launch_pdl(dwconv_tc_kernel<EK_>, dim3(grid), dim3(kThreads), smem_bytes, st, map, a)); \
     break;
   switch (ek) {
     QASR_DWTC_CASE(0)

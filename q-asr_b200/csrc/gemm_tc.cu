@@ -132,6 +132,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -154,6 +155,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
     __syncwarp();
+    pdl_wait();   // weights above are constants of the plan; activations below come from the previous kernel
     const int n_total = g.n_total, n_step = g.n_step, n_tiles = g.n_tiles, nseg = g.nseg, stages = g.stages;
     const int a_res = g.a_resident, MT = g.MT;
     const uint32_t stage_bytes = g.stage_bytes;
@@ -261,6 +263,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t acc_per_stage = (uint32_t)(g.MT * g.nseg * BN);
     int as = 0;
     uint32_t aphase = 0;
+    pdl_wait();   // out / prev / out_lens belong to the stream order
     const int MT = g.MT, nseg = g.nseg, n_tiles = g.n_tiles, T_out = g.T_out, C_out = g.C_out;
     const bool masked = g.ep.flags & QASR_F_MASK;
     const bool wide_ok = (reinterpret_cast<uintptr_t>(g.out) & 31) == 0 && (g.out_ld & 31) == 0;   // 32-byte aligned rows
@@ -556,7 +559,8 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
     if (need_attr)                                                                                             \
       QASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_kernel<V_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                            (int)kSmemBudget));                                                 \
-    gemm_i8_kernel<V_><<<grid, kGemmThreads, smem_bytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);         \
+    QASR_CHECK_CUDA(qasr_launch_pdl(gemm_i8_kernel<V_>, dim3(grid), dim3(kGemmThreads), smem_bytes, st, maps[0],  \
+                                    maps[1], maps[2], maps[3], g));                                            \
     break;
   switch (variant) {
     QASR_GEMM_CASE(0)

@@ -78,6 +78,31 @@ extern "C" int qasr_debug_set(int key, long long value);
 
 #ifdef __CUDACC__
 
+// ---------------------------------------------------------------------------------------------
+// programmatic dependent launch: the hot kernels of a plan run back to back on one stream; each is launched
+// with the "programmatic stream serialization" attribute, triggers its dependents at entry and waits for
+// its predecessor (all of it, memory flushed) right before it first touches activation memory.  The
+// next kernel's launch latency, barrier / TMEM set-up and weight loads then overlap this kernel's tail.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename Kern, typename... Args>
+static inline cudaError_t qasr_launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = qasr_debug_get(9) == 0 ? 0 : 1;   // knob 9 = 0: plain launches
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // m * 2^-e as a double: exact (m has 31 bits), so z * mult rounds exactly like the
 // reference's f64(z) * f64(m) followed by the exact division by 2^e (quant_utils.py:195-196).
 __device__ __forceinline__ double dyad_mult(int m, int e) { return scalbn((double)m, -e); }
