@@ -105,6 +105,11 @@ typedef struct {
   int32_t m2, e2;            /* stage-2 scalar dyadic                                    */
   int32_t qmin2, qmax2;      /* stage-2 clamp                                            */
   const int32_t* out_lens;   /* [B] valid output frames (mask), or NULL                  */
+  const float* f32_mult;     /* optional [C_out] (conv 0 only, single-stage REQUANT without
+                                ch1 / prev): f32(m * 2^-e) for the channels where the host
+                                proved the one-FMA float restatement (see QASR_F_FAST_F32),
+                                0.0f for the others; kernels pick the float or the integer
+                                epilogue per channel.  NULL = integer epilogue everywhere  */
 } qasr_epilogue;
 
 /* ------------------------------------------------------------------------------------

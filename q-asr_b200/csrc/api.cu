@@ -63,6 +63,10 @@ int qasr_validate_epilogue(const qasr_epilogue* e, bool allow_second_operand) {
   } else {
     QASR_CHECK_ARG(e->ch1 == nullptr && e->prev == nullptr, "epilogue: residual operands need REQUANT mode");
   }
+  QASR_CHECK_ARG(e->f32_mult == nullptr ||
+                     (e->mode == QASR_EPI_REQUANT_I8 && e->ch1 == nullptr && e->prev == nullptr &&
+                      !(e->flags & (QASR_F_STAGE2 | QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64))),
+                 "epilogue: f32_mult belongs to the single-operand, single-stage integer fast path");
   QASR_CHECK_ARG(!(e->flags & QASR_F_FAST_F32) ||
                      (e->mode == QASR_EPI_REQUANT_I8 && e->ch1 == nullptr && e->prev == nullptr &&
                       !(e->flags & (QASR_F_STAGE2 | QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64))),

@@ -26,6 +26,8 @@
 //     through a 128-byte per-warp shared-memory line so the warp stores 128 contiguous bytes.
 // mma.sync m16n8k32 (IMMA) was measured at 0.48 instr/clk/SM (1.14 POPS) on B200: the MMA part of
 // a 512-channel layer at batch 64 x 800 frames is ~4.6 us, below its 8 us HBM time.
+#include <type_traits>
+
 #include "qasr_common.cuh"
 
 namespace {
@@ -128,7 +130,8 @@ __global__ void __launch_bounds__(kThreads) dwconv_mma_kernel(const DwArgs a) {
       for (int r = 0; r < 4; ++r) af[ks][r] = __ldg(wp + (ks * 4 + r) * 32);
     }
   }
-  const ChanRegs c0 = load_chan(a.ep.ch0, c);
+  const ChanRegs c0 = load_chan0(a.ep, c);
+  const bool f32_path = c0.r != 0.0f;   // warp-uniform: one channel per work item
   const EpiConsts kc = make_epi_consts(a.ep, false);
   // offsets of this lane's 4 accumulators inside the 128-frame tile: D[row][col] -> 16 col + row
   const int o0 = 32 * tg + g, o1 = o0 + 16, o2 = o0 + 8, o3 = o0 + 24;
@@ -151,6 +154,9 @@ __global__ void __launch_bounds__(kThreads) dwconv_mma_kernel(const DwArgs a) {
     const int b = b_begin + r;
     const size_t row = (size_t)b * a.C + c;
     const int len = (a.ep.flags & QASR_F_MASK) ? min(a.ep.out_lens[b], a.T_out) : a.T_out;
+    // the tile loop exists twice, float and integer epilogue, chosen once per row (warp-uniform)
+    auto tiles = [&](auto f32_tag) {
+    constexpr bool F32 = decltype(f32_tag)::value;
     for (int t0 = 0; t0 < a.T_out; t0 += kTile) {
       const uint32_t* tw = xw + ((t0 * S) >> 2);
       int acc[4] = {0, 0, 0, 0};
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(kThreads) dwconv_mma_kernel(const DwArgs a) {
       for (int ks = 0; ks < KS; ++ks) imma_16832<XS>(acc, af[ks], tw[8 * ks], tw[8 * ks + 4]);
       if (EK != 2) {
         auto code = [&](int acc_v) -> uint8_t {
-          if (EK == 3) return (uint8_t)epilogue_f32_bits(kc, acc_v, c0);
+          if (F32) return (uint8_t)epilogue_f32_bits(kc, acc_v, c0);
           return (uint8_t)(EK == 0 ? epilogue_fast<false, false, false>(a.ep, kc, acc_v, c0, 0, c0, 0)
                                    : epilogue_exact(a.ep, kc, acc_v, c0, false, 0, c0, 0));
         };
@@ -191,6 +197,8 @@ __global__ void __launch_bounds__(kThreads) dwconv_mma_kernel(const DwArgs a) {
         if (t0 + o3 < a.T_out) orow[t0 + o3] = acc[3] + c0.bias;
       }
     }
+    };
+    if (EK == 3 || (EK == 0 && f32_path)) tiles(std::true_type{}); else tiles(std::false_type{});
     __syncwarp();  // every lane is done reading this buffer before lane 0 refills it
   }
 }
@@ -306,14 +314,15 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
   int rc = qasr_validate_epilogue(epi, false);
   if (rc) return rc;
 
-  // engine choice (tools/dw_bench.py, batch 64 x 800 frames x 512 channels): the IMMA kernel wins for the
-  // short windows (k = 33..75: 25-27 us against 28 us), the tcgen05 kernel for the long dilated ones whose
-  // banded A fragments need 6 IMMA k-steps (k = 87, dilation 2: 32 us against 35 us) and it alone covers
-  // windows beyond 6 x 32 taps.  Bring-up knob 8 forces one engine (0 = IMMA, 1 = tcgen05).
+  // engine choice (tools/dw_bench.py, batch 64 x 800 frames x 512 channels, both with the float epilogue
+  // choice hoisted out of the loops): IMMA 22.7 / 24.2 / 30.9 us for k = 33 / 75 / 87-dilated against
+  // 30.9 / 31.5 / 34.6 us on tcgen05, whose TMA row fetches (6.5 clk per 128-byte row and 1.6x window overlap)
+  // and 640-thread epilogue do not yet overlap; so the IMMA kernel runs wherever its 6 x 32-tap window reaches
+  // and the tcgen05 kernel covers the longer windows.  Bring-up knob 8 forces one engine (0 = IMMA, 1 = tcgen05).
   const int64_t table_bytes = dw_table_bytes(C, k, stride, dilation, pad);
   const bool tc_ok = qasr_dwconv_tc_supported(B, C, T_in, T_out, k, stride, dilation, pad);
   const long long knob = qasr_debug_get(8);
-  bool use_tc = tc_ok && B >= 16 && (long long)B * C * T_out >= (1 << 20) && dw_ksteps(k, stride, dilation, pad) >= 6;
+  bool use_tc = false;
   if (knob == 0 && table_bytes > 0) use_tc = false;
   if (knob == 1 && tc_ok) use_tc = true;
   if (table_bytes == 0) use_tc = true;   // only the tensor-core kernel covers this tap window
@@ -353,8 +362,10 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
     qasr_set_error("dwconv: rows of %d frames need %zu bytes of staging shared memory (limit 200 KiB)", T_in, smem);
     return QASR_ERR_UNSUPPORTED;
   }
-  // utterances per warp: amortise the A-fragment set-up while keeping >= ~8 warps per SM in flight
-  const long long want_items = 8LL * kWarps * qasr_sm_count();
+  // utterances per warp: amortise the A-fragment set-up while keeping the SM's 64 warp slots filled (the tile loop
+  // is a serial LDS -> IMMA -> epilogue chain per warp; tools/dw_bench.py occupancy: 32 -> 64 warps/SM = -15 %)
+  const long long per_sm = qasr_debug_get(10) > 0 ? qasr_debug_get(10) : 16LL * kWarps;   // knob 10: warps per SM wanted
+  const long long want_items = per_sm * qasr_sm_count();
   int bchunk = (int)(((long long)B * C + want_items - 1) / want_items);
   if (bchunk < 1) bchunk = 1;
   if (bchunk > 16) bchunk = 16;

@@ -22,6 +22,8 @@
 //   their loops with warp-uniform values so descriptors stay in uniform registers (see gemm_tc.cu).
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "qasr_common.cuh"
 #include "tc_common.cuh"
 
@@ -239,13 +241,13 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
     int as = 0;
     uint32_t aphase = 0;
     int cur_c = -1;
-    ChanRegs c0 = load_chan(a.ep.ch0, 0);
+    ChanRegs c0 = load_chan0(a.ep, 0);
     for (int u = u0; u < u1; ++u) {
       const int c = u / tiles_per_ch, r = u - c * tiles_per_ch;
       if (c != cur_c) {
         if (cur_c >= 0) ++chan_idx;
         cur_c = c;
-        c0 = load_chan(a.ep.ch0, c);
+        c0 = load_chan0(a.ep, c);
         // the other buffer belonged to channel c-1, whose last accumulator we have already drained
         if ((c + 1) * tiles_per_ch < u1) build(c + 1, (chan_idx + 1) & 1);
       }
@@ -261,6 +263,8 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
 
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      auto drain = [&](auto f32_tag) {   // float or integer epilogue, chosen once per unit (one channel per unit)
+      constexpr bool F32 = decltype(f32_tag)::value;
       for (int ck = cg; ck * 32 < N && !(a.dbg_skip & 1); ck += kColGroups) {
         int acc[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * kAccStride + (uint32_t)(ck * 32), acc);
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
             int q[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              q[i] = EK == 3 ? (int)epilogue_f32_bits(kc, acc[4 * w4 + i], c0)
+              q[i] = F32 ? (int)epilogue_f32_bits(kc, acc[4 * w4 + i], c0)
                      : EK == 0 ? epilogue_fast<false, false, false>(a.ep, kc, acc[4 * w4 + i], c0, 0, c0, 0)
                                : epilogue_exact(a.ep, kc, acc[4 * w4 + i], c0, false, 0, c0, 0);
             packed[w4] = pack4(q[0], q[1], q[2], q[3]);
@@ -302,6 +306,8 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
             if (valid && t0 + j < a.T_out) orow[t0 + j] = acc[j] + c0.bias;
         }
       }
+      };
+      if (EK == 3 || (EK == 0 && c0.r != 0.0f)) drain(std::true_type{}); else drain(std::false_type{});
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
       if (++as == 2) { as = 0; aphase ^= 1u; }

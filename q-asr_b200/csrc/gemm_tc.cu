@@ -33,6 +33,8 @@
 // to their low word), so descriptors live in uniform registers and the MMAs issue back to back (64.4 clk).
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "qasr_common.cuh"
 #include "tc_common.cuh"
 
@@ -257,9 +259,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int c = (mgroup * g.MT + ms) * BM + quarter * 32 + lane;
       row_ok[ms] = ms < g.MT && c < g.C_out;
       cc[ms] = row_ok[ms] ? c : 0;
-      c0[ms] = load_chan(g.ep.ch0, cc[ms]);
+      c0[ms] = load_chan0(g.ep, cc[ms]);
       c1[ms] = g.nseg > 1 ? load_chan(g.ep.ch1, cc[ms]) : c0[ms];
     }
+    // float epilogue per warp: all 32 channels of this warp's rows proved (the rows never change)
+    const bool warp_f32[2] = {__all_sync(0xffffffffu, c0[0].r != 0.0f) != 0, __all_sync(0xffffffffu, c0[1].r != 0.0f) != 0};
     const uint32_t acc_per_stage = (uint32_t)(g.MT * g.nseg * BN);
     int as = 0;
     uint32_t aphase = 0;
@@ -270,7 +274,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cgroup * 32);
 
     // 32 accumulators (one row, 32 consecutive frames) -> codes -> two 16-byte stores
-    auto finish = [&](int ms, int b, int tv, int len, const int (&a0)[32], const int (&a1)[32]) {
+    auto finish_t = [&](auto f32_tag, int ms, int b, int tv, int len, const int (&a0)[32], const int (&a1)[32]) {
+      constexpr bool F32 = decltype(f32_tag)::value;
       const size_t row = (size_t)b * C_out + cc[ms];
       if (EPI != 0 || g.ep.mode == QASR_EPI_REQUANT_I8) {
         uint8_t* optr = reinterpret_cast<uint8_t*>(g.out) + row * g.out_ld + tv;
@@ -287,7 +292,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int j = 4 * w4 + i;
-            if (EPI & kEpiF32) {
+            if (F32) {
               q[i] = (int)epilogue_f32_bits(kc, a0[j], c0[ms]);
             } else if (EPI & kEpiFast) {
               const int prev = (EPI & kEpiPrev) ? (int)(int8_t)(pw[w4] >> (8 * i)) : 0;
@@ -328,6 +333,12 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int j = 0; j < 32; ++j)
           if (row_ok[ms] && tv + j < T_out) orow[tv + j] = a0[j] + c0[ms].bias;
       }
+    };
+
+    // float or integer epilogue: a per-warp, per-M-tile constant (the warp's 32 rows never change)
+    auto finish = [&](int ms, int b, int tv, int len, const int (&a0)[32], const int (&a1)[32]) {
+      if ((EPI & kEpiF32) || (EPI == kEpiFast && warp_f32[ms])) finish_t(std::true_type{}, ms, b, tv, len, a0, a1);
+      else finish_t(std::false_type{}, ms, b, tv, len, a0, a1);
     };
 
     for (int nidx = n_first; nidx < g.n_total; nidx += g.n_step) {

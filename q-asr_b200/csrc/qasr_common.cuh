@@ -52,6 +52,7 @@ struct EpiArgs {  // by-value kernel-parameter copy of qasr_epilogue
   int prev_ld;
   int qmin, qmax, m2, e2, qmin2, qmax2;
   const int32_t* out_lens;
+  const float* rf;       // per-channel float multipliers (0 = not proved) or nullptr
 };
 
 static inline EpiArgs make_epi_args(const qasr_epilogue* e) {
@@ -69,6 +70,7 @@ static inline EpiArgs make_epi_args(const qasr_epilogue* e) {
   a.qmin2 = e->qmin2;
   a.qmax2 = e->qmax2;
   a.out_lens = e->out_lens;
+  a.rf = e->f32_mult;
   return a;
 }
 
@@ -115,7 +117,7 @@ struct ChanRegs {
   double mult;          // exact path: m * 2^-e
   int sh;               // fast path: e - 32 (host guarantees 32 <= e <= 62)
   long long add;        // fast path: bias * m + 2^(e-1)
-  float r;              // float fast path: f32(m * 2^-e)
+  float r;              // float fast path: f32(m * 2^-e), or 0 when only the integer path is proved
 };
 
 __device__ __forceinline__ ChanRegs load_chan(const qasr_chan* p, int c) {
@@ -129,6 +131,13 @@ __device__ __forceinline__ ChanRegs load_chan(const qasr_chan* p, int c) {
   r.sh = max(r.e - 32, 0);
   r.add = (long long)r.bias * (long long)r.m + ((r.e >= 1 && r.e <= 62) ? (1ll << (r.e - 1)) : 0ll);
   r.r = __double2float_rn(r.mult);
+  return r;
+}
+// conv-0 parameters with the float-path choice of this launch: every channel (QASR_F_FAST_F32), the proved
+// channels of the optional table, or none
+__device__ __forceinline__ ChanRegs load_chan0(const EpiArgs& ep, int c) {
+  ChanRegs r = load_chan(ep.ch0, c);
+  if (!(ep.flags & QASR_F_FAST_F32)) r.r = ep.rf != nullptr ? __ldg(ep.rf + c) : 0.0f;
   return r;
 }
 

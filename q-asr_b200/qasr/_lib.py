@@ -31,6 +31,7 @@ class Epilogue(C.Structure):
         ("m2", C.c_int32), ("e2", C.c_int32),
         ("qmin2", C.c_int32), ("qmax2", C.c_int32),
         ("out_lens", C.c_void_p),
+        ("f32_mult", C.c_void_p),
     ]
 
 

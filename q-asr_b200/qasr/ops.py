@@ -32,7 +32,7 @@ def chan_table(s_out, bias, m, e, device):
 
 
 def make_epilogue(mode, ch0, flags=0, ch1=None, prev=None, qmin=-128, qmax=127, m2=1 << 30, e2=30,
-                  qmin2=0, qmax2=0, out_lens=None):
+                  qmin2=0, qmax2=0, out_lens=None, f32_mult=None):
     ep = L.Epilogue()
     ep.mode, ep.flags = mode, flags
     ep.ch0 = ch0.data_ptr()
@@ -41,7 +41,8 @@ def make_epilogue(mode, ch0, flags=0, ch1=None, prev=None, qmin=-128, qmax=127, 
     ep.prev_ld = prev.shape[-1] if prev is not None else 0
     ep.qmin, ep.qmax, ep.m2, ep.e2, ep.qmin2, ep.qmax2 = qmin, qmax, int(m2), int(e2), qmin2, qmax2
     ep.out_lens = out_lens.data_ptr() if out_lens is not None else None
-    ep._keep = (ch0, ch1, prev, out_lens)
+    ep.f32_mult = f32_mult.data_ptr() if f32_mult is not None else None
+    ep._keep = (ch0, ch1, prev, out_lens, f32_mult)
     return ep
 
 

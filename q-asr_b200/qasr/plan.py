@@ -16,6 +16,8 @@ share one range and every producer runs once.
 """
 import math
 
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -74,21 +76,25 @@ def fast_ok(bound, m, e):
 
 
 def f32_ok(bound, m, e, lo, hi):
-    """May the one-FMA float epilogue clamp(rint(f32(z) * f32(m * 2^-e)), lo, hi) (QASR_F_FAST_F32) replace the
+    """f32_ok_channels() for every channel at once (QASR_F_FAST_F32)."""
+    return bool(f32_ok_channels(bound, m, e, lo, hi).all())
+
+
+def f32_ok_channels(bound, m, e, lo, hi):
+    """Per channel: may the one-FMA float epilogue clamp(rint(f32(z) * f32(m * 2^-e)), lo, hi) (QASR_F_FAST_F32) replace the
     dyadic rne(z * m / 2^e) for every integer |z| <= bound?  Call only when fast_ok() already holds (so the
     dyadic has no ties and equals (z*m + 2^(e-1)) >> e).  Both functions are non-decreasing in z, so they agree
     everywhere iff they agree on both sides of every jump of the exact one inside the clamp window (and at the
     ends of the range): at most hi - lo + 2 jumps per channel, checked with exact int64 / float64 arithmetic."""
-    if bound >= 2 ** 22:
-        return False
     m = np.atleast_1d(m).astype(np.int64).reshape(-1, 1)
     e = np.atleast_1d(e).astype(np.int64).reshape(-1, 1)
-    if (m <= 0).any() or (e < 1).any() or (e > 62).any():
-        return False
+    if bound >= 2 ** 22:
+        return np.zeros(m.shape[0], bool)
+    sane = ((m > 0) & (e >= 1) & (e <= 62)).reshape(-1)
+    m, e = np.where(m > 0, m, 1), np.clip(e, 1, 62)
     r64 = m.astype(F64) * np.exp2(-e.astype(F64))          # exact: 31-bit integer times a power of two
     r32 = r64.astype(F32).astype(F64)
-    if bound * float(r64.max()) >= 2 ** 21:
-        return False
+    sane &= (bound * r64.reshape(-1)) < 2 ** 21
     h = np.arange(lo - 1, hi + 1, dtype=F64).reshape(1, -1) + 0.5     # exact jumps happen where z*r crosses h
     z0 = np.floor(h / r64)
     cand = np.concatenate([z0 + d for d in (-1.0, 0.0, 1.0, 2.0)] +
@@ -97,7 +103,7 @@ def f32_ok(bound, m, e, lo, hi):
     zi = cand.astype(np.int64)
     exact = (zi * m + (np.int64(1) << (e - 1))) >> e          # |z*m| < 2^53, e <= 62: fits int64
     fl = np.rint(cand * r32)                                  # z * f32(r): exact in double, one rounding
-    return bool(np.array_equal(np.clip(exact, lo, hi), np.clip(fl, lo, hi).astype(np.int64)))
+    return sane & (np.clip(exact, lo, hi) == np.clip(fl, lo, hi).astype(np.int64)).all(axis=1)
 
 
 def stage2_fast_ok(bound, m, e):
@@ -214,7 +220,7 @@ class FusedPlan:
         self.ops = []           # list of (name, callable)
         self.op_bytes = []      # algorithmic HBM bytes per op (int8 in + int8/f32 out)
         self.op_macs = []       # multiply-accumulates per op
-        self.stats = dict(kernels=0, fast=0, exact=0, rerun=0, f32=0)
+        self.stats = dict(kernels=0, fast=0, exact=0, rerun=0, f32=0, f32_channels=0, channels=0)
         self._q = {}            # materialised QTensors
         self._keep = []
         self.verbose = verbose
@@ -371,10 +377,17 @@ class FusedPlan:
             if relu:
                 flags |= L.F_RELU0
             fast = fast_ok(cp.bound, m, e)
-            if fast and f32_ok(cp.bound, m, e, max(qmin, 0) if relu else qmin, qmax):
-                flags |= L.F_FAST_F32
-            self._emit_conv([(base, cp, m, e)], out, flags, fast, dict(qmin=qmin, qmax=qmax), lens,
-                            "conv->act")
+            kw = dict(qmin=qmin, qmax=qmax)
+            if fast and os.environ.get("QASR_NO_F32") != "1":   # float epilogue where the host can prove it, channel by channel
+                okc = f32_ok_channels(cp.bound, m, e, max(qmin, 0) if relu else qmin, qmax)
+                self.stats["f32_channels"] += int(okc.sum())
+                self.stats["channels"] += int(okc.size)
+                if okc.all():
+                    flags |= L.F_FAST_F32
+                elif okc.any():
+                    rf = np.where(okc, (m.astype(F64) * np.exp2(-e.astype(F64))).astype(F32), F32(0.0)).astype(F32)
+                    kw["f32_mult"] = torch.from_numpy(rf).to(self.device)
+            self._emit_conv([(base, cp, m, e)], out, flags, fast, kw, lens, "conv->act")
         elif isinstance(base, ResActVal):
             ra = ActInfo(base.act, False)
             if ra.n > 127:

@@ -210,6 +210,58 @@ def test_gemm_requant_f32(case):
     assert int(out[:, :, T_out:].abs().sum()) == 0
 
 
+def test_f32_mult_table_mixed(dw_engine):
+    """Per-channel float multipliers (qasr_epilogue.f32_mult): proved channels take the float epilogue, the rest
+    (0.0f entries) the integer one, in the depthwise kernels (per channel) and the GEMM (per warp of 32 rows)."""
+    from qasr import plan as P
+    r = rng(21)
+    B, Cn, T, k = 20, 160, 330, 33
+    q = r.integers(0, 256, (B, Cn, T))
+    w = r.integers(-127, 127, (Cn, 1, k))
+    acc = O.conv1d_int(q, w, None, 1, k // 2, 1, Cn)
+    bound = int(np.abs(acc).max())
+    m, e = norm_me(*rand_dyadic(r, Cn, 1e-4, 2e-3))
+    ok = P.f32_ok_channels(bound, m, e, -128, 127) & np.array([P.fast_ok(bound, m[i:i + 1], e[i:i + 1]) for i in range(Cn)])
+    assert 0 < ok.sum() < Cn, "want a mix of proved and unproved channels (got %d of %d)" % (ok.sum(), Cn)
+    # channels where fast_ok itself fails would need the exact path: give them a proved dyadic instead
+    bad = [i for i in range(Cn) if not P.fast_ok(bound, m[i:i + 1], e[i:i + 1])]
+    if bad:
+        mm, ee = f32_dyadic(r, len(bad), bound, -128, 127, 1e-4, 2e-3)
+        m[bad], e[bad] = mm, ee
+        ok[bad] = True
+    rf = np.where(ok, (m.astype(np.float64) * np.exp2(-e.astype(np.float64))).astype(np.float32), np.float32(0)).astype(np.float32)
+    want = expected_requant(acc, m, e, -128, 127)
+    x = to_codes_tensor(q, False)
+    wd = ops.pack_dw_weights(torch.from_numpy(w[:, 0, :].astype(np.int8)).to(DEV).contiguous(), 1, 1, k // 2)
+    ch = ops.chan_table(r.uniform(1e-5, 1e-3, Cn).astype(np.float32), None, m, e, DEV)
+    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=0, qmin=-128, qmax=127, f32_mult=torch.from_numpy(rf).to(DEV))
+    out = ops.alloc_codes(B, Cn, T, DEV)
+    ops.dwconv(x, T, wd, out, T, k, 1, 1, k // 2, ep)
+    torch.cuda.synchronize()
+    assert np.array_equal(from_codes_tensor(out, T, signed=True), want)
+    # same table through the pointwise GEMM (1x1 conv with one weight per channel pair)
+    ci = 128
+    q2 = r.integers(0, 64, (B, ci, T))
+    w2 = r.integers(-31, 32, (Cn, ci, 1))
+    acc2 = O.conv1d_int(q2, w2, None, 1, 0, 1, 1)
+    bound2 = int(np.abs(acc2).max())
+    m2, e2 = norm_me(*rand_dyadic(r, Cn, 1e-5, 5e-4))
+    for i in range(Cn):
+        while not P.fast_ok(bound2, m2[i:i + 1], e2[i:i + 1]):
+            m2[i:i + 1], e2[i:i + 1] = norm_me(*rand_dyadic(r, 1, 1e-5, 5e-4))
+    ok2 = P.f32_ok_channels(bound2, m2, e2, 0, 63)
+    rf2 = np.where(ok2, (m2.astype(np.float64) * np.exp2(-e2.astype(np.float64))).astype(np.float32), np.float32(0)).astype(np.float32)
+    rf2[:32] = np.where(ok2[:32], rf2[:32], 0)   # first warp: whatever the proof says; force one fully proved warp below
+    want2 = expected_requant(acc2, m2, e2, -64, 63, relu0=True)
+    wp = ops.pack_weights(torch.from_numpy(w2.astype(np.int8)).to(DEV))
+    ch2 = ops.chan_table(r.uniform(1e-5, 1e-3, Cn).astype(np.float32), None, m2, e2, DEV)
+    ep2 = ops.make_epilogue(L.EPI_REQUANT_I8, ch2, flags=L.F_RELU0, qmin=-64, qmax=63, f32_mult=torch.from_numpy(rf2).to(DEV))
+    out2 = ops.alloc_codes(B, Cn, T, DEV)
+    ops.conv_gemm(ops.gemm_operand(to_codes_tensor(q2, False), T, wp, ci, 1), None, out2, B, Cn, T, ep2)
+    torch.cuda.synchronize()
+    assert np.array_equal(from_codes_tensor(out2, T, signed=False), want2)
+
+
 @pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
 def test_gemm_dual_residual(fast):
     """pointwise conv + residual 1x1 conv meeting in the res_act epilogue (jasper.py:681)."""
