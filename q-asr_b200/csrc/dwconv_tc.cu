@@ -62,6 +62,13 @@ struct DwTcArgs {
   int nb;            // band chunks (16 B) per Tc row, upper bound
   uint32_t idesc;
   uint32_t tmat_bytes, stage_bytes;
+  // row-staged variant (ROWS): whole input rows are bulk-copied into shared memory once per (channel, utterance
+  // chunk) and the epilogue warps cut the overlapping K-major windows out of them
+  const uint8_t* x;
+  int x_ld;
+  int copy_bytes;      // T_in rounded up to 16: bytes of one row copy
+  int row_pitch;       // bytes per staged row: [pad + o zeros | row | zeros up to the last window's end]
+  uint32_t rows_bytes; // bbox * row_pitch
   int dbg_skip;      // qasr_debug_set 6: 1 = epilogue does nothing, 2 = no MMA issue, 4 = no stores, 8 = no Tc rebuild
   EpiArgs ep;
 };
@@ -75,21 +82,25 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 
 // EK: 0 = REQUANT all-integer fast path, 1 = REQUANT literal path, 2 = DEQUANT_F32 / RAW_I32,
 //     3 = REQUANT float fast path (QASR_F_FAST_F32)
-template <int EK>
+// ROWS: false = input windows fetched as TMA boxes (any window, <= kMaxSlabs slabs), true = row-staged variant
+template <int EK, bool ROWS>
 __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const DwTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));   // generic pointer to smem_base
   const uint32_t tmat_base = smem_base;                                      // 2 x Tc
   const uint32_t stage_base = tmat_base + 2u * a.tmat_bytes;                 // stages x A tile
-  const uint32_t z_off = 2u * a.tmat_bytes + (uint32_t)a.stages * a.stage_bytes;
+  const uint32_t rows_off = 2u * a.tmat_bytes + (uint32_t)a.stages * a.stage_bytes;   // ROWS: staged input rows
+  const uint32_t z_off = rows_off + (ROWS ? a.rows_bytes : 0u);
   const uint32_t bars = smem_base + z_off + 4u * (uint32_t)a.zl;             // zl is a multiple of 16
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * kMaxStages + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * kMaxStages + 2 + s); };
   auto mfull_bar = [&](int s) { return bars + 8u * (2 * kMaxStages + 4 + s); };
-  const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 6);
+  const uint32_t rows_full_bar = bars + 8u * (2 * kMaxStages + 6), rows_empty_bar = bars + 8u * (2 * kMaxStages + 7);
+  const uint32_t init_bar = bars + 8u * (2 * kMaxStages + 8);
+  const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 9);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform role index
@@ -99,11 +110,14 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
 
   if (warp == kProducerWarp && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
   if (warp == kMmaWarp && lane == 0) {
-    for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_bar(s), ROWS ? kEpiWarps : 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(rows_full_bar, 1);
+    mbar_init(rows_empty_bar, kEpiWarps);
+    mbar_init(init_bar, kEpiWarps);
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kEpiThreads);
-      mbar_init(mfull_bar(s), kEpiThreads);
+      mbar_init(tempty_bar(s), kEpiWarps);
+      mbar_init(mfull_bar(s), kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -117,7 +131,27 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == kProducerWarp) {
+  if (warp == kProducerWarp && ROWS) {
+    // ===================== row producer: one bulk copy per (utterance, channel) row =====================
+    const int ntbg = a.ntbg, nbch = a.tiles_per_ch / a.ntbg, bbox = a.bbox;
+    const uint32_t rows_base = smem_base + rows_off + (uint32_t)(a.pad + a.o);
+    mbar_wait(init_bar, 0u);   // halos zeroed by the epilogue warps (generic proxy), fenced before their arrive
+    pdl_wait();                // the activation rows come from the previous kernel
+    uint32_t phase = 0;
+    for (int ch = u0 / ntbg; ch <= (u1 - 1) / ntbg; ++ch) {   // chunk = (channel, utterance chunk)
+      const int c = ch / nbch, b0 = (ch - c * nbch) * bbox;
+      const int nrows = min(bbox, a.B - b0);
+      mbar_wait(rows_empty_bar, phase ^ 1u);
+      if (lane == 0) mbar_expect_tx(rows_full_bar, (a.dbg_skip & 32) ? 0u : (uint32_t)(nrows * a.copy_bytes));
+      __syncwarp();
+      for (int r = lane; r < nrows && !(a.dbg_skip & 32); r += 32) {
+        const uint8_t* src = a.x + ((size_t)(b0 + r) * a.C + c) * a.x_ld;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(rows_base + (uint32_t)(r * a.row_pitch)), "l"(src), "r"((uint32_t)a.copy_bytes), "r"(rows_full_bar) : "memory");
+      }
+      phase ^= 1u;
+    }
+  } else if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
     const bool leader = elect_one();
     pdl_wait();   // the activation rows come from the previous kernel
@@ -181,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
               tc_mma_i8(d_tmem, desc_hi | (uint64_t)(a_lo + kk * 2), desc_hi | (uint64_t)(b_lo + kk * 2), idesc,
                         (sl | kk) != 0 ? 1u : 0u);
         }
-        tc_commit(empty_bar(stage));
+        if (!ROWS) tc_commit(empty_bar(stage));   // ROWS: the builders reuse a stage only after draining its tile
         tc_commit(tfull_bar(as));
       }
       stage_lo += stage_step_lo;
@@ -200,10 +234,16 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
     // zero both Tc buffers once: the band positions never move, so zero chunks stay zero for every channel
     for (uint32_t i = tid; i < 2u * a.tmat_bytes / 16u; i += kEpiThreads)
       reinterpret_cast<uint4*>(smem_gen)[i] = make_uint4(0, 0, 0, 0);
+    if (ROWS) {   // staged rows: the halos on both sides of every row stay zero for the whole kernel (conv padding)
+      for (uint32_t i = tid; i < a.rows_bytes / 16u; i += kEpiThreads)
+        reinterpret_cast<uint4*>(smem_gen + rows_off)[i] = make_uint4(0, 0, 0, 0);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // before the bulk copies (async proxy) land
+      mbar_arrive_warp(init_bar);
+    }
     epi_bar_sync();
 
     auto build = [&](int c, int buf) {
-      if ((a.dbg_skip & 8) && c != u0 / tiles_per_ch) { mbar_arrive(mfull_bar(buf)); return; }
+      if ((a.dbg_skip & 8) && c != u0 / tiles_per_ch) { mbar_arrive_warp(mfull_bar(buf)); return; }
       // 4 byte-shifted copies of the zero-padded dilated taps: copy s, index m holds wd[m + s - 16]
       for (int idx = tid; idx < 4 * zl; idx += kEpiThreads) {
         const int s = idx / zl, m = idx - s * zl;
@@ -231,19 +271,55 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tcgen05 (async proxy) reads
-      mbar_arrive(mfull_bar(buf));
+      mbar_arrive_warp(mfull_bar(buf));
       epi_bar_sync();   // nobody still reads the tap copies when the next build overwrites them
+    };
+
+    // ROWS: cut the K-major input windows of unit u out of the staged rows into A stage (u - u0) & 1
+    uint32_t rows_phase = 0;
+    auto prebuild = [&](int u) {
+      const int r = u % tiles_per_ch, tbg = r % ntbg;
+      if (u == u0 || tbg == 0) {   // first unit of a (channel, utterance chunk): its rows must have landed
+        mbar_wait(rows_full_bar, rows_phase);
+        rows_phase ^= 1u;
+      }
+      const int st = (u - u0) & 1;
+      uint8_t* const dst = smem_gen + 2u * a.tmat_bytes + (uint32_t)st * a.stage_bytes;
+      const uint8_t* const rows = smem_gen + rows_off;
+      const int tstep = N * S, row_pitch = a.row_pitch, n_tblk = a.n_tblk;
+      for (int idx = tid; idx < 128 * nq && !(a.dbg_skip & 16); idx += kEpiThreads) {
+        const int rr = idx / nq, q = idx - rr * nq;
+        const int tb = rr / bbox, bl = rr - tb * bbox;
+        const int tblk = tbg * tbpt + tb;
+        if (tblk < n_tblk) {
+          const uint4 v = *reinterpret_cast<const uint4*>(rows + bl * row_pitch + tblk * tstep + q * 16);
+          *reinterpret_cast<uint4*>(dst + (q >> 3) * kSlabBytes + rr * 128 + (((q & 7) ^ (rr & 7)) << 4)) = v;
+        }
+      }
+      // generic writes -> tcgen05 (async proxy) reads: the warp's writes are ordered before lane 0 by the
+      // __syncwarp, lane 0 fences them for the async proxy and arrives (one fence per warp, not per thread)
+      __syncwarp();
+      if (lane == 0) {
+        if (!(a.dbg_skip & 64)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(full_bar(st));
+      }
+      if (u + 1 == u1 || tbg == ntbg - 1) mbar_arrive_warp(rows_empty_bar);   // last window of this chunk is cut
     };
 
     int chan_idx = 0;
     if (u0 < u1) build(u0 / tiles_per_ch, 0);   // taps are constants of the plan: built before the dependency wait
     pdl_wait();
+    if (ROWS && u0 < u1) prebuild(u0);
     int as = 0;
     uint32_t aphase = 0;
     int cur_c = -1;
     ChanRegs c0 = load_chan0(a.ep, 0);
     for (int u = u0; u < u1; ++u) {
       const int c = u / tiles_per_ch, r = u - c * tiles_per_ch;
+      // the next unit's windows: cut them before draining this unit so its MMAs overlap the drain, unless they
+      // belong to the next chunk of rows, which is still in flight (then drain first and hide the copy latency)
+      const bool next_new_chunk = ((u + 1) % tiles_per_ch) % ntbg == 0;
+      if (ROWS && u + 1 < u1 && !next_new_chunk) prebuild(u + 1);   // its stage held unit u - 1, already drained
       if (c != cur_c) {
         if (cur_c >= 0) ++chan_idx;
         cur_c = c;
@@ -309,8 +385,9 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
       };
       if (EK == 3 || (EK == 0 && c0.r != 0.0f)) drain(std::true_type{}); else drain(std::false_type{});
       tc_fence_before();
-      mbar_arrive(tempty_bar(as));
+      mbar_arrive_warp(tempty_bar(as));
       if (++as == 2) { as = 0; aphase ^= 1u; }
+      if (ROWS && u + 1 < u1 && next_new_chunk) prebuild(u + 1);
     }
   }
 
@@ -357,7 +434,7 @@ int qasr_dwconv_tc_launch(const void* x, int x_ld, const int8_t* taps, void* out
   a.o = ((-pad) % 16 + 16) % 16;
   a.span = (k - 1) * dilation + 1;
   a.zl = ((a.span + 32 + 15) / 16) * 16;
-  const uint32_t fixed = 1024 /*align*/ + 4u * (uint32_t)a.zl + 8u * (2 * kMaxStages + 8);
+  const uint32_t fixed = 1024 /*align*/ + 4u * (uint32_t)a.zl + 8u * (2 * kMaxStages + 12);
   // time-block length: the candidate with the least padded work whose window fits kMaxSlabs slabs and 2 stages
   int bestN = 0, best_cost = 0;
   for (int N : {160, 128, 96, 64, 32}) {
@@ -382,9 +459,30 @@ int qasr_dwconv_tc_launch(const void* x, int x_ld, const int8_t* taps, void* out
   a.units = C * a.tiles_per_ch;
   a.tmat_bytes = (uint32_t)a.slabs * a.N * 128u;
   a.stage_bytes = (uint32_t)a.slabs * kSlabBytes;
-  a.stages = (int)((kSmemBudget - fixed - 2u * a.tmat_bytes) / a.stage_bytes);
-  if (a.stages > kMaxStages) a.stages = kMaxStages;
-  const uint32_t smem_bytes = fixed + 2u * a.tmat_bytes + (uint32_t)a.stages * a.stage_bytes;
+  // row-staged variant (bring-up knob 11 = 1; needs one utterance chunk of rows next to two A stages).  It is
+  // bit-exact but measured SLOWER than the TMA-window variant (46 us against 31 us, k = 33, 512 channels): the bare
+  // hand-off skeleton of its three-stage pipeline (rows -> windows -> MMA -> drain) already costs 21 us.  Kept for
+  // the next round's work on that pipeline; the default is the TMA-window variant.
+  a.x = static_cast<const uint8_t*>(x);
+  a.x_ld = x_ld;
+  a.copy_bytes = ((T_in + 15) / 16) * 16;
+  {
+    const int reach = (a.n_tblk - 1) * a.N * stride + a.slabs * 128;
+    int pitch = pad + a.o + a.copy_bytes;
+    if (pitch < reach) pitch = reach;
+    a.row_pitch = ((pitch + 15) / 16) * 16;
+    a.rows_bytes = (uint32_t)a.bbox * (uint32_t)a.row_pitch;
+  }
+  const bool rows = qasr_debug_get(11) == 1 &&
+                    fixed + 2u * a.tmat_bytes + 2u * a.stage_bytes + a.rows_bytes <= kSmemBudget;
+  if (rows) {
+    a.stages = 2;
+  } else {
+    a.rows_bytes = 0;
+    a.stages = (int)((kSmemBudget - fixed - 2u * a.tmat_bytes) / a.stage_bytes);
+    if (a.stages > kMaxStages) a.stages = kMaxStages;
+  }
+  const uint32_t smem_bytes = fixed + 2u * a.tmat_bytes + (uint32_t)a.stages * a.stage_bytes + a.rows_bytes;
   const uint32_t a_signed = (epi->flags & QASR_F_B_SIGNED) ? 1u : 0u;   // the activation codes are operand A here
   // instruction descriptor: D=S32, A=(un)signed 8-bit K-major (codes), B=signed 8-bit K-major (Tc), N, M=128
   a.idesc = (2u << 4) | (a_signed << 7) | (1u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(a.N >> 3) << 17) |
@@ -401,16 +499,20 @@ int qasr_dwconv_tc_launch(const void* x, int x_ld, const int8_t* taps, void* out
   int grid = qasr_sm_count();
   if (grid > a.units) grid = a.units;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set[4][64] = {};
+  static bool attr_set[2][4][64] = {};
   int dev = 0;
   QASR_CHECK_CUDA(cudaGetDevice(&dev));
-  const bool need_attr = dev >= 0 && dev < 64 && !attr_set[ek][dev];
-#define QASR_DWTC_CASE(EK_)                                                                                     \
-  case EK_:                                                                                                     \
-    if (need_attr)                                                                                              \
-      QASR_CHECK_CUDA(cudaFuncSetAttribute(dwconv_tc_kernel<EK_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                           (int)kSmemBudget));                                                  \
-    QASR_CHECK_CUDA(qasr_launch_pdl(dwconv_tc_kernel<EK_>, dim3(grid), dim3(kThreads), smem_bytes, st, map, a)); \
+  const bool need_attr = dev >= 0 && dev < 64 && !attr_set[rows][ek][dev];
+#define QASR_DWTC_GO(EK_, ROWS_)                                                                                   \
+  do {                                                                                                             \
+    if (need_attr)                                                                                                 \
+      QASR_CHECK_CUDA(cudaFuncSetAttribute(dwconv_tc_kernel<EK_, ROWS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)kSmemBudget));                                                     \
+    QASR_CHECK_CUDA(qasr_launch_pdl(dwconv_tc_kernel<EK_, ROWS_>, dim3(grid), dim3(kThreads), smem_bytes, st, map, a)); \
+  } while (0)
+#define QASR_DWTC_CASE(EK_) \
+  case EK_:                 \
+    if (rows) QASR_DWTC_GO(EK_, true); else QASR_DWTC_GO(EK_, false); \
     break;
   switch (ek) {
     QASR_DWTC_CASE(0)
@@ -419,6 +521,7 @@ int qasr_dwconv_tc_launch(const void* x, int x_ld, const int8_t* taps, void* out
     QASR_DWTC_CASE(3)
   }
 #undef QASR_DWTC_CASE
-  if (need_attr) attr_set[ek][dev] = true;
+#undef QASR_DWTC_GO
+  if (need_attr) attr_set[rows][ek][dev] = true;
   return qasr_check_launch("dwconv_tc_kernel");
 }

@@ -126,7 +126,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   if (warp == kMmaWarp && lane == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 32 * kEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
     mbar_init(afull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -351,7 +351,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (g.dbg_skip & 1) {
         // (bring-up: accumulators are dropped)
         tc_fence_before();
-        mbar_arrive(tempty_bar(as));
+        mbar_arrive_warp(tempty_bar(as));
       } else if (!(EPI & kEpiDual) && nseg == 1 && MT == 2) {
         // both M tiles' accumulators leave TMEM first: the buffer goes back to the MMA warp before the math
         int a0[32], a1[32];
@@ -359,7 +359,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tmem_ld32(taddr + BN, a1);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(tempty_bar(as));
+        mbar_arrive_warp(tempty_bar(as));
         finish(0, b, tv, len, a0, a0);
         finish(1, b, tv, len, a1, a1);
       } else {
@@ -372,7 +372,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           tmem_ld_wait();
           if (ms == MT - 1) {
             tc_fence_before();
-            mbar_arrive(tempty_bar(as));
+            mbar_arrive_warp(tempty_bar(as));
           }
           finish(ms, b, tv, len, a0, nseg > 1 ? a1 : a0);
         }

@@ -426,12 +426,15 @@ DW_CASES = [
 ]
 
 
-@pytest.fixture(params=[0, 1], ids=["imma", "tcgen05"])
+@pytest.fixture(params=[0, 1, 2], ids=["imma", "tcgen05", "tcgen05_rows"])
 def dw_engine(request):
-    """Forces one of the two depthwise engines (bring-up knob 8) so both are checked on every case."""
-    L.lib().qasr_debug_set(8, request.param)
+    """Forces one of the depthwise engines (bring-up knobs 8 / 11) so all are checked on every case: IMMA,
+    tcgen05 with TMA-fetched windows, tcgen05 with bulk-copied rows cut into windows in shared memory."""
+    L.lib().qasr_debug_set(8, min(request.param, 1))
+    L.lib().qasr_debug_set(11, 1 if request.param == 2 else -1)
     yield request.param
     L.lib().qasr_debug_set(8, -1)
+    L.lib().qasr_debug_set(11, -1)
 
 
 @pytest.mark.parametrize("fast", [False, True, "f32"], ids=["exact", "fast", "f32"])

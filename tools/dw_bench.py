@@ -43,6 +43,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "occupancy":
             per_sm, run(512, 33, 1, {8: 0, 10: per_sm}), run(512, 75, 1, {8: 0, 10: per_sm}), run(256, 33, 1, {8: 0, 10: per_sm})), flush=True)
 if len(sys.argv) > 1 and sys.argv[1] == "knobs":
     for name, kn in (("full", {}), ("no-epilogue", {6: 1}), ("no-mma", {6: 2}), ("no-stores", {6: 4}), ("no-rebuild", {6: 8}),
-                     ("loads only", {6: 3 + 8}), ("loads+mma", {6: 1 + 8}), ("loads+epi", {6: 2 + 8})):
+                     ("loads only", {6: 3 + 8}), ("loads+mma", {6: 1 + 8}), ("loads+epi", {6: 2 + 8}),
+                     ("rows, no cut", {11: 1, 6: 3 + 8 + 16}), ("cut, no rows", {11: 1, 6: 3 + 8 + 32}), ("neither", {11: 1, 6: 3 + 8 + 48}),
+                     ("row-staged", {11: 1}), ("row-staged loads only", {11: 1, 6: 3 + 8})):
         kn = dict(kn); kn[8] = 1
         print("C=512 k=33 %-12s %6.1f us" % (name, run(512, 33, 1, kn)), flush=True)
