@@ -88,7 +88,10 @@ __device__ __forceinline__ void row_copy_async(uint32_t dst, const void* src, ui
 // EK: 0 = REQUANT all-integer fast path, 1 = REQUANT literal path, 2 = DEQUANT_F32 / RAW_I32,
 //     3 = REQUANT float fast path (QASR_F_FAST_F32)
 template <int KS, int S, bool XS, int EK>
-__global__ void __launch_bounds__(kThreads) dwconv_mma_kernel(const DwArgs a) {
+#ifndef QASR_DW_MIN_BLOCKS
+#define QASR_DW_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kernel(const DwArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint32_t stage[kWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

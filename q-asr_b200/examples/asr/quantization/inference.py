@@ -130,15 +130,22 @@ def main():
     vocabulary = asr_model.decoder.vocabulary
     hypotheses, references = [], []
     audio_s, t0 = 0.0, time.perf_counter()
-    for i, (feats, lens, transcripts) in enumerate(test_data):
-        if i == args.eval_early_stop:
-            break
-        log_probs, encoded_len, greedy = asr_model(processed_signal=feats.cuda().float(),
-                                                   processed_signal_length=lens.cuda())
+    # same loop as the reference (inference.py:127-149), with the host<->device copies pipelined around the kernels
+    meta = []
+
+    def host_batches():
+        for i, (feats, lens, transcripts) in enumerate(test_data):
+            if i == args.eval_early_stop:
+                break
+            meta.append((transcripts, float(lens.sum()) / 100.0))
+            yield feats.float().pin_memory(), lens.to(torch.int32).pin_memory()
+
+    for k, greedy in enumerate(asr_model.transcribe_stream(host_batches())):
         hypotheses += ctc_decoder_predictions_tensor(greedy, vocabulary)
+        transcripts, secs = meta[k]
         if transcripts is not None:
             references += list(transcripts)
-        audio_s += float(lens.sum()) / 100.0
+        audio_s += secs
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print("decoded %d utterances, %.1f audio-seconds in %.3f s (%.0f audio-s/s incl. host)" %

@@ -50,6 +50,70 @@ class EncDecCTCModel(nn.Module):
         from qasr import plan as _plan
         return _plan.get_plan(self.encoder, self.decoder, shape, device, self._plan_cache)
 
+    @torch.no_grad()
+    def transcribe_stream(self, batches, device=None):
+        """Serving loop: the evaluation loop of examples/asr/quantization/inference.py:127-149 (for batch in the
+        loader: .cuda() -> forward -> greedy argmax -> .cpu()) with the copies taken off the critical path.
+        `batches` yields (processed_signal (B, C, T) float32, length (B,) int) HOST tensors, pinned for asynchronous
+        copies; greedy label tensors (B, T') int64 come back on the host, in order.  The host->device copy of batch
+        i+1 runs on a copy stream into the other of two staging buffers while the kernels of batch i run, and the
+        labels of batch i are read back asynchronously and handed out while batch i+1 is in flight.  Falls back to
+        forward() per batch when the model is not in the fused static state."""
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        compute = torch.cuda.current_stream(device)
+        copier = torch.cuda.Stream(device)
+        stage, copied, consumed = [None, None], [None, None], [None, None]
+        host_out, out_ready = [None, None], [None, None]
+        it = iter(batches)
+
+        def prefetch(j, batch):
+            x, n = batch
+            if stage[j] is None or stage[j][0].shape != x.shape:
+                stage[j] = (torch.empty(x.shape, dtype=torch.float32, device=device),
+                            torch.empty(n.shape, dtype=torch.int32, device=device))
+            with torch.cuda.stream(copier):
+                if consumed[j] is not None:
+                    copier.wait_event(consumed[j])       # the kernels that read this staging buffer are done with it
+                stage[j][0].copy_(x, non_blocking=True)
+                stage[j][1].copy_(n.to(torch.int32), non_blocking=True)
+                copied[j] = torch.cuda.Event()
+                copied[j].record(copier)
+
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        prefetch(0, nxt)
+        i, pending = 0, None
+        while nxt is not None:
+            j = i & 1
+            cur, nxt = nxt, next(it, None)
+            if nxt is not None:
+                prefetch(j ^ 1, nxt)
+            compute.wait_event(copied[j])
+            x, n = stage[j]
+            if self._fusable(x):
+                p = self.plan_for(x.shape, device)
+                p.run(x, n)                               # device copy into the plan's input + one graph replay
+                consumed[j] = torch.cuda.Event()
+                consumed[j].record(compute)
+                labels = p.greedy()
+            else:
+                labels = self.forward(processed_signal=x, processed_signal_length=n)[2].to(torch.int32)
+                consumed[j] = torch.cuda.Event()
+                consumed[j].record(compute)
+            if host_out[j] is None or host_out[j].shape != labels.shape:
+                host_out[j] = torch.empty(labels.shape, dtype=torch.int32).pin_memory()
+            host_out[j].copy_(labels, non_blocking=True)   # in stream order: before the next replay overwrites it
+            out_ready[j] = torch.cuda.Event()
+            out_ready[j].record(compute)
+            if pending is not None:
+                out_ready[pending].synchronize()
+                yield host_out[pending].to(torch.long)
+            pending = j
+            i += 1
+        out_ready[pending].synchronize()
+        yield host_out[pending].to(torch.long)
+
     def forward(self, input_signal=None, input_signal_length=None, processed_signal=None,
                 processed_signal_length=None):
         has_input = input_signal is not None and input_signal_length is not None

@@ -356,3 +356,32 @@ def test_jasper10x5dr_static_vs_oracle():
             checked += 1
     assert checked >= 50
     print("jasper plan stats", plan.stats)
+
+
+@pytest.mark.gpu
+def test_transcribe_stream_matches_forward():
+    """The pipelined serving loop (H2D prefetch on a copy stream, asynchronous label read-back) returns exactly
+    forward()'s greedy labels, batch by batch, in order."""
+    from nemo.collections.asr.models.ctc_models import EncDecCTCModel
+    from qasr.params import reestimate_bn_, synthetic_features
+    import nemo.quantization.utils.quantize_model as qm
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    model = EncDecCTCModel.from_topology("tiny_quartznet")
+    model.eval()
+    reestimate_bn_(model.encoder)
+    model.encoder.bn_folding()
+    model = model.to(dev)
+    qm.calibrate(model)
+    for i in range(2):
+        cx, cl = synthetic_features(4, 160, seed=100 + i)
+        e, l, sf = model.encoder(cx.to(dev), cl.to(dev))
+        model.decoder(e, sf)
+    qm.evaluate(model)
+    qm.set_dynamic(model, False)
+    batches = [synthetic_features(4, 160, seed=10 + i, ragged=True) for i in range(5)]
+    want = [model(processed_signal=x.to(dev), processed_signal_length=l.to(dev))[2].cpu() for x, l in batches]
+    got = list(model.transcribe_stream((x.pin_memory(), l.to(torch.int32).pin_memory()) for x, l in batches))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.dtype == torch.long and torch.equal(g, w)
