@@ -212,10 +212,14 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       tc_fence_after();
       const uint32_t d_round = tmem_base + (uint32_t)as * acc_per_stage;
+      // the last time tile of an utterance is partial: issue only the frames it has (N rounded up to 16; the
+      // B descriptor walks the same 128-column box, the untouched accumulator columns are never stored)
+      const int nt_mma = nidx % g.n_tiles;
+      const int cols = min(BN, ((g.T_out - nt_mma * BN + 15) >> 4) << 4);
       for (int sg = 0; sg < nseg; ++sg) {
         const GemmSeg& s = g.seg[sg];
         const int slabs = s.taps * s.cblocks;
-        const uint32_t idesc = s.idesc;
+        const uint32_t idesc = (s.idesc & ~(0x3Fu << 17)) | ((uint32_t)(cols >> 3) << 17);
         uint32_t a_res_lo = a_region_lo + (uint32_t)s.slab0 * kSlabLo;
         for (int it = 0; it < slabs; ++it) {
           mbar_wait(full_bar(stage), phase);
@@ -337,6 +341,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
     // float or integer epilogue: a per-warp, per-M-tile constant (the warp's 32 rows never change)
     auto finish = [&](int ms, int b, int tv, int len, const int (&a0)[32], const int (&a1)[32]) {
+      if (tv >= T_out) return;   // warp-uniform: this column group lies past the end of the utterance
       if ((EPI & kEpiF32) || (EPI == kEpiFast && warp_f32[ms])) finish_t(std::true_type{}, ms, b, tv, len, a0, a1);
       else finish_t(std::false_type{}, ms, b, tv, len, a0, a1);
     };

@@ -107,7 +107,12 @@ static inline cudaError_t qasr_launch_pdl(Kern kern, dim3 grid, dim3 block, size
 
 // m * 2^-e as a double: exact (m has 31 bits), so z * mult rounds exactly like the
 // reference's f64(z) * f64(m) followed by the exact division by 2^e (quant_utils.py:195-196).
-__device__ __forceinline__ double dyad_mult(int m, int e) { return scalbn((double)m, -e); }
+__device__ __forceinline__ double dyad_mult(int m, int e) {
+  // 2^-e assembled from its exponent bits when 0 <= e <= 1022 (always, in practice): three instructions instead
+  // of the generic scalbn; both are exact
+  if ((unsigned)e <= 1022u) return (double)m * __longlong_as_double((long long)(1023 - e) << 52);
+  return scalbn((double)m, -e);
+}
 
 // Per-channel registers of one conv operand.
 struct ChanRegs {
@@ -130,14 +135,15 @@ __device__ __forceinline__ ChanRegs load_chan(const qasr_chan* p, int c) {
   r.mult = dyad_mult(r.m, r.e);
   r.sh = max(r.e - 32, 0);
   r.add = (long long)r.bias * (long long)r.m + ((r.e >= 1 && r.e <= 62) ? (1ll << (r.e - 1)) : 0ll);
-  r.r = __double2float_rn(r.mult);
+  r.r = 0.0f;
   return r;
 }
 // conv-0 parameters with the float-path choice of this launch: every channel (QASR_F_FAST_F32), the proved
 // channels of the optional table, or none
 __device__ __forceinline__ ChanRegs load_chan0(const EpiArgs& ep, int c) {
   ChanRegs r = load_chan(ep.ch0, c);
-  if (!(ep.flags & QASR_F_FAST_F32)) r.r = ep.rf != nullptr ? __ldg(ep.rf + c) : 0.0f;
+  if (ep.flags & QASR_F_FAST_F32) r.r = __double2float_rn(dyad_mult(r.m, r.e));
+  else if (ep.rf != nullptr) r.r = __ldg(ep.rf + c);
   return r;
 }
 
