@@ -248,6 +248,9 @@ def run_ours(args):
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms, serial_ms = float(t[0]), float(t[1]), float(t[2])
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()   # clean shutdown: no NCCL warning after the JSON line
     audio_s_per_step = world * B * T / FRAMES_PER_AUDIO_SECOND
     value = audio_s_per_step * args.steps / (total_ms / 1e3)
     e2e_value = audio_s_per_step * args.steps / (e2e_ms / 1e3)
