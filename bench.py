@@ -134,6 +134,16 @@ def kernel_breakdown(plan, flush, iters=3):
     return classes
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of each dominant-kernel class, from the committed
+# `ncu --set full` capture (bench workload, a 512-channel layer: 52.4 MB algorithmic bytes per launch)
+NCU_TRAFFIC = {
+    "dwconv": dict(bytes=27142400, note="512-channel depthwise layer, 52.4 MB algorithmic per launch; the 26 MB output "
+                                        "stays in the 126 MB L2 (profiles/r01_ncu_dw512_gemm512.txt)"),
+    "gemm_i8_tc": dict(bytes=26611200, note="512x512 pointwise layer, 52.4 MB algorithmic per launch; output stays in L2 "
+                                            "(profiles/r01_ncu_dw512_gemm512.txt)"),
+}
+
+
 def apply_debug_knobs():
     """QASR_DEBUG="4=1,5=1" -> qasr_debug_set(4, 1), (5, 1): schedule experiments only."""
     spec = os.environ.get("QASR_DEBUG")
@@ -265,7 +275,9 @@ def run_ours(args):
     achieved = classes[dom]["bytes"] / (classes[dom]["ms"] / 1e3) / 1e9
     macs = sum(m for (n, _), m in zip(plan.ops, plan.op_macs) if n.startswith("gemm_"))
     roofline = dict(bound="hbm", kernel=dom, achieved=round(achieved, 1), peak=peak, unit="GB/s",
-                    frac=round(achieved / peak, 4), traffic=None, peak_source=peak_src,
+                    frac=round(achieved / peak, 4),
+                    traffic=NCU_TRAFFIC.get(dom, {}).get("bytes"), traffic_note=NCU_TRAFFIC.get(dom, {}).get("note"),
+                    peak_source=peak_src,
                     launches_per_step=classes[dom]["launches"],
                     algorithmic_bytes_per_step=classes[dom]["bytes"],
                     kernel_ms_per_step=round(classes[dom]["ms"], 4),
