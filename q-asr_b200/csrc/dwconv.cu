@@ -326,11 +326,11 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
   int rc = qasr_validate_epilogue(epi, false);
   if (rc) return rc;
 
-  // engine choice (tools/dw_bench.py, batch 64 x 800 frames x 512 channels, both with the float epilogue
-  // choice hoisted out of the loops): IMMA 22.7 / 24.2 / 30.9 us for k = 33 / 75 / 87-dilated against
-  // 30.9 / 31.5 / 34.6 us on tcgen05, whose TMA row fetches (6.5 clk per 128-byte row and 1.6x window overlap)
-  // and 640-thread epilogue do not yet overlap; so the IMMA kernel runs wherever its 6 x 32-tap window reaches
-  // and the tcgen05 kernel covers the longer windows.  Bring-up knob 8 forces one engine (0 = IMMA, 1 = tcgen05).
+  // engine choice (tools/dw_bench.py, batch 64 x 800 frames x 512 channels, float epilogue): IMMA 19.8 / 21.7 / 28.6 us
+  // for k = 33 / 75 / 87-dilated against 22.2 / 24.5 / 28.1 us on tcgen05 with TMA-fetched windows (its input
+  // delivery costs 6.5 clk per 128-byte row per SM at 1.6x window overlap = 11 us, which the 20 epilogue warps'
+  // drain does not yet hide).  The IMMA kernel runs wherever its 6 x 32-tap window reaches, the tcgen05 kernel
+  // covers the longer windows.  Bring-up knob 8 forces one engine (0 = IMMA, 1 = tcgen05).
   const int64_t table_bytes = dw_table_bytes(C, k, stride, dilation, pad);
   const bool tc_ok = qasr_dwconv_tc_supported(B, C, T_in, T_out, k, stride, dilation, pad);
   const long long knob = qasr_debug_get(8);

@@ -62,13 +62,15 @@ struct DwTcArgs {
   int nb;            // band chunks (16 B) per Tc row, upper bound
   uint32_t idesc;
   uint32_t tmat_bytes, stage_bytes;
-  // row-staged variant (ROWS): whole input rows are bulk-copied into shared memory once per (channel, utterance
-  // chunk) and the epilogue warps cut the overlapping K-major windows out of them
+  // row-staged variant (ROWS): per unit, the piece of every utterance row that its time blocks need (one bulk copy
+  // per row, two piece buffers in flight) lands in shared memory and the epilogue warps cut the overlapping
+  // K-major windows out of it; bytes outside [0, copy_bytes) of a row are the conv padding and are cut as zeros
   const uint8_t* x;
   int x_ld;
-  int copy_bytes;      // T_in rounded up to 16: bytes of one row copy
-  int row_pitch;       // bytes per staged row: [pad + o zeros | row | zeros up to the last window's end]
-  uint32_t rows_bytes; // bbox * row_pitch
+  int copy_bytes;      // T_in rounded up to 16: valid bytes of one row
+  int row_pitch;       // bytes of one row's piece: (tb_per_tile - 1) * N * stride + slabs * 128
+  uint32_t rows_bytes; // one piece buffer: bbox * row_pitch (two of them follow the A stages)
+  unsigned long long* dbg_trace;   // qasr_debug_set 7: device buffer, role timeline of CTA 0 (3 x 256 slots)
   int dbg_skip;      // qasr_debug_set 6: 1 = epilogue does nothing, 2 = no MMA issue, 4 = no stores, 8 = no Tc rebuild
   EpiArgs ep;
 };
@@ -79,6 +81,8 @@ __device__ __forceinline__ bool elect_one() {
   return p != 0;
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+#define DWTC_TRACE(role, n) do { if (a.dbg_trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (n) < 256) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.dbg_trace[(role) * 256 + (n)] = t_; } } while (0)
 
 // EK: 0 = REQUANT all-integer fast path, 1 = REQUANT literal path, 2 = DEQUANT_F32 / RAW_I32,
 //     3 = REQUANT float fast path (QASR_F_FAST_F32)
@@ -91,16 +95,16 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
   const uint32_t tmat_base = smem_base;                                      // 2 x Tc
   const uint32_t stage_base = tmat_base + 2u * a.tmat_bytes;                 // stages x A tile
   const uint32_t rows_off = 2u * a.tmat_bytes + (uint32_t)a.stages * a.stage_bytes;   // ROWS: staged input rows
-  const uint32_t z_off = rows_off + (ROWS ? a.rows_bytes : 0u);
+  const uint32_t z_off = rows_off + (ROWS ? 2u * a.rows_bytes : 0u);
   const uint32_t bars = smem_base + z_off + 4u * (uint32_t)a.zl;             // zl is a multiple of 16
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * kMaxStages + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * kMaxStages + 2 + s); };
   auto mfull_bar = [&](int s) { return bars + 8u * (2 * kMaxStages + 4 + s); };
-  const uint32_t rows_full_bar = bars + 8u * (2 * kMaxStages + 6), rows_empty_bar = bars + 8u * (2 * kMaxStages + 7);
-  const uint32_t init_bar = bars + 8u * (2 * kMaxStages + 8);
-  const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 9);
+  auto pfull_bar = [&](int s) { return bars + 8u * (2 * kMaxStages + 6 + s); };
+  auto pempty_bar = [&](int s) { return bars + 8u * (2 * kMaxStages + 8 + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 10);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform role index
@@ -111,10 +115,9 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
   if (warp == kProducerWarp && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
   if (warp == kMmaWarp && lane == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_bar(s), ROWS ? kEpiWarps : 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(rows_full_bar, 1);
-    mbar_init(rows_empty_bar, kEpiWarps);
-    mbar_init(init_bar, kEpiWarps);
     for (int s = 0; s < 2; ++s) {
+      mbar_init(pfull_bar(s), 1);
+      mbar_init(pempty_bar(s), kEpiWarps);
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), kEpiWarps);
       mbar_init(mfull_bar(s), kEpiWarps);
@@ -132,24 +135,39 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == kProducerWarp && ROWS) {
-    // ===================== row producer: one bulk copy per (utterance, channel) row =====================
-    const int ntbg = a.ntbg, nbch = a.tiles_per_ch / a.ntbg, bbox = a.bbox;
-    const uint32_t rows_base = smem_base + rows_off + (uint32_t)(a.pad + a.o);
-    mbar_wait(init_bar, 0u);   // halos zeroed by the epilogue warps (generic proxy), fenced before their arrive
+    // ===================== row producer: per unit, one bulk copy per utterance row =====================
+    const int tiles_per_ch = a.tiles_per_ch, ntbg = a.ntbg, bbox = a.bbox;
+    const int piece_step = a.tb_per_tile * a.N * a.stride, piece_len = a.row_pitch, tshift = a.pad + a.o;
     pdl_wait();                // the activation rows come from the previous kernel
+    int c = u0 / tiles_per_ch, bc, tbg;
+    {
+      const int r = u0 - c * tiles_per_ch;
+      bc = r / ntbg;
+      tbg = r - bc * ntbg;
+    }
     uint32_t phase = 0;
-    for (int ch = u0 / ntbg; ch <= (u1 - 1) / ntbg; ++ch) {   // chunk = (channel, utterance chunk)
-      const int c = ch / nbch, b0 = (ch - c * nbch) * bbox;
+    int pb = 0;
+    for (int u = u0; u < u1; ++u) {
+      const int b0 = bc * bbox;
       const int nrows = min(bbox, a.B - b0);
-      mbar_wait(rows_empty_bar, phase ^ 1u);
-      if (lane == 0) mbar_expect_tx(rows_full_bar, (a.dbg_skip & 32) ? 0u : (uint32_t)(nrows * a.copy_bytes));
+      // the piece covers row bytes [t_p, t_p + piece_len); only its part inside [0, copy_bytes) exists in memory
+      const int t_p = tbg * piece_step - tshift;
+      const int src0 = max(t_p, 0);
+      const int len = min(t_p + piece_len, a.copy_bytes) - src0;   // multiples of 16 throughout
+      mbar_wait(pempty_bar(pb), phase ^ 1u);
+      if (lane == 0) mbar_expect_tx(pfull_bar(pb), (len > 0 && !(a.dbg_skip & 32)) ? (uint32_t)(nrows * len) : 0u);
       __syncwarp();
-      for (int r = lane; r < nrows && !(a.dbg_skip & 32); r += 32) {
-        const uint8_t* src = a.x + ((size_t)(b0 + r) * a.C + c) * a.x_ld;
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(rows_base + (uint32_t)(r * a.row_pitch)), "l"(src), "r"((uint32_t)a.copy_bytes), "r"(rows_full_bar) : "memory");
+      if (len > 0 && !(a.dbg_skip & 32)) {
+        const uint32_t dst0 = smem_base + rows_off + (uint32_t)pb * a.rows_bytes + (uint32_t)(src0 - t_p);
+        const uint8_t* srow = a.x + ((size_t)b0 * a.C + c) * a.x_ld + src0;
+        for (int r = lane; r < nrows; r += 32)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst0 + (uint32_t)(r * piece_len)), "l"(srow + (size_t)r * a.C * a.x_ld), "r"((uint32_t)len),
+                         "r"(pfull_bar(pb)) : "memory");
       }
-      phase ^= 1u;
+      pb ^= 1;
+      phase ^= (uint32_t)(pb == 0);
+      if (++tbg == ntbg) { tbg = 0; if (++bc * ntbg == tiles_per_ch) { bc = 0; ++c; } }
     }
   } else if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
@@ -204,6 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       mbar_wait(full_bar(stage), phase);
       tc_fence_after();
+      DWTC_TRACE(1, 2 * (u - u0));
       if (leader) {
         const uint32_t d_tmem = tmem_base + (uint32_t)as * kAccStride;
         for (int sl = 0; sl < slabs; ++sl) {
@@ -218,6 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
         if (!ROWS) tc_commit(empty_bar(stage));   // ROWS: the builders reuse a stage only after draining its tile
         tc_commit(tfull_bar(as));
       }
+      DWTC_TRACE(1, 2 * (u - u0) + 1);
       stage_lo += stage_step_lo;
       if (++stage == stages) { stage = 0; phase ^= 1u; stage_lo = stage_lo0; }
       if (++as == 2) { as = 0; aphase ^= 1u; }
@@ -234,12 +254,6 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
     // zero both Tc buffers once: the band positions never move, so zero chunks stay zero for every channel
     for (uint32_t i = tid; i < 2u * a.tmat_bytes / 16u; i += kEpiThreads)
       reinterpret_cast<uint4*>(smem_gen)[i] = make_uint4(0, 0, 0, 0);
-    if (ROWS) {   // staged rows: the halos on both sides of every row stay zero for the whole kernel (conv padding)
-      for (uint32_t i = tid; i < a.rows_bytes / 16u; i += kEpiThreads)
-        reinterpret_cast<uint4*>(smem_gen + rows_off)[i] = make_uint4(0, 0, 0, 0);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // before the bulk copies (async proxy) land
-      mbar_arrive_warp(init_bar);
-    }
     epi_bar_sync();
 
     auto build = [&](int c, int buf) {
@@ -275,75 +289,110 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
       epi_bar_sync();   // nobody still reads the tap copies when the next build overwrites them
     };
 
-    // ROWS: cut the K-major input windows of unit u out of the staged rows into A stage (u - u0) & 1
-    uint32_t rows_phase = 0;
-    auto prebuild = [&](int u) {
-      const int r = u % tiles_per_ch, tbg = r % ntbg;
-      if (u == u0 || tbg == 0) {   // first unit of a (channel, utterance chunk): its rows must have landed
-        mbar_wait(rows_full_bar, rows_phase);
-        rows_phase ^= 1u;
-      }
-      const int st = (u - u0) & 1;
-      uint8_t* const dst = smem_gen + 2u * a.tmat_bytes + (uint32_t)st * a.stage_bytes;
-      const uint8_t* const rows = smem_gen + rows_off;
-      const int tstep = N * S, row_pitch = a.row_pitch, n_tblk = a.n_tblk;
-      for (int idx = tid; idx < 128 * nq && !(a.dbg_skip & 16); idx += kEpiThreads) {
-        const int rr = idx / nq, q = idx - rr * nq;
-        const int tb = rr / bbox, bl = rr - tb * bbox;
-        const int tblk = tbg * tbpt + tb;
-        if (tblk < n_tblk) {
-          const uint4 v = *reinterpret_cast<const uint4*>(rows + bl * row_pitch + tblk * tstep + q * 16);
-          *reinterpret_cast<uint4*>(dst + (q >> 3) * kSlabBytes + rr * 128 + (((q & 7) ^ (rr & 7)) << 4)) = v;
+    // Per-unit control is kept free of divisions: a single warp runs dependent scalar code at ~6 clk per
+    // instruction (measured: ~1 us per unit of pure index arithmetic and barrier traffic before this rewrite), so
+    // the (channel, utterance chunk, time-block group) decomposition is carried incrementally and everything that
+    // depends on the thread only is computed once.
+    const int n_tblk = a.n_tblk;
+    // ROWS: this thread's 16-byte chunks of a 128-row x (slabs x 128 B) window tile
+    constexpr int kCut = 4;   // 128 rows x 16 chunks (2 slabs) / 640 threads
+    int cut_src[kCut], cut_dst[kCut], cut_tb[kCut], cut_t[kCut];
+#pragma unroll
+    for (int i = 0; i < kCut; ++i) {
+      const int idx = tid + i * kEpiThreads;
+      const int rr = idx / nq, q = idx - rr * nq;
+      const int tb = rr / bbox, bl = rr - tb * bbox;
+      cut_tb[i] = idx < 128 * nq ? tb : (1 << 20);                      // beyond the tile: never valid
+      cut_t[i] = tb * (N * S) + q * 16;
+      cut_src[i] = bl * a.row_pitch + cut_t[i];
+      cut_dst[i] = (q >> 3) * (int)kSlabBytes + rr * 128 + (((q & 7) ^ (rr & 7)) << 4);
+    }
+    // cut the windows of unit number i (time-block group tbg) out of piece buffer i & 1 into A stage i & 1
+    const int piece_step = tbpt * N * S, tshift = a.pad + o, copy_bytes = a.copy_bytes;
+    uint32_t piece_phase = 0;
+    auto prebuild = [&](int i, int tbg) {
+      const int pb = i & 1;
+      mbar_wait(pfull_bar(pb), piece_phase);
+      piece_phase ^= (uint32_t)pb;   // flips after buffer 1, i.e. once per pair of units
+      uint8_t* const dst = smem_gen + 2u * a.tmat_bytes + (uint32_t)pb * a.stage_bytes;
+      const uint8_t* const src = smem_gen + rows_off + (uint32_t)pb * a.rows_bytes;
+      const int tb_left = n_tblk - tbg * tbpt;    // time blocks that exist in this group
+      const int t_p = tbg * piece_step - tshift;  // row byte at piece offset 0
+      const bool interior = t_p >= 0 && t_p + a.row_pitch <= copy_bytes;   // warp-uniform: no padding inside
+      if (!(a.dbg_skip & 16)) {
+#pragma unroll
+        for (int j = 0; j < kCut; ++j) {
+          if (cut_tb[j] < tb_left) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            const int t = t_p + cut_t[j];
+            if (interior || (t >= 0 && t < copy_bytes)) v = *reinterpret_cast<const uint4*>(src + cut_src[j]);
+            *reinterpret_cast<uint4*>(dst + cut_dst[j]) = v;
+          }
         }
       }
-      // generic writes -> tcgen05 (async proxy) reads: the warp's writes are ordered before lane 0 by the
-      // __syncwarp, lane 0 fences them for the async proxy and arrives (one fence per warp, not per thread)
+      // generic reads of the piece are done and generic writes of the windows must reach the async proxy (tcgen05
+      // reads them, the next bulk copy overwrites the piece): the warp's accesses are ordered before lane 0 by the
+      // __syncwarp, lane 0 fences for the async proxy and arrives (one fence per warp, not per thread)
       __syncwarp();
       if (lane == 0) {
-        if (!(a.dbg_skip & 64)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(full_bar(st));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(full_bar(pb));
+        mbar_arrive(pempty_bar(pb));
       }
-      if (u + 1 == u1 || tbg == ntbg - 1) mbar_arrive_warp(rows_empty_bar);   // last window of this chunk is cut
     };
 
+    // this thread's row of the 128-row tile
+    const int rowi = quarter * 32 + lane;
+    const int my_tb = rowi / bbox, my_bl = rowi - my_tb * bbox;
+    const int t_store_end = ((a.T_out + 15) >> 4) << 4;   // stores cover T_out rounded up to 16 (zero filled)
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool masked = a.ep.flags & QASR_F_MASK;
+
     int chan_idx = 0;
-    if (u0 < u1) build(u0 / tiles_per_ch, 0);   // taps are constants of the plan: built before the dependency wait
+    // unit u0 decomposed once; afterwards (c, bc, tbg) advance incrementally
+    int c = u0 / tiles_per_ch, bc, tbg;
+    {
+      const int r = u0 - c * tiles_per_ch;
+      bc = r / ntbg;
+      tbg = r - bc * ntbg;
+    }
+    if (u0 < u1) build(c, 0);   // taps are constants of the plan: built before the dependency wait
     pdl_wait();
-    if (ROWS && u0 < u1) prebuild(u0);
+    if (ROWS && u0 < u1) prebuild(0, tbg);
     int as = 0;
     uint32_t aphase = 0;
-    int cur_c = -1;
-    ChanRegs c0 = load_chan0(a.ep, 0);
+    bool new_channel = true;
+    ChanRegs c0 = load_chan0(a.ep, c);
     for (int u = u0; u < u1; ++u) {
-      const int c = u / tiles_per_ch, r = u - c * tiles_per_ch;
-      // the next unit's windows: cut them before draining this unit so its MMAs overlap the drain, unless they
-      // belong to the next chunk of rows, which is still in flight (then drain first and hide the copy latency)
-      const bool next_new_chunk = ((u + 1) % tiles_per_ch) % ntbg == 0;
-      if (ROWS && u + 1 < u1 && !next_new_chunk) prebuild(u + 1);   // its stage held unit u - 1, already drained
-      if (c != cur_c) {
-        if (cur_c >= 0) ++chan_idx;
-        cur_c = c;
-        c0 = load_chan0(a.ep, c);
+      // next unit's coordinates
+      int nc = c, nbc = bc, ntg = tbg + 1;
+      if (ntg == ntbg) { ntg = 0; if (++nbc * ntbg == tiles_per_ch) { nbc = 0; ++nc; } }
+      const bool has_next = u + 1 < u1;
+      if (warp == 0) DWTC_TRACE(2, 4 * (u - u0));
+      // the next unit's windows are cut before this unit is drained, so its MMAs overlap the drain (its piece was
+      // requested two units ago; its A stage held unit u - 1, whose accumulator is already drained)
+      if (ROWS && has_next) prebuild(u + 1 - u0, ntg);
+      if (warp == 0) DWTC_TRACE(2, 4 * (u - u0) + 1);
+      if (new_channel) {
+        if (u != u0) { ++chan_idx; c0 = load_chan0(a.ep, c); }
         // the other buffer belonged to channel c-1, whose last accumulator we have already drained
         if ((c + 1) * tiles_per_ch < u1) build(c + 1, (chan_idx + 1) & 1);
       }
-      const int bc = r / ntbg, tbg = r - bc * ntbg;
-      const int rowi = quarter * 32 + lane;
-      const int tb = rowi / bbox, b = bc * bbox + (rowi - tb * bbox);
-      const int tblk = tbg * tbpt + tb;
-      const bool valid = tblk < a.n_tblk && b < a.B;
+      const int b = bc * bbox + my_bl;
+      const int tblk = tbg * tbpt + my_tb;
+      const bool valid = tblk < n_tblk && b < a.B;
       const int bb = valid ? b : 0;
-      const int len = (a.ep.flags & QASR_F_MASK) ? min(a.ep.out_lens[bb], a.T_out) : a.T_out;
+      const int len = masked ? min(a.ep.out_lens[bb], a.T_out) : a.T_out;
       const size_t row = (size_t)bb * a.C + c;
-      const int t_store_end = ((a.T_out + 15) >> 4) << 4;   // stores cover T_out rounded up to 16 (zero filled)
 
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      if (warp == 0) DWTC_TRACE(2, 4 * (u - u0) + 2);
       auto drain = [&](auto f32_tag) {   // float or integer epilogue, chosen once per unit (one channel per unit)
       constexpr bool F32 = decltype(f32_tag)::value;
       for (int ck = cg; ck * 32 < N && !(a.dbg_skip & 1); ck += kColGroups) {
         int acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * kAccStride + (uint32_t)(ck * 32), acc);
+        tmem_ld32(lane_taddr + (uint32_t)as * kAccStride + (uint32_t)(ck * 32), acc);
         tmem_ld_wait();
         const int t0 = tblk * N + ck * 32;
         if (EK != 2) {
@@ -386,8 +435,11 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
       if (EK == 3 || (EK == 0 && c0.r != 0.0f)) drain(std::true_type{}); else drain(std::false_type{});
       tc_fence_before();
       mbar_arrive_warp(tempty_bar(as));
-      if (++as == 2) { as = 0; aphase ^= 1u; }
-      if (ROWS && u + 1 < u1 && next_new_chunk) prebuild(u + 1);
+      as ^= 1;
+      aphase ^= (uint32_t)(as == 0);
+      if (warp == 0) DWTC_TRACE(2, 4 * (u - u0) + 3);
+      new_channel = nc != c;
+      c = nc; bc = nbc; tbg = ntg;
     }
   }
 
@@ -435,14 +487,32 @@ int qasr_dwconv_tc_launch(const void* x, int x_ld, const int8_t* taps, void* out
   a.span = (k - 1) * dilation + 1;
   a.zl = ((a.span + 32 + 15) / 16) * 16;
   const uint32_t fixed = 1024 /*align*/ + 4u * (uint32_t)a.zl + 8u * (2 * kMaxStages + 12);
-  // time-block length: the candidate with the least padded work whose window fits kMaxSlabs slabs and 2 stages
+  // time-block length.  Row-staged variant (knob 11 = 1): the epilogue warps are the critical resource, so take the
+  // N with the fewest drain rounds (time blocks x passes of the 5 column groups) among those with <= 2 slabs whose
+  // buffers fit; TMA-window variant: least padded work (fetched window bytes x MMA depth).
+  const bool want_rows = qasr_debug_get(11) == 1;
+  const int bbox_plan = B >= 128 ? 128 : (B > 32 ? 64 : (B > 16 ? 32 : (B > 8 ? 16 : 8)));
   int bestN = 0, best_cost = 0;
-  for (int N : {160, 128, 96, 64, 32}) {
-    const int slabs = ceil_div(stride * (N - 1) + a.span + a.o, 128);
-    if (slabs > kMaxSlabs) continue;
-    if (fixed + 2u * slabs * N * 128u + 2u * slabs * kSlabBytes > kSmemBudget) continue;
-    const int cost = ceil_div(T_out, N) * ceil_div(N / 32, kColGroups) * slabs;   // ~ epilogue rounds x MMA depth
-    if (bestN == 0 || cost < best_cost) { bestN = N; best_cost = cost; }
+  bool rows = false;
+  if (want_rows) {
+    for (int N : {160, 128, 96, 64, 32}) {
+      const int slabs = ceil_div(stride * (N - 1) + a.span + a.o, 128);
+      if (slabs > 2) continue;
+      const int n_tblk = ceil_div(T_out, N);
+      const int pitch = (128 / bbox_plan - 1) * N * stride + slabs * 128;   // one row's piece
+      if (fixed + 2u * slabs * N * 128u + 2u * slabs * kSlabBytes + 2u * (uint32_t)bbox_plan * pitch > kSmemBudget) continue;
+      const int cost = n_tblk * ceil_div(N / 32, kColGroups);
+      if (bestN == 0 || cost < best_cost) { bestN = N; best_cost = cost; rows = true; }
+    }
+  }
+  if (!rows) {
+    for (int N : {160, 128, 96, 64, 32}) {
+      const int slabs = ceil_div(stride * (N - 1) + a.span + a.o, 128);
+      if (slabs > kMaxSlabs) continue;
+      if (fixed + 2u * slabs * N * 128u + 2u * slabs * kSlabBytes > kSmemBudget) continue;
+      const int cost = ceil_div(T_out, N) * ceil_div(N / 32, kColGroups) * slabs;   // ~ epilogue rounds x MMA depth
+      if (bestN == 0 || cost < best_cost) { bestN = N; best_cost = cost; }
+    }
   }
   if (bestN == 0) {
     qasr_set_error("dwconv(tc): tap span %d does not fit the %d x 128-byte window", a.span, kMaxSlabs);
@@ -451,7 +521,7 @@ int qasr_dwconv_tc_launch(const void* x, int x_ld, const int8_t* taps, void* out
   a.N = bestN;
   a.slabs = ceil_div(stride * (a.N - 1) + a.span + a.o, 128);
   a.nb = (a.span + 14) / 16 + 1;
-  a.bbox = B >= 128 ? 128 : (B > 32 ? 64 : (B > 16 ? 32 : (B > 8 ? 16 : 8)));
+  a.bbox = bbox_plan;
   a.tb_per_tile = 128 / a.bbox;
   a.n_tblk = ceil_div(T_out, a.N);
   a.ntbg = ceil_div(a.n_tblk, a.tb_per_tile);
@@ -459,22 +529,14 @@ int qasr_dwconv_tc_launch(const void* x, int x_ld, const int8_t* taps, void* out
   a.units = C * a.tiles_per_ch;
   a.tmat_bytes = (uint32_t)a.slabs * a.N * 128u;
   a.stage_bytes = (uint32_t)a.slabs * kSlabBytes;
-  // row-staged variant (bring-up knob 11 = 1; needs one utterance chunk of rows next to two A stages).  It is
-  // bit-exact but measured SLOWER than the TMA-window variant (46 us against 31 us, k = 33, 512 channels): the bare
-  // hand-off skeleton of its three-stage pipeline (rows -> windows -> MMA -> drain) already costs 21 us.  Kept for
-  // the next round's work on that pipeline; the default is the TMA-window variant.
+  // row-staged variant (bring-up knob 11 = 1): two piece buffers next to two A stages.  Bit-exact, but measured slower
+  // than TMA windows (34.7 us against 22.2 us, k = 33, 512 channels, float epilogue): 64 bulk copies of ~416 B per
+  // unit cost ~47 clk each on the SM's copy engine (16 us per layer), more than the 6.5 clk per 128-byte TMA row.
   a.x = static_cast<const uint8_t*>(x);
   a.x_ld = x_ld;
   a.copy_bytes = ((T_in + 15) / 16) * 16;
-  {
-    const int reach = (a.n_tblk - 1) * a.N * stride + a.slabs * 128;
-    int pitch = pad + a.o + a.copy_bytes;
-    if (pitch < reach) pitch = reach;
-    a.row_pitch = ((pitch + 15) / 16) * 16;
-    a.rows_bytes = (uint32_t)a.bbox * (uint32_t)a.row_pitch;
-  }
-  const bool rows = qasr_debug_get(11) == 1 &&
-                    fixed + 2u * a.tmat_bytes + 2u * a.stage_bytes + a.rows_bytes <= kSmemBudget;
+  a.row_pitch = (a.tb_per_tile - 1) * a.N * stride + a.slabs * 128;
+  a.rows_bytes = (uint32_t)a.bbox * (uint32_t)a.row_pitch;
   if (rows) {
     a.stages = 2;
   } else {
@@ -482,13 +544,14 @@ int qasr_dwconv_tc_launch(const void* x, int x_ld, const int8_t* taps, void* out
     a.stages = (int)((kSmemBudget - fixed - 2u * a.tmat_bytes) / a.stage_bytes);
     if (a.stages > kMaxStages) a.stages = kMaxStages;
   }
-  const uint32_t smem_bytes = fixed + 2u * a.tmat_bytes + (uint32_t)a.stages * a.stage_bytes + a.rows_bytes;
+  const uint32_t smem_bytes = fixed + 2u * a.tmat_bytes + (uint32_t)a.stages * a.stage_bytes + 2u * a.rows_bytes;
   const uint32_t a_signed = (epi->flags & QASR_F_B_SIGNED) ? 1u : 0u;   // the activation codes are operand A here
   // instruction descriptor: D=S32, A=(un)signed 8-bit K-major (codes), B=signed 8-bit K-major (Tc), N, M=128
   a.idesc = (2u << 4) | (a_signed << 7) | (1u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(a.N >> 3) << 17) |
             ((uint32_t)(128 >> 4) << 24);
   a.ep = make_epi_args(epi);
   a.dbg_skip = qasr_debug_get(6) > 0 ? (int)qasr_debug_get(6) : 0;
+  a.dbg_trace = qasr_debug_get(7) > 0 ? reinterpret_cast<unsigned long long*>(qasr_debug_get(7)) : nullptr;
   CUtensorMap map;
   int rc = make_map_rows(&map, x, T_in, C, B, x_ld, a.bbox);
   if (rc) return rc;
