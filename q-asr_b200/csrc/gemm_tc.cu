@@ -163,15 +163,23 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t stage_bytes = g.stage_bytes;
     int stage = 0;
     uint32_t phase = 0;
-    for (int nidx = n_first; nidx < n_total; nidx += n_step) {
-      const int nt = nidx % n_tiles, b = nidx / n_tiles;
-      for (int sg = 0; sg < nseg; ++sg) {
+    // (time tile, utterance) of the walk carried incrementally: no division on the per-round path
+    const int step_nt = n_step % n_tiles, step_b = n_step / n_tiles;
+    int nt = n_first % n_tiles, b = n_first / n_tiles;
+    const int seg_taps[2] = {g.seg[0].taps, g.seg[1].taps}, seg_cblocks[2] = {g.seg[0].cblocks, g.seg[1].cblocks};
+    const int seg_tstep[2] = {BN * g.seg[0].stride, BN * g.seg[1].stride}, seg_dil[2] = {g.seg[0].dil, g.seg[1].dil};
+    const int seg_pad[2] = {g.seg[0].pad, g.seg[1].pad};
+    for (int nidx = n_first; nidx < n_total; nidx += n_step, nt += step_nt, b += step_b) {
+      if (nt >= n_tiles) { nt -= n_tiles; ++b; }
+#pragma unroll
+      for (int sg = 0; sg < 2; ++sg) {
+        if (sg >= nseg) break;
         const GemmSeg& s = g.seg[sg];
         const CUtensorMap* mA = sg == 0 ? &tmA0 : &tmA1;
         const CUtensorMap* mB = sg == 0 ? &tmB0 : &tmB1;
-        const int taps = s.taps, cblocks = s.cblocks;
+        const int taps = seg_taps[sg], cblocks = seg_cblocks[sg];
         for (int tap = 0; tap < taps; ++tap) {
-          const int tcoord = nt * BN * s.stride + tap * s.dil - s.pad;
+          const int tcoord = nt * seg_tstep[sg] + tap * seg_dil[sg] - seg_pad[sg];
           for (int cb = 0; cb < cblocks; ++cb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (leader) {
@@ -208,19 +216,26 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_wait(afull_bar, 0u);
       tc_fence_after();
     }
-    for (int nidx = n_first; nidx < n_total; nidx += n_step) {
+    const int n_tiles_m = g.n_tiles, step_nt = n_step % n_tiles_m, T_out_m = g.T_out;
+    int nt_mma = n_first % n_tiles_m;
+    // per-segment constants live in registers: the kernel-parameter bank costs a dependent load per use
+    const int seg_slabs[2] = {g.seg[0].taps * g.seg[0].cblocks, g.seg[1].taps * g.seg[1].cblocks};
+    const uint32_t seg_idesc[2] = {g.seg[0].idesc & ~(0x3Fu << 17), g.seg[1].idesc & ~(0x3Fu << 17)};
+    const uint32_t seg_a_lo[2] = {a_region_lo + (uint32_t)g.seg[0].slab0 * kSlabLo, a_region_lo + (uint32_t)g.seg[1].slab0 * kSlabLo};
+    for (int nidx = n_first; nidx < n_total; nidx += n_step, nt_mma += step_nt) {
+      if (nt_mma >= n_tiles_m) nt_mma -= n_tiles_m;
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       tc_fence_after();
       const uint32_t d_round = tmem_base + (uint32_t)as * acc_per_stage;
       // the last time tile of an utterance is partial: issue only the frames it has (N rounded up to 16; the
       // B descriptor walks the same 128-column box, the untouched accumulator columns are never stored)
-      const int nt_mma = nidx % g.n_tiles;
-      const int cols = min(BN, ((g.T_out - nt_mma * BN + 15) >> 4) << 4);
-      for (int sg = 0; sg < nseg; ++sg) {
-        const GemmSeg& s = g.seg[sg];
-        const int slabs = s.taps * s.cblocks;
-        const uint32_t idesc = (s.idesc & ~(0x3Fu << 17)) | ((uint32_t)(cols >> 3) << 17);
-        uint32_t a_res_lo = a_region_lo + (uint32_t)s.slab0 * kSlabLo;
+      const int cols = min(BN, ((T_out_m - nt_mma * BN + 15) >> 4) << 4);
+#pragma unroll
+      for (int sg = 0; sg < 2; ++sg) {
+        if (sg >= nseg) break;
+        const int slabs = seg_slabs[sg];
+        const uint32_t idesc = seg_idesc[sg] | ((uint32_t)(cols >> 3) << 17);
+        uint32_t a_res_lo = seg_a_lo[sg];
         for (int it = 0; it < slabs; ++it) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -346,8 +361,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       else finish_t(std::false_type{}, ms, b, tv, len, a0, a1);
     };
 
-    for (int nidx = n_first; nidx < g.n_total; nidx += g.n_step) {
-      const int nt = nidx % n_tiles, b = nidx / n_tiles;
+    const int n_total = g.n_total, n_step = g.n_step, step_nt = n_step % n_tiles, step_b = n_step / n_tiles;
+    int nt = n_first % n_tiles, b = n_first / n_tiles;
+    for (int nidx = n_first; nidx < n_total; nidx += n_step, nt += step_nt, b += step_b) {
+      if (nt >= n_tiles) { nt -= n_tiles; ++b; }
       const int len = masked ? min(g.ep.out_lens[b], T_out) : T_out;
       const int tv = nt * BN + cgroup * 32;   // first frame of this thread's 32 columns
       const uint32_t taddr = lane_base + (uint32_t)as * acc_per_stage;
