@@ -68,6 +68,7 @@ struct GemmArgs {
   int a_resident;    // weights of the CTA's M group stay in shared memory
   int a_slabs;       // 16 KB weight slabs per M tile (all segments)
   int stages;        // pipeline depth
+  int bn;            // CTA-pair kernel: frames per tile across the pair (256, or 128 with two operands)
   uint32_t stage_bytes;
   GemmSeg seg[2];
   uint32_t b_lbo, b_sbo, a_sbo;  // smem descriptor strides (bytes)
@@ -89,6 +90,71 @@ __device__ __forceinline__ bool elect_one() {
   uint32_t p;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
   return p != 0;
+}
+
+// 32 accumulators of one output row (32 consecutive frames) -> codes -> one 32-byte (or two 16-byte) store.
+// Shared by the 1-CTA and the CTA-pair kernels.
+template <int EPI, bool F32>
+__device__ __forceinline__ void finish32(const GemmArgs& g, const EpiConsts& kc, const ChanRegs& c0, const ChanRegs& c1,
+                                         bool row_ok, int cc, int b, int tv, int len, bool wide_ok, const int (&a0)[32],
+                                         const int (&a1)[32]) {
+    const size_t row = (size_t)b * g.C_out + cc;
+    if (EPI != 0 || g.ep.mode == QASR_EPI_REQUANT_I8) {
+      uint8_t* optr = reinterpret_cast<uint8_t*>(g.out) + row * g.out_ld + tv;
+      uint32_t pw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if ((EPI == 0 || (EPI & kEpiPrev)) && g.ep.prev != nullptr && row_ok) {
+        const int8_t* pp = g.ep.prev + row * g.ep.prev_ld + tv;
+        if (tv < g.T_out) { const uint4 v = *reinterpret_cast<const uint4*>(pp); pw[0] = v.x; pw[1] = v.y; pw[2] = v.z; pw[3] = v.w; }
+        if (tv + 16 < g.T_out) { const uint4 v = *reinterpret_cast<const uint4*>(pp + 16); pw[4] = v.x; pw[5] = v.y; pw[6] = v.z; pw[7] = v.w; }
+      }
+      uint32_t packed[8];
+#pragma unroll
+      for (int w4 = 0; w4 < 8; ++w4) {
+        int q[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = 4 * w4 + i;
+          if (F32) {
+            q[i] = (int)epilogue_f32_bits(kc, a0[j], c0);
+          } else if (EPI & kEpiFast) {
+            const int prev = (EPI & kEpiPrev) ? (int)(int8_t)(pw[w4] >> (8 * i)) : 0;
+            q[i] = epilogue_fast<(EPI & kEpiDual) != 0, (EPI & kEpiPrev) != 0, (EPI & kEpiStage2) != 0>(
+                g.ep, kc, a0[j], c0, (EPI & kEpiDual) ? a1[j] : 0, c1, prev);
+          } else {
+            const int prev = (int)(int8_t)((pw[w4] >> (8 * i)) & 0xff);
+            q[i] = epilogue_exact(g.ep, kc, a0[j], c0, g.nseg > 1, g.nseg > 1 ? a1[j] : 0, c1, prev);
+          }
+        }
+        packed[w4] = pack4(q[0], q[1], q[2], q[3]);
+      }
+      if (tv + 32 > len) {  // length mask / row tail: zero the bytes at t >= len
+#pragma unroll
+        for (int w4 = 0; w4 < 8; ++w4) {
+          const int nvalid = len - (tv + 4 * w4);
+          packed[w4] &= nvalid >= 4 ? 0xffffffffu : (nvalid <= 0 ? 0u : (0xffffffffu >> (8 * (4 - nvalid))));
+        }
+      }
+      if (row_ok && !(g.dbg_skip & 4)) {
+        if (wide_ok && tv + 16 < g.T_out) {
+          // one 32-byte store = one full L2 sector per lane (the lanes of a warp are 32 different rows)
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(optr), "r"(packed[0]), "r"(packed[1]),
+                       "r"(packed[2]), "r"(packed[3]), "r"(packed[4]), "r"(packed[5]), "r"(packed[6]), "r"(packed[7]) : "memory");
+        } else {
+          if (tv < g.T_out) *reinterpret_cast<uint4*>(optr) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          if (tv + 16 < g.T_out) *reinterpret_cast<uint4*>(optr + 16) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        }
+      }
+    } else if (g.ep.mode == QASR_EPI_DEQUANT_F32) {
+      float* orow = reinterpret_cast<float*>(g.out) + row * g.out_ld;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (row_ok && tv + j < g.T_out) orow[tv + j] = epilogue_dequant(g.ep, a0[j], c0);
+    } else {
+      int32_t* orow = reinterpret_cast<int32_t*>(g.out) + row * g.out_ld;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (row_ok && tv + j < g.T_out) orow[tv + j] = a0[j] + c0.bias;
+    }
 }
 
 template <int EPI>
@@ -287,73 +353,15 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int as = 0;
     uint32_t aphase = 0;
     pdl_wait();   // out / prev / out_lens belong to the stream order
-    const int MT = g.MT, nseg = g.nseg, n_tiles = g.n_tiles, T_out = g.T_out, C_out = g.C_out;
+    const int MT = g.MT, nseg = g.nseg, n_tiles = g.n_tiles, T_out = g.T_out;
     const bool masked = g.ep.flags & QASR_F_MASK;
     const bool wide_ok = (reinterpret_cast<uintptr_t>(g.out) & 31) == 0 && (g.out_ld & 31) == 0;   // 32-byte aligned rows
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cgroup * 32);
 
     // 32 accumulators (one row, 32 consecutive frames) -> codes -> two 16-byte stores
     auto finish_t = [&](auto f32_tag, int ms, int b, int tv, int len, const int (&a0)[32], const int (&a1)[32]) {
-      constexpr bool F32 = decltype(f32_tag)::value;
-      const size_t row = (size_t)b * C_out + cc[ms];
-      if (EPI != 0 || g.ep.mode == QASR_EPI_REQUANT_I8) {
-        uint8_t* optr = reinterpret_cast<uint8_t*>(g.out) + row * g.out_ld + tv;
-        uint32_t pw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if ((EPI == 0 || (EPI & kEpiPrev)) && g.ep.prev != nullptr && row_ok[ms]) {
-          const int8_t* pp = g.ep.prev + row * g.ep.prev_ld + tv;
-          if (tv < T_out) { const uint4 v = *reinterpret_cast<const uint4*>(pp); pw[0] = v.x; pw[1] = v.y; pw[2] = v.z; pw[3] = v.w; }
-          if (tv + 16 < T_out) { const uint4 v = *reinterpret_cast<const uint4*>(pp + 16); pw[4] = v.x; pw[5] = v.y; pw[6] = v.z; pw[7] = v.w; }
-        }
-        uint32_t packed[8];
-#pragma unroll
-        for (int w4 = 0; w4 < 8; ++w4) {
-          int q[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = 4 * w4 + i;
-            if (F32) {
-              q[i] = (int)epilogue_f32_bits(kc, a0[j], c0[ms]);
-            } else if (EPI & kEpiFast) {
-              const int prev = (EPI & kEpiPrev) ? (int)(int8_t)(pw[w4] >> (8 * i)) : 0;
-              q[i] = epilogue_fast<(EPI & kEpiDual) != 0, (EPI & kEpiPrev) != 0, (EPI & kEpiStage2) != 0>(
-                  g.ep, kc, a0[j], c0[ms], (EPI & kEpiDual) ? a1[j] : 0, c1[ms], prev);
-            } else {
-              const int prev = (int)(int8_t)((pw[w4] >> (8 * i)) & 0xff);
-              q[i] = epilogue_exact(g.ep, kc, a0[j], c0[ms], nseg > 1, nseg > 1 ? a1[j] : 0, c1[ms], prev);
-            }
-          }
-          packed[w4] = pack4(q[0], q[1], q[2], q[3]);
-        }
-        if (tv + 32 > len) {  // length mask / row tail: zero the bytes at t >= len
-#pragma unroll
-          for (int w4 = 0; w4 < 8; ++w4) {
-            const int nvalid = len - (tv + 4 * w4);
-            packed[w4] &= nvalid >= 4 ? 0xffffffffu : (nvalid <= 0 ? 0u : (0xffffffffu >> (8 * (4 - nvalid))));
-          }
-        }
-        if (row_ok[ms] && !(g.dbg_skip & 4)) {
-          if (wide_ok && tv + 16 < T_out) {
-            // one 32-byte store = one full L2 sector per lane (the lanes of a warp are 32 different rows)
-            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(optr), "r"(packed[0]), "r"(packed[1]),
-                         "r"(packed[2]), "r"(packed[3]), "r"(packed[4]), "r"(packed[5]), "r"(packed[6]), "r"(packed[7]) : "memory");
-          } else {
-            if (tv < T_out) *reinterpret_cast<uint4*>(optr) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            if (tv + 16 < T_out) *reinterpret_cast<uint4*>(optr + 16) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-          }
-        }
-      } else if (g.ep.mode == QASR_EPI_DEQUANT_F32) {
-        float* orow = reinterpret_cast<float*>(g.out) + row * g.out_ld;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (row_ok[ms] && tv + j < T_out) orow[tv + j] = epilogue_dequant(g.ep, a0[j], c0[ms]);
-      } else {
-        int32_t* orow = reinterpret_cast<int32_t*>(g.out) + row * g.out_ld;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (row_ok[ms] && tv + j < T_out) orow[tv + j] = a0[j] + c0[ms].bias;
-      }
+      finish32<EPI, decltype(f32_tag)::value>(g, kc, c0[ms], c1[ms], row_ok[ms], cc[ms], b, tv, len, wide_ok, a0, a1);
     };
-
     // float or integer epilogue: a per-warp, per-M-tile constant (the warp's 32 rows never change)
     auto finish = [&](int ms, int b, int tv, int len, const int (&a0)[32], const int (&a1)[32]) {
       if (tv >= T_out) return;   // warp-uniform: this column group lies past the end of the utterance
@@ -407,6 +415,289 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   if (warp == kAllocWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair kernel (tcgen05 cta_group::2)
+// ------------------------------------------------------------------------------------------
+// Two CTAs of a cluster (the two SMs of a TPC) run ONE MMA stream of M = 256: each keeps the weights of its own
+// 128-row M tile resident and streams its own HALF of every activation slab (bn / 2 of the tile's bn frames), the
+// leader issues tcgen05.mma.cta_group::2 and both drain their own 128 accumulator rows.  Why: a 128x128x32 SS
+// MMA reads 8 KB of shared memory per 64 clk = the SM's whole 128 B/clk, so in the 1-CTA kernel the TMA writes
+// and the operand reads time-share the port (measured 602-640 clk per 16 KB slab, loads and MMAs adding up
+// instead of overlapping); the pair reads 8 KB per 128 clk per SM and the bare pipeline runs at the tensor
+// pipe's 512 clk per slab with TMA fully hidden (tools/microbench/gemm_pipe_2cta.cu, umma_2cta.cu).
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t leader_addr(uint32_t local) {   // same shared-memory offset in cluster rank 0
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(0u));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// relaxed: the hand-off orders TMEM reads (tcgen05.wait::ld + tcgen05 fence), not global memory; a .release at
+// cluster scope would first drain the previous round's output stores (~1 us per round per warp, measured)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on the same barrier offset in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                    const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                    const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_region = smem_base;                                  // this CTA's M tile: a_slabs x 16 KB, resident
+  const uint32_t a_region_bytes = (uint32_t)g.a_slabs * kABytes;
+  const uint32_t stage_base = smem_base + a_region_bytes;               // stages x 16 KB: this CTA's half of a slab
+  const uint32_t bars = stage_base + (uint32_t)g.stages * kBBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };                 // leader's copy collects both CTAs' loads
+  auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * kMaxStages + 2 + s); };   // leader's copy, both CTAs arrive
+  const uint32_t afull_bar = bars + 8u * (2 * kMaxStages + 4);
+  const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 5);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const int pair = blockIdx.x >> 1;
+  const int mpair = pair % g.m_groups;          // which pair of M tiles: fixed for the pair's life
+  const int n_first = pair / g.m_groups;
+  const int mt = mpair * 2 + (int)rank;         // this CTA's M tile
+  const int bn = g.bn;
+
+  if (warp == kProducerWarp && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB0) : "memory");
+    if (g.nseg > 1) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
+    }
+  }
+  if (warp == kMmaWarp && lane == 0) {
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
+    mbar_init(afull_bar, 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kAllocWarp) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  pdl_trigger();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers are initialised before anyone signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int n_total = g.n_total, n_step = g.n_step, n_tiles = g.n_tiles, nseg = g.nseg, stages = g.stages, T_out = g.T_out;
+  const int step_nt = n_step % n_tiles, step_b = n_step / n_tiles;
+
+  if (warp == kProducerWarp) {
+    // ===================== TMA producer (both CTAs: own weights once, own half of every activation slab) =====================
+    const bool leader = elect_one();
+    if (leader) {
+      const uint32_t lafull = leader_addr(afull_bar);
+      mbar_expect_tx_cluster(lafull, a_region_bytes);
+      for (int sg = 0; sg < nseg; ++sg) {
+        const GemmSeg& s = g.seg[sg];
+        const CUtensorMap* mA = sg == 0 ? &tmA0 : &tmA1;
+        for (int tap = 0; tap < s.taps; ++tap)
+          for (int cb = 0; cb < s.cblocks; ++cb)
+            tma_load_2d_pair(a_region + (uint32_t)(s.slab0 + tap * s.cblocks + cb) * kABytes, mA, cb * BK,
+                             tap * s.c_out_pad + mt * BM, lafull);
+      }
+    }
+    __syncwarp();
+    pdl_wait();   // weights above are constants of the plan; activations below come from the previous kernel
+    int stage = 0;
+    uint32_t phase = 0;
+    int nt = n_first % n_tiles, b = n_first / n_tiles;
+    const int seg_taps[2] = {g.seg[0].taps, g.seg[1].taps}, seg_cblocks[2] = {g.seg[0].cblocks, g.seg[1].cblocks};
+    const int seg_dil[2] = {g.seg[0].dil, g.seg[1].dil}, seg_pad[2] = {g.seg[0].pad, g.seg[1].pad};
+    for (int nidx = n_first; nidx < n_total; nidx += n_step, nt += step_nt, b += step_b) {
+      if (nt >= n_tiles) { nt -= n_tiles; ++b; }
+      // frames of this tile, rounded up to 32: the pair splits them in halves of a multiple of 16 (TMA alignment)
+      const int cols = min(bn, ((T_out - nt * bn + 31) >> 5) << 5);
+      const int t_half = nt * bn + (int)rank * (cols >> 1);
+#pragma unroll
+      for (int sg = 0; sg < 2; ++sg) {
+        if (sg >= nseg) break;
+        const CUtensorMap* mB = sg == 0 ? &tmB0 : &tmB1;
+        const int taps = seg_taps[sg], cblocks = seg_cblocks[sg];
+        for (int tap = 0; tap < taps; ++tap) {
+          const int tcoord = t_half + tap * seg_dil[sg] - seg_pad[sg];
+          for (int cb = 0; cb < cblocks; ++cb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            if (leader) {
+              const uint32_t lfull = leader_addr(full_bar(stage));
+              mbar_expect_tx_cluster(lfull, kBBytes);
+              tma_load_3d_pair(stage_base + (uint32_t)stage * kBBytes, mB, tcoord, cb * BK, b, lfull);
+            }
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp && rank == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    const bool leader = elect_one();
+    const int skip_mma = g.dbg_skip & 2;
+    const uint64_t a_hi = make_smem_desc(0, 0, g.a_sbo), b_hi = make_smem_desc(0, g.b_lbo, g.b_sbo);
+    const uint32_t a_region_lo = (a_region & 0x3FFFFu) >> 4, stage_lo0 = (stage_base & 0x3FFFFu) >> 4;
+    constexpr uint32_t kSlabLo = kABytes >> 4, kStageLo = kBBytes >> 4, kKStepA = 32u >> 4, kKStepB = (32u * BN) >> 4;
+    const uint32_t acc_per_stage = (uint32_t)(nseg * bn);
+    int stage = 0;
+    uint32_t phase = 0, stage_lo = stage_lo0;
+    int as = 0;
+    uint32_t aphase = 0;
+    mbar_wait(afull_bar, 0u);   // both CTAs' weights have landed
+    tc_fence_after();
+    int nt = n_first % n_tiles;
+    const int seg_slabs[2] = {g.seg[0].taps * g.seg[0].cblocks, g.seg[1].taps * g.seg[1].cblocks};
+    // instruction descriptor: the operand's own formats, N = this tile's frames, M = 256 across the pair
+    const uint32_t fmt_mask = ~((0x3Fu << 17) | (0x1Fu << 24));
+    const uint32_t seg_idesc[2] = {(g.seg[0].idesc & fmt_mask) | ((uint32_t)(256 >> 4) << 24),
+                                   (g.seg[1].idesc & fmt_mask) | ((uint32_t)(256 >> 4) << 24)};
+    const uint32_t seg_a_lo[2] = {a_region_lo + (uint32_t)g.seg[0].slab0 * kSlabLo, a_region_lo + (uint32_t)g.seg[1].slab0 * kSlabLo};
+    for (int nidx = n_first; nidx < n_total; nidx += n_step, nt += step_nt) {
+      if (nt >= n_tiles) nt -= n_tiles;
+      const int cols = min(bn, ((T_out - nt * bn + 31) >> 5) << 5);
+      mbar_wait(tempty_bar(as), aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_round = tmem_base + (uint32_t)as * acc_per_stage;
+#pragma unroll
+      for (int sg = 0; sg < 2; ++sg) {
+        if (sg >= nseg) break;
+        const int slabs = seg_slabs[sg];
+        const uint32_t idesc = seg_idesc[sg] | ((uint32_t)(cols >> 3) << 17);
+        const uint32_t d_tmem = d_round + (uint32_t)(sg * bn);
+        uint32_t a_lo = seg_a_lo[sg];
+        for (int it = 0; it < slabs; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int kk = 0; kk < BK / 32; ++kk) {
+              if (!skip_mma)
+                tc_mma_i8_pair(d_tmem, a_hi | (uint64_t)(a_lo + kk * kKStepA), b_hi | (uint64_t)(stage_lo + kk * kKStepB), idesc,
+                               (it | kk) != 0 ? 1u : 0u);
+            }
+            tc_commit_pair(empty_bar(stage));   // frees the slot in both CTAs once these MMAs have read it
+          }
+          a_lo += kSlabLo;
+          stage_lo += kStageLo;
+          if (++stage == stages) { stage = 0; phase ^= 1u; stage_lo = stage_lo0; }
+        }
+      }
+      if (leader) tc_commit_pair(tfull_bar(as));   // both CTAs' accumulator halves are complete
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  } else if (warp < kEpiWarps) {
+    // ===================== epilogue (each CTA drains its own 128 rows x bn columns) =====================
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int cgroup = warp >> 2;             // which quarter of the tile's columns
+    const EpiConsts kc = make_epi_consts(g.ep, nseg > 1);
+    const int c = mt * BM + quarter * 32 + lane;
+    const bool row_ok = c < g.C_out;
+    const int cc = row_ok ? c : 0;
+    const ChanRegs c0 = load_chan0(g.ep, cc);
+    const ChanRegs c1 = nseg > 1 ? load_chan(g.ep.ch1, cc) : c0;
+    const bool warp_f32 = __all_sync(0xffffffffu, c0.r != 0.0f) != 0;
+    const uint32_t acc_per_stage = (uint32_t)(nseg * bn);
+    const uint32_t ltempty[2] = {leader_addr(tempty_bar(0)), leader_addr(tempty_bar(1))};
+    int as = 0;
+    uint32_t aphase = 0;
+    pdl_wait();   // out / prev / out_lens belong to the stream order
+    const bool masked = g.ep.flags & QASR_F_MASK;
+    const bool wide_ok = (reinterpret_cast<uintptr_t>(g.out) & 31) == 0 && (g.out_ld & 31) == 0;
+    const int chunks = bn >> 7;               // 32-column chunks per warp: 2 for bn = 256, 1 for bn = 128
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cgroup * chunks * 32);
+    auto finish = [&](int b, int tv, int len, const int (&a0)[32], const int (&a1)[32]) {
+      if (tv >= T_out) return;   // warp-uniform: past the end of the utterance
+      if ((EPI & kEpiF32) || (EPI == kEpiFast && warp_f32)) finish32<EPI, true>(g, kc, c0, c1, row_ok, cc, b, tv, len, wide_ok, a0, a1);
+      else finish32<EPI, false>(g, kc, c0, c1, row_ok, cc, b, tv, len, wide_ok, a0, a1);
+    };
+    int nt = n_first % n_tiles, b = n_first / n_tiles;
+    for (int nidx = n_first; nidx < n_total; nidx += n_step, nt += step_nt, b += step_b) {
+      if (nt >= n_tiles) { nt -= n_tiles; ++b; }
+      const int len = masked ? min(g.ep.out_lens[b], T_out) : T_out;
+      const int tv = nt * bn + cgroup * chunks * 32;   // first frame of this warp's columns
+      const uint32_t taddr = lane_base + (uint32_t)as * acc_per_stage;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      if (g.dbg_skip & 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(ltempty[as]);
+      } else if (nseg == 1 && chunks == 2) {
+        int a0[32], a1[32];
+        tmem_ld32(taddr, a0);
+        tmem_ld32(taddr + 32, a1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(ltempty[as]);   // the buffer goes back to the leader before the math
+        finish(b, tv, len, a0, a0);
+        finish(b, tv + 32, len, a1, a1);
+      } else {
+        for (int h = 0; h < chunks; ++h) {
+          int a0[32], a1[32];
+          tmem_ld32(taddr + (uint32_t)(h * 32), a0);
+          if (nseg > 1) tmem_ld32(taddr + (uint32_t)(bn + h * 32), a1);
+          tmem_ld_wait();
+          if (h == chunks - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(ltempty[as]);
+          }
+          finish(b, tv + h * 32, len, a0, nseg > 1 ? a1 : a0);
+        }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's shared memory and TMEM stay alive until the leader's last MMA has retired
+  if (warp == kAllocWarp) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -577,6 +868,63 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   if (fast)
     variant = kEpiFast | (op1 ? kEpiDual : 0) | (epi->prev ? kEpiPrev : 0) | ((epi->flags & QASR_F_STAGE2) ? kEpiStage2 : 0);
   if (fast && (epi->flags & QASR_F_FAST_F32)) variant = kEpiFast | kEpiF32;
+  // CTA-pair kernel (tcgen05 cta_group::2): an even number of M tiles keep their weights resident one tile per CTA;
+  // halves the shared-memory operand reads per MMA so TMA writes and MMA reads stop time-sharing the port.
+  // Bit-exact on every GEMM test and its loads + MMAs run faster than the 1-CTA kernel's (11.5 us against 13.3 us,
+  // 512x512 at batch 64 x 800 frames), but both kernels are bound by the 16 epilogue warps' issue slots (1.4 us of
+  // integer / 1.05 us of float requantisation per 256x128 outputs against 1.04 us of MMAs) and the pair pays ~0.3 us
+  // more hand-off per round, so whole steps measured 2.72 ms against 2.65 ms: opt-in (bring-up knob 12 = 1) until the
+  // epilogue is cheaper.
+  bool pair = qasr_debug_get(12) == 1 && g.m_tiles % 2 == 0 && a_bytes(1) + 4 * kBBytes <= budget && qasr_sm_count() >= 2;
+  for (int i = 0; i < g.nseg; ++i) pair = pair && g.seg[i].stride == 1;
+  if (pair) {
+    g.MT = 1;
+    g.a_resident = 1;
+    g.bn = g.nseg == 1 ? 256 : 128;   // two buffers of (operands x bn) accumulator columns fill the 512 TMEM columns
+    g.m_groups = g.m_tiles / 2;
+    g.n_tiles = (T_out + g.bn - 1) / g.bn;
+    g.n_total = g.n_tiles * B;
+    g.stage_bytes = kBBytes;
+    g.stages = (int)((budget - a_bytes(1)) / kBBytes);
+    if (g.stages > kMaxStages) g.stages = kMaxStages;
+    const uint32_t pair_smem = a_bytes(1) + (uint32_t)g.stages * kBBytes + kSmemSlack;
+    int pairs_per_group = (qasr_sm_count() / 2) / g.m_groups;
+    if (pairs_per_group < 1) pairs_per_group = 1;
+    if (pairs_per_group > g.n_total) pairs_per_group = g.n_total;
+    g.n_step = pairs_per_group;
+    const int pair_grid = 2 * pairs_per_group * g.m_groups;
+    cudaStream_t pst = (cudaStream_t)stream;
+    static bool pair_attr_set[32][64] = {};
+    int pdev = 0;
+    QASR_CHECK_CUDA(cudaGetDevice(&pdev));
+    const bool pneed = pdev >= 0 && pdev < 64 && !pair_attr_set[variant][pdev];
+#define QASR_PAIR_CASE(V_)                                                                                          \
+  case V_:                                                                                                          \
+    if (pneed)                                                                                                      \
+      QASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_pair_kernel<V_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                           (int)kSmemBudget));                                                      \
+    QASR_CHECK_CUDA(qasr_launch_pdl_pair(gemm_i8_pair_kernel<V_>, dim3(pair_grid), dim3(kGemmThreads), pair_smem, pst, \
+                                         maps[0], maps[1], maps[2], maps[3], g));                                   \
+    break;
+    switch (variant) {
+      QASR_PAIR_CASE(0)
+      QASR_PAIR_CASE(1)
+      QASR_PAIR_CASE(3)
+      QASR_PAIR_CASE(5)
+      QASR_PAIR_CASE(7)
+      QASR_PAIR_CASE(9)
+      QASR_PAIR_CASE(11)
+      QASR_PAIR_CASE(13)
+      QASR_PAIR_CASE(15)
+      QASR_PAIR_CASE(17)
+      default:
+        qasr_set_error("conv1d_gemm: internal: no pair kernel variant %d", variant);
+        return QASR_ERR_INVALID;
+    }
+#undef QASR_PAIR_CASE
+    if (pneed) pair_attr_set[variant][pdev] = true;
+    return qasr_check_launch("gemm_i8_pair_kernel");
+  }
   int per_group = qasr_sm_count() / g.m_groups;
   if (per_group < 1) per_group = 1;
   if (per_group > g.n_total) per_group = g.n_total;

@@ -104,6 +104,26 @@ static inline cudaError_t qasr_launch_pdl(Kern kern, dim3 grid, dim3 block, size
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
+// same, as clusters of two CTAs (the two SMs of a TPC: tcgen05 cta_group::2 kernels)
+template <typename Kern, typename... Args>
+static inline cudaError_t qasr_launch_pdl_pair(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = qasr_debug_get(9) == 0 ? 0 : 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 
 // m * 2^-e as a double: exact (m has 31 bits), so z * mult rounds exactly like the
 // reference's f64(z) * f64(m) followed by the exact division by 2^e (quant_utils.py:195-196).

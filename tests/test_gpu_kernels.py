@@ -153,9 +153,18 @@ def test_gemm_raw_i32(case):
     assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
 
 
+@pytest.fixture(params=[0, 1], ids=["cta1", "cta_pair"])
+def gemm_engine(request):
+    """Both GEMM schedules on every requantising case: one CTA per SM, and CTA pairs issuing tcgen05 cta_group::2
+    (bring-up knob 12; shapes with an odd number of 128-row tiles fall back to one CTA either way)."""
+    L.lib().qasr_debug_set(12, request.param)
+    yield request.param
+    L.lib().qasr_debug_set(12, -1)
+
+
 @pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
 @pytest.mark.parametrize("case", GEMM_CASES[:5], ids=lambda c: c[0])
-def test_gemm_requant(case, fast):
+def test_gemm_requant(case, fast, gemm_engine):
     name, B, ci, co, T, k, dil, signed = case
     q, w, bias, pad = _gemm_inputs(case, seed=1)
     acc = O.conv1d_int(q, w, bias, 1, pad, dil, 1)
@@ -185,7 +194,7 @@ def test_gemm_requant(case, fast):
 
 
 @pytest.mark.parametrize("case", GEMM_CASES[:5], ids=lambda c: c[0])
-def test_gemm_requant_f32(case):
+def test_gemm_requant_f32(case, gemm_engine):
     """Float fast path (QASR_F_FAST_F32): single operand, ReLU folded into the clamp, host-proved dyadics."""
     name, B, ci, co, T, k, dil, signed = case
     q, w, bias, pad = _gemm_inputs(case, seed=1)
@@ -263,7 +272,7 @@ def test_f32_mult_table_mixed(dw_engine):
 
 
 @pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
-def test_gemm_dual_residual(fast):
+def test_gemm_dual_residual(fast, gemm_engine):
     """pointwise conv + residual 1x1 conv meeting in the res_act epilogue (jasper.py:681)."""
     B, ci0, ci1, co, T = 2, 256, 128, 256, 200
     r = rng(3)
