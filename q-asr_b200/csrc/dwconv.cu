@@ -160,10 +160,9 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
     // the tile loop exists twice, float and integer epilogue, chosen once per row (warp-uniform)
     auto tiles = [&](auto f32_tag) {
     constexpr bool F32 = decltype(f32_tag)::value;
-    // float path: the bias rides in as the MMA's initial accumulator (exact integer add, no instruction)
-    const int acc_init = F32 ? c0.bias : 0;
-    ChanRegs cz = c0;
-    if (F32) cz.bias = 0;
+    // float path: the MMA's initial accumulator is 0x4B400000 + bias, so the finished accumulator's BITS are the
+    // float 1.5 * 2^23 + (acc + bias): the bias add and the int -> float conversion cost no instruction
+    const int acc_init = F32 ? kF32MagicBits + c0.bias : 0;
     // stores of whole tiles below `full_end` need neither the length mask nor the row-end test (warp-uniform split)
     const int full_end = min(len, out_words * 4);
     uint32_t* const orow_w = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(a.out) + row * a.out_ld) + lane;
@@ -174,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
       for (int ks = 0; ks < KS; ++ks) imma_16832<XS>(acc, af[ks], tw[8 * ks], tw[8 * ks + 4]);
       if (EK != 2) {
         auto code = [&](int acc_v) -> uint8_t {
-          if (F32) return (uint8_t)epilogue_f32_bits(kc, acc_v, cz);
+          if (F32) return (uint8_t)epilogue_f32_bits_biased(kc, acc_v, c0);
           return (uint8_t)(EK == 0 ? epilogue_fast<false, false, false>(a.ep, kc, acc_v, c0, 0, c0, 0)
                                    : epilogue_exact(a.ep, kc, acc_v, c0, false, 0, c0, 0));
         };

@@ -250,6 +250,16 @@ __device__ __forceinline__ uint32_t epilogue_f32_bits(const EpiConsts& k, int ac
   return __float_as_uint(fminf(fmaxf(y, k.flo), k.fhi));
 }
 
+// Same, for an accumulator that was STARTED at 0x4B400000 + bias (the bit pattern of 1.5 * 2^23 + bias): its bits
+// are then the float 1.5 * 2^23 + (acc + bias) exactly (|acc + bias| < 2^22), and one FADD replaces the half-rate
+// I2F.  Used where the MMA's initial accumulator is free to choose (the IMMA depthwise kernel).
+constexpr int kF32MagicBits = 0x4B400000;
+__device__ __forceinline__ uint32_t epilogue_f32_bits_biased(const EpiConsts& k, int acc_bits, const ChanRegs& c) {
+  const float f = __int_as_float(acc_bits) - kF32Magic;
+  const float y = fmaf(f, c.r, kF32Magic);
+  return __float_as_uint(fminf(fmaxf(y, k.flo), k.fhi));
+}
+
 // Literal float recipe (runtime flags; any accumulator size, exact ties, 64-bit bias).
 __device__ __forceinline__ int epilogue_exact(const EpiArgs& ep, const EpiConsts& k, int acc0, const ChanRegs& c0,
                                               bool has1, int acc1, const ChanRegs& c1, int prev) {
