@@ -484,10 +484,10 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const uint32_t bars = stage_base + (uint32_t)g.stages * kBBytes;
   auto full_bar = [&](int s) { return bars + 8u * s; };                 // leader's copy collects both CTAs' loads
   auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
-  auto tfull_bar = [&](int s) { return bars + 8u * (2 * kMaxStages + s); };
-  auto tempty_bar = [&](int s) { return bars + 8u * (2 * kMaxStages + 2 + s); };   // leader's copy, both CTAs arrive
-  const uint32_t afull_bar = bars + 8u * (2 * kMaxStages + 4);
-  const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 5);
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * kMaxStages + s); };       // up to 4 accumulator buffers
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * kMaxStages + 4 + s); };   // leader's copy, both CTAs arrive
+  const uint32_t afull_bar = bars + 8u * (2 * kMaxStages + 8);
+  const uint32_t tmem_slot = bars + 8u * (2 * kMaxStages + 9);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -510,7 +510,7 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   }
   if (warp == kMmaWarp && lane == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
+    for (int s = 0; s < 4; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
     mbar_init(afull_bar, 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -527,6 +527,7 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
   const int n_total = g.n_total, n_step = g.n_step, n_tiles = g.n_tiles, nseg = g.nseg, stages = g.stages, T_out = g.T_out;
   const int step_nt = n_step % n_tiles, step_b = n_step / n_tiles;
+  const int nbuf = min(4, (int)kTmemCols / (nseg * bn));   // accumulator buffers that fit the 512 TMEM columns
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer (both CTAs: own weights once, own half of every activation slab) =====================
@@ -626,7 +627,7 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
       }
       if (leader) tc_commit_pair(tfull_bar(as));   // both CTAs' accumulator halves are complete
-      if (++as == 2) { as = 0; aphase ^= 1u; }
+      if (++as == nbuf) { as = 0; aphase ^= 1u; }
     }
   } else if (warp < kEpiWarps) {
     // ===================== epilogue (each CTA drains its own 128 rows x bn columns) =====================
@@ -640,7 +641,7 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const ChanRegs c1 = nseg > 1 ? load_chan(g.ep.ch1, cc) : c0;
     const bool warp_f32 = __all_sync(0xffffffffu, c0.r != 0.0f) != 0;
     const uint32_t acc_per_stage = (uint32_t)(nseg * bn);
-    const uint32_t ltempty[2] = {leader_addr(tempty_bar(0)), leader_addr(tempty_bar(1))};
+    const uint32_t ltempty0 = leader_addr(tempty_bar(0));   // the barriers are 8 bytes apart in the leader too
     int as = 0;
     uint32_t aphase = 0;
     pdl_wait();   // out / prev / out_lens belong to the stream order
@@ -664,7 +665,7 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       if (g.dbg_skip & 1) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(ltempty[as]);
+        if (lane == 0) mbar_arrive_cluster(ltempty0 + 8u * as);
       } else if (nseg == 1 && chunks == 2) {
         int a0[32], a1[32];
         tmem_ld32(taddr, a0);
@@ -672,7 +673,7 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(ltempty[as]);   // the buffer goes back to the leader before the math
+        if (lane == 0) mbar_arrive_cluster(ltempty0 + 8u * as);   // the buffer goes back to the leader before the math
         finish(b, tv, len, a0, a0);
         finish(b, tv + 32, len, a1, a1);
       } else {
@@ -684,12 +685,12 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           if (h == chunks - 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(ltempty[as]);
+            if (lane == 0) mbar_arrive_cluster(ltempty0 + 8u * as);
           }
           finish(b, tv + h * 32, len, a0, nseg > 1 ? a1 : a0);
         }
       }
-      if (++as == 2) { as = 0; aphase ^= 1u; }
+      if (++as == nbuf) { as = 0; aphase ^= 1u; }
     }
   }
 
@@ -870,17 +871,21 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   if (fast && (epi->flags & QASR_F_FAST_F32)) variant = kEpiFast | kEpiF32;
   // CTA-pair kernel (tcgen05 cta_group::2): an even number of M tiles keep their weights resident one tile per CTA;
   // halves the shared-memory operand reads per MMA so TMA writes and MMA reads stop time-sharing the port.
-  // Bit-exact on every GEMM test and its loads + MMAs run faster than the 1-CTA kernel's (11.5 us against 13.3 us,
-  // 512x512 at batch 64 x 800 frames), but both kernels are bound by the 16 epilogue warps' issue slots (1.4 us of
-  // integer / 1.05 us of float requantisation per 256x128 outputs against 1.04 us of MMAs) and the pair pays ~0.3 us
-  // more hand-off per round, so whole steps measured 2.72 ms against 2.65 ms: opt-in (bring-up knob 12 = 1) until the
-  // epilogue is cheaper.
-  bool pair = qasr_debug_get(12) == 1 && g.m_tiles % 2 == 0 && a_bytes(1) + 4 * kBBytes <= budget && qasr_sm_count() >= 2;
+  // Bit-exact on every GEMM test.  Its loads + MMAs run faster than the 1-CTA kernel's (11.4 us against 13.2 us,
+  // 512x512 at batch 64 x 800 frames), but both kernels end up bound by the 16 epilogue warps' issue slots and the
+  // pair pays ~0.3 us more hand-off per round, so it is chosen where it measured faster (tools/gemm_bench.py, float
+  // epilogue): single-operand layers with K >= 512 and 4 M tiles (15.6 us against 16.9 us), or K >= 1024 (41.6 us
+  // against 56.8 us, where one CTA cannot keep two M tiles resident); 256-channel and two-operand layers stay on the
+  // 1-CTA kernel (8.5 / 12.6 / 36.1 us against 9.7 / 14.1 / 35.6 us).  Bring-up knob 12 forces either (0 / 1).
+  const bool pair_auto = g.nseg == 1 && g.m_tiles >= 4 && (g.a_slabs >= 8 || (g.a_slabs >= 4 && g.m_tiles == 4));
+  bool pair = (qasr_debug_get(12) == 1 || (qasr_debug_get(12) != 0 && pair_auto)) && g.m_tiles % 2 == 0 &&
+              a_bytes(1) + 4 * kBBytes <= budget && qasr_sm_count() >= 2;
   for (int i = 0; i < g.nseg; ++i) pair = pair && g.seg[i].stride == 1;
   if (pair) {
     g.MT = 1;
     g.a_resident = 1;
     g.bn = g.nseg == 1 ? 256 : 128;   // two buffers of (operands x bn) accumulator columns fill the 512 TMEM columns
+    if (qasr_debug_get(13) == 128) g.bn = 128;   // bring-up: narrower tiles, 4 accumulator buffers
     g.m_groups = g.m_tiles / 2;
     g.n_tiles = (T_out + g.bn - 1) / g.bn;
     g.n_total = g.n_tiles * B;
