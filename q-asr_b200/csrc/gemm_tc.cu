@@ -885,7 +885,7 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
     g.MT = 1;
     g.a_resident = 1;
     g.bn = g.nseg == 1 ? 256 : 128;   // two buffers of (operands x bn) accumulator columns fill the 512 TMEM columns
-    if (qasr_debug_get(13) == 128) g.bn = 128;   // bring-up: narrower tiles, 4 accumulator buffers
+    if (qasr_debug_get(13) == 128 || qasr_debug_get(13) == 256) g.bn = (int)qasr_debug_get(13);   // bring-up: 4 buffers / 1 buffer
     g.m_groups = g.m_tiles / 2;
     g.n_tiles = (T_out + g.bn - 1) / g.bn;
     g.n_total = g.n_tiles * B;
