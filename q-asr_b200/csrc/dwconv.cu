@@ -116,14 +116,8 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
   __syncwarp();
   const uint8_t* xbase = a.x + ((size_t)b_begin * a.C + c) * a.x_ld;
   const size_t xstep = (size_t)a.C * a.x_ld;  // next utterance, same channel
-  pdl_wait();   // activations (and the output buffer) belong to the stream order; everything above is set-up
-  if (lane == 0) {
-    for (int r = 0; r < min(nrows, kBufs - 1); ++r)
-      row_copy_async(smem_addr(bufs + r * a.buf_bytes + a.halo), xbase + r * xstep, a.copy_bytes,
-                     smem_addr(bars + r));
-  }
-
-  // ---- banded A fragments of this channel: pre-packed per lane by qasr_pack_dw_weights
+  // ---- banded A fragments of this channel: pre-packed per lane by qasr_pack_dw_weights (constants of the plan:
+  //      loaded before the dependency wait so they overlap the previous kernel's tail)
   uint32_t af[KS][4];
   {
     const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.w) + (size_t)c * KS * 128 + lane;
@@ -136,6 +130,13 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
   const ChanRegs c0 = load_chan0(a.ep, c);
   const bool f32_path = c0.r != 0.0f;   // warp-uniform: one channel per work item
   const EpiConsts kc = make_epi_consts(a.ep, false);
+  pdl_wait();   // activations (and the output buffer) belong to the stream order; everything above is set-up
+  if (lane == 0) {
+    for (int r = 0; r < min(nrows, kBufs - 1); ++r)
+      row_copy_async(smem_addr(bufs + r * a.buf_bytes + a.halo), xbase + r * xstep, a.copy_bytes,
+                     smem_addr(bars + r));
+  }
+
   // offsets of this lane's 4 accumulators inside the 128-frame tile: D[row][col] -> 16 col + row
   const int o0 = 32 * tg + g, o1 = o0 + 16, o2 = o0 + 8, o3 = o0 + 24;
   uint8_t* sb = reinterpret_cast<uint8_t*>(stage[warp]);
