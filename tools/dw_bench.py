@@ -39,7 +39,7 @@ def run(C, k, dil, knobs, iters=20):
 for (C, k, dil) in ((512, 33, 1), (512, 75, 1), (256, 33, 1), (512, 87, 2)):
     print("C=%d k=%d dil=%d: imma %6.1f us   tcgen05 %6.1f us" % (C, k, dil, run(C, k, dil, {8: 0}), run(C, k, dil, {8: 1})), flush=True)
 if len(sys.argv) > 1 and sys.argv[1] == "occupancy":
-    for per_sm in (16, 24, 32, 48, 64, 96, 128, 256):
+    for per_sm in (28, 32, 36, 40, 44, 48, 56, 64, 80):
         print("warps/SM wanted %3d: C=512 k=33 %6.1f us   C=512 k=75 %6.1f us   C=256 k=33 %6.1f us" % (
             per_sm, run(512, 33, 1, {8: 0, 10: per_sm}), run(512, 75, 1, {8: 0, 10: per_sm}), run(256, 33, 1, {8: 0, 10: per_sm})), flush=True)
 if len(sys.argv) > 1 and sys.argv[1] == "knobs":
