@@ -83,6 +83,12 @@ __device__ __forceinline__ ChanRegs load_chan_smem(const uint4* fast, const uint
 // EPI as in gemm_tc.cu: bit0 fast, bit1 dual, bit2 prev, bit3 stage2; 0 = literal path
 constexpr int kEpiFast = 1, kEpiDual = 2, kEpiPrev = 4, kEpiStage2 = 8;
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
+  return p != 0;
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmW0,
@@ -99,7 +105,8 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
   uint4* tab = reinterpret_cast<uint4*>(gen_base + kStages * kStageBytes + 256);  // [op][fast|exact][BN]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform role index
+  const int lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW0) : "memory");
@@ -123,63 +130,73 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-        const int ct = tile % g.c_tiles;
-        const int rest = tile / g.c_tiles;
-        const int tt = rest % g.t_tiles, b = rest / g.t_tiles;
-        for (int sg = 0; sg < g.nseg; ++sg) {
-          const Seg& s = g.seg[sg];
-          const CUtensorMap* mX = sg == 0 ? &tmX0 : &tmX1;
-          const CUtensorMap* mW = sg == 0 ? &tmW0 : &tmW1;
-          for (int tap = 0; tap < s.taps; ++tap) {
-            const int tcoord = tt * BM * s.stride + tap * s.dil - s.pad;
-            for (int cb = 0; cb < s.cblocks; ++cb) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
+    // ===================== TMA producer (whole warp walks with uniform values, one elected lane issues) =====================
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      const int ct = tile % g.c_tiles;
+      const int rest = tile / g.c_tiles;
+      const int tt = rest % g.t_tiles, b = rest / g.t_tiles;
+      for (int sg = 0; sg < g.nseg; ++sg) {
+        const Seg& s = g.seg[sg];
+        const CUtensorMap* mX = sg == 0 ? &tmX0 : &tmX1;
+        const CUtensorMap* mW = sg == 0 ? &tmW0 : &tmW1;
+        const int taps = s.taps, cblocks = s.cblocks, wrow0 = ct * BN, c_out_pad = s.c_out_pad;
+        const int t0 = tt * BM * s.stride - s.pad, dil = s.dil;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int tcoord = t0 + tap * dil;
+          for (int cb = 0; cb < cblocks; ++cb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            if (leader) {
               const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
               mbar_expect_tx(full_bar(stage), kStageBytes);
               tma_load_3d(sa, mX, cb * BK, tcoord, b, full_bar(stage));
-              tma_load_2d(sb, mW, cb * BK, tap * s.c_out_pad + ct * BN, full_bar(stage));
-              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              tma_load_2d(sb, mW, cb * BK, tap * c_out_pad + wrow0, full_bar(stage));
             }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(as), aphase ^ 1u);
-        tc_fence_after();
-        for (int sg = 0; sg < g.nseg; ++sg) {
-          const Seg& s = g.seg[sg];
-          const uint32_t d_tmem = tmem_base + (uint32_t)(as * 2 * BN + sg * BN);
-          const int slabs = s.taps * s.cblocks;
-          for (int it = 0; it < slabs; ++it) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+    // ===================== MMA issuer (whole warp walks; descriptors stay in uniform registers: see gemm_tc.cu) =====================
+    const bool leader = elect_one();
+    const uint64_t desc_hi = make_smem_desc(0, 0, 1024);
+    const uint32_t stage_lo0 = (smem_base & 0x3FFFFu) >> 4;
+    constexpr uint32_t kStageLo = kStageBytes >> 4, kBLo = kABytes >> 4;
+    const int seg_slabs[2] = {g.seg[0].taps * g.seg[0].cblocks, g.seg[1].taps * g.seg[1].cblocks};
+    const uint32_t seg_idesc[2] = {g.seg[0].idesc, g.seg[1].idesc};
+    const int nseg = g.nseg;
+    int stage = 0;
+    uint32_t phase = 0, stage_lo = stage_lo0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(as), aphase ^ 1u);
+      tc_fence_after();
 #pragma unroll
-            for (int kk = 0; kk < BK / 32; ++kk) {
-              const uint64_t adesc = make_smem_desc(sa + kk * 32, 0, 1024);
-              const uint64_t bdesc = make_smem_desc(sb + kk * 32, 0, 1024);
-              tc_mma_i8(d_tmem, adesc, bdesc, s.idesc, (it | kk) != 0 ? 1u : 0u);
-            }
+      for (int sg = 0; sg < 2; ++sg) {
+        if (sg >= nseg) break;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 2 * BN + sg * BN);
+        const int slabs = seg_slabs[sg];
+        const uint32_t idesc = seg_idesc[sg];
+        for (int it = 0; it < slabs; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int kk = 0; kk < BK / 32; ++kk)
+              tc_mma_i8(d_tmem, desc_hi | (uint64_t)(stage_lo + kk * 2), desc_hi | (uint64_t)(stage_lo + kBLo + kk * 2), idesc,
+                        (it | kk) != 0 ? 1u : 0u);
             tc_commit(empty_bar(stage));
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
+          stage_lo += kStageLo;
+          if (++stage == kStages) { stage = 0; phase ^= 1u; stage_lo = stage_lo0; }
         }
-        tc_commit(tfull_bar(as));
-        if (++as == 2) { as = 0; aphase ^= 1u; }
       }
+      if (leader) tc_commit(tfull_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
