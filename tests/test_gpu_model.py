@@ -385,3 +385,47 @@ def test_transcribe_stream_matches_forward():
     assert len(got) == len(want)
     for g, w in zip(got, want):
         assert g.dtype == torch.long and torch.equal(g, w)
+
+
+@pytest.mark.gpu
+def test_full_size_properties_bench_workload():
+    """BASELINE.json configs[1] at its full size (QuartzNet15x5 W6A6 percentile 99.996, batch 64 x 1600 frames), where
+    the CPU oracle would take minutes: size-independent properties that tie the full-size run to the small-size
+    runs the oracle checks bit-exactly (same calibrated model, same kernels):
+      * batch independence: every utterance's logits in the batch-64 run are bit-identical to its logits in a
+        batch-4 run of the same utterances (static evaluation has no cross-utterance term);
+      * padding invariance: frames at t >= length do not influence the logits inside the length (MaskedConv1d);
+      * determinism: two runs give identical bytes;
+      * the serving loop returns forward()'s labels."""
+    import bench
+    from qasr.params import synthetic_features
+    wl = dict(bench.WORKLOAD)
+    model = bench.build_model(torch.device(DEV), wl)
+    B, T = wl["batch"], wl["frames"]
+    x, lens = synthetic_features(B, T, seed=77, ragged=True)
+    xd, ld = x.to(DEV), lens.to(DEV)
+    plan = model.plan_for(xd.shape, torch.device(DEV))
+    assert plan.stats["exact"] == 0 and plan.stats["f32_channels"] > 0.9 * plan.stats["channels"]
+    logits = plan.run(xd, ld).clone()
+    greedy = plan.greedy().clone()
+    out_lens = plan.out_lens().clone()
+    torch.cuda.synchronize()
+    assert torch.equal(plan.run(xd, ld), logits)                                  # determinism
+    # padding invariance: garbage beyond each utterance's length
+    x2 = x.clone()
+    for b in range(B):
+        x2[b, :, int(lens[b]):] = 1000.0 * torch.randn(x.shape[1], T - int(lens[b]))
+    logits2 = plan.run(x2.to(DEV), ld)
+    for b in range(0, B, 7):
+        n = int(out_lens[b])
+        assert torch.equal(logits2[b, :, :n], logits[b, :, :n])
+    # batch independence against batch-4 plans of the same model (a different plan / graph / grid)
+    for b0 in (0, 28, 60):
+        small = model.plan_for((4,) + tuple(xd.shape[1:]), torch.device(DEV))
+        ls = small.run(xd[b0:b0 + 4].contiguous(), ld[b0:b0 + 4].contiguous())
+        for i in range(4):
+            n = int(out_lens[b0 + i])
+            assert torch.equal(ls[i, :, :n], logits[b0 + i, :, :n]), "utterance %d differs between batch 64 and batch 4" % (b0 + i)
+    # serving loop == forward
+    got = list(model.transcribe_stream([(x.pin_memory(), lens.to(torch.int32).pin_memory())] * 2))
+    assert len(got) == 2 and torch.equal(got[0], greedy.cpu().to(torch.long)) and torch.equal(got[1], got[0])
