@@ -144,20 +144,27 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
   const int lane_w = ((a.halo - a.pad - a.d) >> 2) + 4 * S * g + tg;
   const int out_words = ((a.T_out + 15) >> 4) << 2;  // stores cover T_out rounded up to 16 (zero filled)
 
-  for (int r = 0; r < nrows; ++r) {
-    const int buf = r % kBufs;
+  // per-row bookkeeping is carried incrementally (no modulo / 64-bit multiplies on the row path)
+  const bool masked = a.ep.flags & QASR_F_MASK;
+  const int T_out = a.T_out, buf_bytes = a.buf_bytes;
+  const uint32_t copy_bytes = (uint32_t)a.copy_bytes;
+  const size_t out_row_step = (size_t)a.C * a.out_ld * (a.ep.mode == QASR_EPI_REQUANT_I8 ? 1 : 4);
+  uint8_t* out_row = reinterpret_cast<uint8_t*>(a.out) + ((size_t)b_begin * a.C + c) * a.out_ld * (a.ep.mode == QASR_EPI_REQUANT_I8 ? 1 : 4);
+  const uint8_t* x_next = xbase + (size_t)(kBufs - 1) * xstep;       // row r + kBufs - 1
+  int buf = 0, nb = kBufs - 1;
+  uint32_t par = 0;
+  for (int r = 0; r < nrows; ++r, out_row += out_row_step, x_next += xstep) {
     // keep kBufs-1 rows in flight: the buffer being refilled was consumed in iteration r-1
     if (lane == 0 && r + kBufs - 1 < nrows) {
-      const int nb = (r + kBufs - 1) % kBufs;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      row_copy_async(smem_addr(bufs + nb * a.buf_bytes + a.halo), xbase + (size_t)(r + kBufs - 1) * xstep,
-                     a.copy_bytes, smem_addr(bars + nb));
+      row_copy_async(smem_addr(bufs + nb * buf_bytes + a.halo), x_next, copy_bytes, smem_addr(bars + nb));
     }
-    bar_wait(smem_addr(bars + buf), (uint32_t)((r / kBufs) & 1));
-    const uint32_t* xw = reinterpret_cast<const uint32_t*>(bufs + buf * a.buf_bytes) + lane_w;
+    bar_wait(smem_addr(bars + buf), par);
+    const uint32_t* xw = reinterpret_cast<const uint32_t*>(bufs + buf * buf_bytes) + lane_w;
+    if (++nb == kBufs) nb = 0;
+    if (++buf == kBufs) { buf = 0; par ^= 1u; }
     const int b = b_begin + r;
-    const size_t row = (size_t)b * a.C + c;
-    const int len = (a.ep.flags & QASR_F_MASK) ? min(a.ep.out_lens[b], a.T_out) : a.T_out;
+    const int len = masked ? min(a.ep.out_lens[b], T_out) : T_out;
     // the tile loop exists twice, float and integer epilogue, chosen once per row (warp-uniform)
     auto tiles = [&](auto f32_tag) {
     constexpr bool F32 = decltype(f32_tag)::value;
@@ -166,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
     const int acc_init = F32 ? kF32MagicBits + c0.bias : 0;
     // stores of whole tiles below `full_end` need neither the length mask nor the row-end test (warp-uniform split)
     const int full_end = min(len, out_words * 4);
-    uint32_t* const orow_w = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(a.out) + row * a.out_ld) + lane;
+    uint32_t* const orow_w = reinterpret_cast<uint32_t*>(out_row) + lane;
     for (int t0 = 0; t0 < a.T_out; t0 += kTile) {
       const uint32_t* tw = xw + ((t0 * S) >> 2);
       int acc[4] = {acc_init, acc_init, acc_init, acc_init};
@@ -196,13 +203,13 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
           if ((tl >> 2) < out_words) orow_w[t0 >> 2] = word;
         }
       } else if (a.ep.mode == QASR_EPI_DEQUANT_F32) {
-        float* orow = reinterpret_cast<float*>(a.out) + row * a.out_ld;
+        float* orow = reinterpret_cast<float*>(out_row);
         if (t0 + o0 < a.T_out) orow[t0 + o0] = epilogue_dequant(a.ep, acc[0], c0);
         if (t0 + o1 < a.T_out) orow[t0 + o1] = epilogue_dequant(a.ep, acc[1], c0);
         if (t0 + o2 < a.T_out) orow[t0 + o2] = epilogue_dequant(a.ep, acc[2], c0);
         if (t0 + o3 < a.T_out) orow[t0 + o3] = epilogue_dequant(a.ep, acc[3], c0);
       } else {
-        int32_t* orow = reinterpret_cast<int32_t*>(a.out) + row * a.out_ld;
+        int32_t* orow = reinterpret_cast<int32_t*>(out_row);
         if (t0 + o0 < a.T_out) orow[t0 + o0] = acc[0] + c0.bias;
         if (t0 + o1 < a.T_out) orow[t0 + o1] = acc[1] + c0.bias;
         if (t0 + o2 < a.T_out) orow[t0 + o2] = acc[2] + c0.bias;
