@@ -93,7 +93,7 @@ template <int KS, int S, bool XS, int EK>
 #endif
 __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kernel(const DwArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint32_t stage[kWarps][32];
+  __shared__ uint32_t stage[kWarps][64];   // two 128-byte transpose lines per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, tg = lane & 3;
   pdl_trigger();
@@ -174,23 +174,21 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
     // stores of whole tiles below `full_end` need neither the length mask nor the row-end test (warp-uniform split)
     const int full_end = min(len, out_words * 4);
     uint32_t* const orow_w = reinterpret_cast<uint32_t*>(out_row) + lane;
-    for (int t0 = 0; t0 < a.T_out; t0 += kTile) {
-      const uint32_t* tw = xw + ((t0 * S) >> 2);
-      int acc[4] = {acc_init, acc_init, acc_init, acc_init};
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) imma_16832<XS>(acc, af[ks], tw[8 * ks], tw[8 * ks + 4]);
+    auto code = [&](int acc_v) -> uint8_t {
+      if (F32) return (uint8_t)epilogue_f32_bits_biased(kc, acc_v, c0);
+      return (uint8_t)(EK == 0 ? epilogue_fast<false, false, false>(a.ep, kc, acc_v, c0, 0, c0, 0)
+                               : epilogue_exact(a.ep, kc, acc_v, c0, false, 0, c0, 0));
+    };
+    // finished accumulators of the tile at t0 -> codes -> (transpose through the warp's staging line `sl`) -> store
+    auto finish_tile = [&](int t0, const int (&acc)[4], int sl) {
       if (EK != 2) {
-        auto code = [&](int acc_v) -> uint8_t {
-          if (F32) return (uint8_t)epilogue_f32_bits_biased(kc, acc_v, c0);
-          return (uint8_t)(EK == 0 ? epilogue_fast<false, false, false>(a.ep, kc, acc_v, c0, 0, c0, 0)
-                                   : epilogue_exact(a.ep, kc, acc_v, c0, false, 0, c0, 0));
-        };
-        sb[o0] = code(acc[0]);
-        sb[o1] = code(acc[1]);
-        sb[o2] = code(acc[2]);
-        sb[o3] = code(acc[3]);
+        uint8_t* sbl = sb + 128 * sl;
+        sbl[o0] = code(acc[0]);
+        sbl[o1] = code(acc[1]);
+        sbl[o2] = code(acc[2]);
+        sbl[o3] = code(acc[3]);
         __syncwarp();
-        uint32_t word = stage[warp][lane];
+        uint32_t word = stage[warp][32 * sl + lane];
         __syncwarp();
         if (t0 + kTile <= full_end) {
           orow_w[t0 >> 2] = word;
@@ -215,6 +213,28 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
         if (t0 + o2 < a.T_out) orow[t0 + o2] = acc[2] + c0.bias;
         if (t0 + o3 < a.T_out) orow[t0 + o3] = acc[3] + c0.bias;
       }
+    };
+    // two tiles per iteration: their dependent MMA chains interleave (no issue slots lost to the MMA latency) and
+    // their epilogues give the scheduler independent work
+    int t0 = 0;
+    for (; t0 + kTile < a.T_out; t0 += 2 * kTile) {
+      const uint32_t* tw0 = xw + ((t0 * S) >> 2);
+      const uint32_t* tw1 = tw0 + ((kTile * S) >> 2);
+      int acc0[4] = {acc_init, acc_init, acc_init, acc_init}, acc1[4] = {acc_init, acc_init, acc_init, acc_init};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        imma_16832<XS>(acc0, af[ks], tw0[8 * ks], tw0[8 * ks + 4]);
+        imma_16832<XS>(acc1, af[ks], tw1[8 * ks], tw1[8 * ks + 4]);
+      }
+      finish_tile(t0, acc0, 0);
+      finish_tile(t0 + kTile, acc1, 1);
+    }
+    if (t0 < a.T_out) {   // odd tile count: the last one alone
+      const uint32_t* tw = xw + ((t0 * S) >> 2);
+      int acc[4] = {acc_init, acc_init, acc_init, acc_init};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) imma_16832<XS>(acc, af[ks], tw[8 * ks], tw[8 * ks + 4]);
+      finish_tile(t0, acc, 0);
     }
     };
     if (EK == 3 || (EK == 0 && f32_path)) tiles(std::true_type{}); else tiles(std::false_type{});
