@@ -105,24 +105,30 @@ class ClockSampler:
                     reasons=reasons, samples=len(sm))
 
 
-def kernel_breakdown(plan, flush, iters=3):
-    """Per-op device time with CUDA events on the launching stream (plan run eagerly, op by op),
-    aggregated per kernel class, with the algorithmic bytes each class moves (each
-    conv reads its int8 input once and writes its int8 output once)."""
-    names = [n for n, _ in plan.ops]
-    acc = {n: 0.0 for n in names}
-    per_op = [0.0] * len(plan.ops)
+def kernel_breakdown(plan, flush, iters=5):
+    """Per-op device time with CUDA events on the launching stream, aggregated per kernel class, with the
+    algorithmic bytes each class moves (each conv reads its int8 input once and writes its int8
+    output once).  The plan is run eagerly, op by op, with one event recorded between consecutive launches and a
+    single synchronize at the end of the pass; a device-side spin in front keeps the device busy until the host has
+    queued the whole pass, so an op's time is the distance
+    between its two in-stream timestamps (kernel + the event records next to it), not a launch + sync round trip.
+    The events break the programmatic-dependent-launch overlap the CUDA graph of the timed step has, so the sum
+    over ops stays above the graph's step time; both are reported."""
+    n = len(plan.ops)
+    per_op = [0.0] * n
     for _ in range(iters):
         flush()
         for fn in plan._lens_fns:
             fn()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        torch.cuda._sleep(8_000_000)   # ~4 ms of device spin: every launch below is queued before the first one runs
+        evs[0].record()
         for i, (name, fn) in enumerate(plan.ops):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
             fn()
-            b.record()
-            b.synchronize()
-            per_op[i] += a.elapsed_time(b) / iters
+            evs[i + 1].record()
+        evs[n].synchronize()
+        for i in range(n):
+            per_op[i] += evs[i].elapsed_time(evs[i + 1]) / iters
     classes = {}
     for (name, _), ms, nbytes in zip(plan.ops, per_op, plan.op_bytes):
         cls = "dwconv" if name.startswith("dw_") else (
@@ -223,6 +229,14 @@ def run_ours(args):
     for _ in range(3):
         labels = step_e2e()
     barrier()
+    # the 26 MB pinned host -> device copy alone (explains the floor of the end-to-end number on this box)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        x_stage.copy_(x_pin, non_blocking=True)
+    b.record()
+    b.synchronize()
+    h2d_alone_ms = a.elapsed_time(b) / 5
     serial_ms = 0.0   # one batch at a time: copy in -> forward -> labels out (latency view)
     for _ in range(args.steps):
         flush()
@@ -269,21 +283,35 @@ def run_ours(args):
         return
     # ---- roofline of the dominant kernel class (rank 0, measured live, eager op-by-op run)
     classes = kernel_breakdown(plan, flush)
-    step_ms = sum(c["ms"] for c in classes.values())
+    eager_ms = sum(c["ms"] for c in classes.values())
     dom = max(classes, key=lambda k: classes[k]["ms"])
     peak, peak_src = peaks()
-    achieved = classes[dom]["bytes"] / (classes[dom]["ms"] / 1e3) / 1e9
+    # The timed step replays all launches from ONE CUDA graph with programmatic dependent launch, so a kernel has no
+    # event of its own inside it.  Its time inside the step = the step's device time (CUDA events, above) x the
+    # kernel class's share of the eager event pass (the same share the committed ncu launch list shows); the eager
+    # per-launch figure (events between launches, no launch overlap) is kept next to it as the lower bound.
+    step_ms_graph = total_ms / args.steps
+    share = classes[dom]["ms"] / eager_ms
+    in_step_ms = step_ms_graph * share
+    achieved = classes[dom]["bytes"] / (in_step_ms / 1e3) / 1e9
+    achieved_eager = classes[dom]["bytes"] / (classes[dom]["ms"] / 1e3) / 1e9
     macs = sum(m for (n, _), m in zip(plan.ops, plan.op_macs) if n.startswith("gemm_"))
+    tc_share = sum(v["ms"] for k, v in classes.items() if "tc" in k) / eager_ms
     roofline = dict(bound="hbm", kernel=dom, achieved=round(achieved, 1), peak=peak, unit="GB/s",
                     frac=round(achieved / peak, 4),
                     traffic=NCU_TRAFFIC.get(dom, {}).get("bytes"), traffic_note=NCU_TRAFFIC.get(dom, {}).get("note"),
                     peak_source=peak_src,
                     launches_per_step=classes[dom]["launches"],
                     algorithmic_bytes_per_step=classes[dom]["bytes"],
-                    kernel_ms_per_step=round(classes[dom]["ms"], 4),
-                    share_of_step=round(classes[dom]["ms"] / step_ms, 3),
-                    tensor_tops=round(2 * macs / (sum(v["ms"] for k, v in classes.items() if "tc" in k) / 1e3) / 1e12, 1),
-                    classes={k: dict(ms=round(v["ms"], 4), gbs=round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1),
+                    kernel_ms_per_step=round(in_step_ms, 4),
+                    share_of_step=round(share, 3),
+                    method="kernel time in the step = graph step time (CUDA events) x the class's share of an eager pass "
+                           "timed with one CUDA event between consecutive launches (no host sync inside the pass)",
+                    eager=dict(ms_per_step=round(eager_ms, 4), kernel_ms=round(classes[dom]["ms"], 4),
+                               achieved=round(achieved_eager, 1), frac=round(achieved_eager / peak, 4)),
+                    tensor_tops=round(2 * macs / (step_ms_graph * tc_share / 1e3) / 1e12, 1),
+                    classes={k: dict(eager_ms=round(v["ms"], 4), share=round(v["ms"] / eager_ms, 3),
+                                     gbs_in_step=round(v["bytes"] / (step_ms_graph * v["ms"] / eager_ms / 1e3) / 1e9, 1),
                                      launches=v["launches"]) for k, v in classes.items()})
     cpu = cpu_baseline(model, wl, seconds_budget=20.0)
     line = dict(
@@ -298,7 +326,9 @@ def run_ours(args):
                  ms_per_step=round(e2e_ms / args.steps, 4),
                  api="EncDecCTCModel.transcribe_stream: pinned host batches in, greedy labels out, copies "
                      "double-buffered around the kernels; K steps in one bracket, working set 3.3 GB/step > L2",
-                 serial_ms_per_step=round(serial_ms / args.steps, 4)),
+                 serial_ms_per_step=round(serial_ms / args.steps, 4),
+                 h2d_copy_alone_ms=round(h2d_alone_ms, 4),
+                 h2d_copy_alone_gbs=round(x_pin.numel() * 4 / (h2d_alone_ms / 1e3) / 1e9, 1)),
         gpu_launches=int(args.steps * (len(plan.ops) + 1) * 2),
         roofline=roofline, cpu_baseline=cpu, clocks=clocks, plan=plan.stats)
     print(json.dumps(line), flush=True)

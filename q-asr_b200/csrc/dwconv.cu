@@ -93,7 +93,7 @@ template <int KS, int S, bool XS, int EK>
 #endif
 __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kernel(const DwArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint32_t stage[kWarps][64];   // two 128-byte transpose lines per warp
+  __shared__ uint32_t stage[kWarps][128];  // four 128-byte transpose lines per warp (two per loop iteration, alternating)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, tg = lane & 3;
   pdl_trigger();
@@ -188,8 +188,9 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
         sbl[o2] = code(acc[2]);
         sbl[o3] = code(acc[3]);
         __syncwarp();
+        // no second barrier: the next iteration writes the OTHER pair of lines, and the barrier of that iteration
+        // orders these reads before the writes that reuse this line two iterations later
         uint32_t word = stage[warp][32 * sl + lane];
-        __syncwarp();
         if (t0 + kTile <= full_end) {
           orow_w[t0 >> 2] = word;
         } else {   // last tile(s) of the row: length mask (zero the bytes at t >= len) and row end
@@ -216,8 +217,8 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
     };
     // two tiles per iteration: their dependent MMA chains interleave (no issue slots lost to the MMA latency) and
     // their epilogues give the scheduler independent work
-    int t0 = 0;
-    for (; t0 + kTile < a.T_out; t0 += 2 * kTile) {
+    int t0 = 0, sp = 0;   // sp: which pair of staging lines this iteration uses
+    for (; t0 + kTile < a.T_out; t0 += 2 * kTile, sp ^= 2) {
       const uint32_t* tw0 = xw + ((t0 * S) >> 2);
       const uint32_t* tw1 = tw0 + ((kTile * S) >> 2);
       int acc0[4] = {acc_init, acc_init, acc_init, acc_init}, acc1[4] = {acc_init, acc_init, acc_init, acc_init};
@@ -226,15 +227,15 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
         imma_16832<XS>(acc0, af[ks], tw0[8 * ks], tw0[8 * ks + 4]);
         imma_16832<XS>(acc1, af[ks], tw1[8 * ks], tw1[8 * ks + 4]);
       }
-      finish_tile(t0, acc0, 0);
-      finish_tile(t0 + kTile, acc1, 1);
+      finish_tile(t0, acc0, sp);
+      finish_tile(t0 + kTile, acc1, sp + 1);
     }
     if (t0 < a.T_out) {   // odd tile count: the last one alone
       const uint32_t* tw = xw + ((t0 * S) >> 2);
       int acc[4] = {acc_init, acc_init, acc_init, acc_init};
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) imma_16832<XS>(acc, af[ks], tw[8 * ks], tw[8 * ks + 4]);
-      finish_tile(t0, acc, 0);
+      finish_tile(t0, acc, sp);
     }
     };
     if (EK == 3 || (EK == 0 && f32_path)) tiles(std::true_type{}); else tiles(std::false_type{});

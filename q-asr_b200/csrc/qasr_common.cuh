@@ -246,7 +246,11 @@ __device__ __forceinline__ int epilogue_fast(const EpiArgs& ep, const EpiConsts&
 // pattern, so the caller packs the returned words directly.  Equality with the dyadic for every reachable
 // accumulator and this clamp is proved on the host (qasr/plan.py f32_ok).
 __device__ __forceinline__ uint32_t epilogue_f32_bits(const EpiConsts& k, int acc, const ChanRegs& c) {
-  const float y = fmaf((float)(acc + c.bias), c.r, kF32Magic);
+  // int -> float without the half-rate I2F: |acc + bias| < 2^22 (host proof), so 0x4B400000 + (acc + bias) is the
+  // bit pattern of 1.5 * 2^23 + (acc + bias) and one FADD recovers the exact float; the constant
+  // bias + 0x4B400000 is loop invariant (one IADD + FADD per output instead of IADD + I2F)
+  const float f = __int_as_float(acc + (c.bias + 0x4B400000)) - kF32Magic;
+  const float y = fmaf(f, c.r, kF32Magic);
   return __float_as_uint(fminf(fmaxf(y, k.flo), k.fhi));
 }
 

@@ -110,6 +110,9 @@ GEMM_CASES = [
     ("pw_512_512_s8", 1, 512, 512, 130, 1, 1, True),
     ("dec_1024_29_s8", 2, 1024, 29, 77, 1, 1, True),
     ("tiny_32_48_u8", 3, 32, 48, 40, 1, 1, False),
+    ("pw_512_512_u8_t800", 3, 512, 512, 800, 1, 1, False),
+    ("pw_256_512_s8_t300", 2, 256, 512, 300, 1, 1, True),
+    ("pw_512_1024_u8_t520", 1, 512, 1024, 520, 1, 1, False),
     ("dense_k5", 2, 128, 128, 150, 5, 1, False),
     ("dense_k11_c384", 1, 256, 384, 140, 11, 1, False),
     ("dense_k7_dil2", 2, 96, 160, 90, 7, 2, False),
@@ -163,7 +166,7 @@ def gemm_engine(request):
 
 
 @pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
-@pytest.mark.parametrize("case", GEMM_CASES[:5], ids=lambda c: c[0])
+@pytest.mark.parametrize("case", GEMM_CASES[:8], ids=lambda c: c[0])
 def test_gemm_requant(case, fast, gemm_engine):
     name, B, ci, co, T, k, dil, signed = case
     q, w, bias, pad = _gemm_inputs(case, seed=1)
@@ -193,7 +196,7 @@ def test_gemm_requant(case, fast, gemm_engine):
     assert int(out[:, :, T_out:].abs().sum()) == 0  # pitch padding stays zero
 
 
-@pytest.mark.parametrize("case", GEMM_CASES[:5], ids=lambda c: c[0])
+@pytest.mark.parametrize("case", GEMM_CASES[:8], ids=lambda c: c[0])
 def test_gemm_requant_f32(case, gemm_engine):
     """Float fast path (QASR_F_FAST_F32): single operand, ReLU folded into the clamp, host-proved dyadics."""
     name, B, ci, co, T, k, dil, signed = case
