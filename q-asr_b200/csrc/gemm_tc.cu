@@ -72,6 +72,8 @@ struct GemmArgs {
   uint32_t stage_bytes;
   GemmSeg seg[2];
   uint32_t b_lbo, b_sbo, a_sbo;  // smem descriptor strides (bytes)
+  uint32_t b_layout;             // smem descriptor layout type of the activation operand: 2 = 128-byte swizzle, 4 = 64-byte swizzle
+  uint32_t b_kstep;              // bytes between two K steps (32 channels) of the activation operand inside a stage
   int dbg_align, dbg_nonneg;     // bring-up knobs (qasr_debug_set 2 / 3)
   int dbg_skip;                  // qasr_debug_set 6: 1 = epilogue does nothing, 2 = no MMA issue, 4 = no stores
   EpiArgs ep;
@@ -481,7 +483,7 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const uint32_t a_region = smem_base;                                  // this CTA's M tile: a_slabs x 16 KB, resident
   const uint32_t a_region_bytes = (uint32_t)g.a_slabs * kABytes;
   const uint32_t stage_base = smem_base + a_region_bytes;               // stages x 16 KB: this CTA's half of a slab
-  const uint32_t bars = stage_base + (uint32_t)g.stages * kBBytes;
+  const uint32_t bars = stage_base + (uint32_t)g.stages * g.stage_bytes;
   auto full_bar = [&](int s) { return bars + 8u * s; };                 // leader's copy collects both CTAs' loads
   auto empty_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * kMaxStages + s); };       // up to 4 accumulator buffers
@@ -548,6 +550,7 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     pdl_wait();   // weights above are constants of the plan; activations below come from the previous kernel
     int stage = 0;
     uint32_t phase = 0;
+    const uint32_t stage_bytes = g.stage_bytes;   // 16 KB (128-frame boxes) or 8 KB (64-frame boxes, bn = 128)
     int nt = n_first % n_tiles, b = n_first / n_tiles;
     const int seg_taps[2] = {g.seg[0].taps, g.seg[1].taps}, seg_cblocks[2] = {g.seg[0].cblocks, g.seg[1].cblocks};
     const int seg_dil[2] = {g.seg[0].dil, g.seg[1].dil}, seg_pad[2] = {g.seg[0].pad, g.seg[1].pad};
@@ -567,8 +570,8 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (leader) {
               const uint32_t lfull = leader_addr(full_bar(stage));
-              mbar_expect_tx_cluster(lfull, kBBytes);
-              tma_load_3d_pair(stage_base + (uint32_t)stage * kBBytes, mB, tcoord, cb * BK, b, lfull);
+              mbar_expect_tx_cluster(lfull, stage_bytes);
+              tma_load_3d_pair(stage_base + (uint32_t)stage * stage_bytes, mB, tcoord, cb * BK, b, lfull);
             }
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
@@ -579,9 +582,11 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // ===================== MMA issuer (leader CTA only) =====================
     const bool leader = elect_one();
     const int skip_mma = g.dbg_skip & 2;
-    const uint64_t a_hi = make_smem_desc(0, 0, g.a_sbo), b_hi = make_smem_desc(0, g.b_lbo, g.b_sbo);
+    const uint64_t a_hi = make_smem_desc(0, 0, g.a_sbo);
+    const uint64_t b_hi = (make_smem_desc(0, g.b_lbo, g.b_sbo) & ~((uint64_t)7 << 61)) | ((uint64_t)g.b_layout << 61);
     const uint32_t a_region_lo = (a_region & 0x3FFFFu) >> 4, stage_lo0 = (stage_base & 0x3FFFFu) >> 4;
-    constexpr uint32_t kSlabLo = kABytes >> 4, kStageLo = kBBytes >> 4, kKStepA = 32u >> 4, kKStepB = (32u * BN) >> 4;
+    constexpr uint32_t kSlabLo = kABytes >> 4, kKStepA = 32u >> 4;
+    const uint32_t kStageLo = g.stage_bytes >> 4, kKStepB = g.b_kstep >> 4;
     const uint32_t acc_per_stage = (uint32_t)(nseg * bn);
     int stage = 0;
     uint32_t phase = 0, stage_lo = stage_lo0;
@@ -737,15 +742,17 @@ int make_map_weights(CUtensorMap* map, const int8_t* wp, int rows, int c_in_pad)
   return QASR_OK;
 }
 
-int make_map_acts(CUtensorMap* map, const void* x, int T, int C, int B, int ld) {
+// frames = 128: the [128 frames][128 channels] box of the 128-byte swizzle; frames = 64: the half box a CTA of a pair
+// streams when the pair's tile is 128 frames wide (64-byte rows, 64-byte swizzle)
+int make_map_acts(CUtensorMap* map, const void* x, int T, int C, int B, int ld, int frames = BN) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { qasr_set_error("cuTensorMapEncodeTiled entry point not available"); return QASR_ERR_CUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)C, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)ld * (cuuint64_t)C};
-  cuuint32_t box[3] = {(cuuint32_t)BN, (cuuint32_t)BK, 1};
+  cuuint32_t box[3] = {(cuuint32_t)frames, (cuuint32_t)BK, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(x), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, frames == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { qasr_set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return QASR_ERR_CUDA; }
   return QASR_OK;
@@ -858,6 +865,8 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   g.a_sbo = 1024;
   g.b_sbo = qasr_debug_get(1) >= 0 ? (uint32_t)qasr_debug_get(1) : 1024;
   g.b_lbo = qasr_debug_get(0) >= 0 ? (uint32_t)qasr_debug_get(0) : (uint32_t)(BK * 128);
+  g.b_layout = 2;
+  g.b_kstep = 32u * BN;
   g.ep = make_epi_args(epi);
   g.dbg_align = qasr_debug_get(2) > 0 ? (int)qasr_debug_get(2) : 0;
   g.dbg_nonneg = qasr_debug_get(3) > 0 ? 1 : 0;
@@ -890,9 +899,23 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
     g.n_tiles = (T_out + g.bn - 1) / g.bn;
     g.n_total = g.n_tiles * B;
     g.stage_bytes = kBBytes;
-    g.stages = (int)((budget - a_bytes(1)) / kBBytes);
+    // 128-frame tiles: each CTA streams 64 frames of every slab as a [64 frames][128 channels] box in the 64-byte
+    // swizzle (8 KB per stage, nothing fetched twice).  Bring-up knob 14 = 0 keeps the full 128-frame boxes.
+    if (g.bn == 128 && qasr_debug_get(14) != 0) {
+      for (int i = 0; i < g.nseg; ++i) {
+        rc = make_map_acts(&maps[2 * i + 1], ops[i]->x, ops[i]->T_in, ops[i]->C_in, B, ops[i]->x_ld, 64);
+        if (rc) return rc;
+      }
+      if (g.nseg == 1) maps[3] = maps[1];
+      g.stage_bytes = kBBytes / 2;
+      g.b_layout = 4;
+      g.b_kstep = 32u * 64u;
+      g.b_sbo = qasr_debug_get(1) >= 0 ? (uint32_t)qasr_debug_get(1) : 512;
+      g.b_lbo = qasr_debug_get(0) >= 0 ? (uint32_t)qasr_debug_get(0) : (uint32_t)(BK * 64);
+    }
+    g.stages = (int)((budget - a_bytes(1)) / g.stage_bytes);
     if (g.stages > kMaxStages) g.stages = kMaxStages;
-    const uint32_t pair_smem = a_bytes(1) + (uint32_t)g.stages * kBBytes + kSmemSlack;
+    const uint32_t pair_smem = a_bytes(1) + (uint32_t)g.stages * g.stage_bytes + kSmemSlack;
     int pairs_per_group = (qasr_sm_count() / 2) / g.m_groups;
     if (pairs_per_group < 1) pairs_per_group = 1;
     if (pairs_per_group > g.n_total) pairs_per_group = g.n_total;

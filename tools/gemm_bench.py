@@ -49,8 +49,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "knobs":
     sys.exit(0)
 for (ci, co, dual) in ((512, 512, False), (512, 512, True), (256, 256, False), (256, 256, True), (256, 512, False), (256, 512, True),
                        (512, 1024, False), (1024, 1024, False)):
-    print("%4dx%4d dual=%d   1 CTA %7.1f us   CTA pair %7.1f us   pair bn256 %7.1f us" % (
-        ci, co, dual, run(ci, co, dual, {12: 0}), run(ci, co, dual, {12: 1}), run(ci, co, dual, {12: 1, 13: 256})), flush=True)
+    print("%4dx%4d dual=%d   1 CTA %7.1f us   CTA pair %7.1f us   pair bn128 half boxes %7.1f us   pair bn128 full boxes %7.1f us" % (
+        ci, co, dual, run(ci, co, dual, {12: 0}), run(ci, co, dual, {12: 1}), run(ci, co, dual, {12: 1, 13: 128}),
+        run(ci, co, dual, {12: 1, 13: 128, 14: 0})), flush=True)
 
 
 def run_ntc(ci, co, dual, iters=20):
