@@ -7,7 +7,7 @@ import numpy as np, torch
 from qasr import _lib as L, ops
 dev = "cuda:0"
 lib = L.lib()
-B, T = 64, 800
+B, T = int(os.environ.get("BENCH_B", "64")), 800
 FLUSH = False
 def run(ci, co, dual, knobs, iters=20, ld=None):
     ld = ld or T
