@@ -64,6 +64,20 @@ __device__ __forceinline__ void imma_16832(int (&acc)[4], const uint32_t (&a)[4]
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// first MMA of a chain: D = A x B + C with every C register = c (the initial accumulator value), D written to
+// fresh registers, so the loop needs no moves to re-initialise its accumulators
+template <bool XS>
+__device__ __forceinline__ void imma_16832_init(int (&acc)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, int c) {
+  if (XS)
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(c));
+  else
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(c));
+}
+
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -217,24 +231,47 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
     };
     // two tiles per iteration: their dependent MMA chains interleave (no issue slots lost to the MMA latency) and
     // their epilogues give the scheduler independent work
-    int t0 = 0, sp = 0;   // sp: which pair of staging lines this iteration uses
-    for (; t0 + kTile < a.T_out; t0 += 2 * kTile, sp ^= 2) {
-      const uint32_t* tw0 = xw + ((t0 * S) >> 2);
-      const uint32_t* tw1 = tw0 + ((kTile * S) >> 2);
-      int acc0[4] = {acc_init, acc_init, acc_init, acc_init}, acc1[4] = {acc_init, acc_init, acc_init, acc_init};
+    auto mma_pair = [&](const uint32_t* tw0, const uint32_t* tw1, int (&acc0)[4], int (&acc1)[4]) {
+      imma_16832_init<XS>(acc0, af[0], tw0[0], tw0[4], acc_init);
+      imma_16832_init<XS>(acc1, af[0], tw1[0], tw1[4], acc_init);
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
+      for (int ks = 1; ks < KS; ++ks) {
         imma_16832<XS>(acc0, af[ks], tw0[8 * ks], tw0[8 * ks + 4]);
         imma_16832<XS>(acc1, af[ks], tw1[8 * ks], tw1[8 * ks + 4]);
       }
+    };
+    int t0 = 0, sp = 0;   // sp: which pair of staging lines this iteration uses
+    if (EK != 2) {
+      // pairs of whole tiles below `full_end`: no mask, no row-end test, pointers advance by constants
+      const uint32_t* tw = xw;
+      uint32_t* ow = orow_w;
+      uint8_t* const sb0 = sb;
+      for (; t0 + 2 * kTile <= full_end; t0 += 2 * kTile, sp ^= 2, tw += (2 * kTile * S) >> 2, ow += (2 * kTile) >> 2) {
+        int acc0[4], acc1[4];
+        mma_pair(tw, tw + ((kTile * S) >> 2), acc0, acc1);
+        uint8_t* const l0 = sb0 + 128 * sp;
+        l0[o0] = code(acc0[0]); l0[o1] = code(acc0[1]); l0[o2] = code(acc0[2]); l0[o3] = code(acc0[3]);
+        l0[128 + o0] = code(acc1[0]); l0[128 + o1] = code(acc1[1]); l0[128 + o2] = code(acc1[2]); l0[128 + o3] = code(acc1[3]);
+        __syncwarp();
+        // no second barrier: the next iteration writes the OTHER pair of lines (see finish_tile)
+        const uint32_t w0 = stage[warp][32 * sp + lane], w1 = stage[warp][32 * sp + 32 + lane];
+        ow[0] = w0;
+        ow[kTile >> 2] = w1;
+      }
+    }
+    for (; t0 + kTile < a.T_out; t0 += 2 * kTile, sp ^= 2) {
+      const uint32_t* tw0 = xw + ((t0 * S) >> 2);
+      int acc0[4], acc1[4];
+      mma_pair(tw0, tw0 + ((kTile * S) >> 2), acc0, acc1);
       finish_tile(t0, acc0, sp);
       finish_tile(t0 + kTile, acc1, sp + 1);
     }
     if (t0 < a.T_out) {   // odd tile count: the last one alone
       const uint32_t* tw = xw + ((t0 * S) >> 2);
-      int acc[4] = {acc_init, acc_init, acc_init, acc_init};
+      int acc[4];
+      imma_16832_init<XS>(acc, af[0], tw[0], tw[4], acc_init);
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) imma_16832<XS>(acc, af[ks], tw[8 * ks], tw[8 * ks + 4]);
+      for (int ks = 1; ks < KS; ++ks) imma_16832<XS>(acc, af[ks], tw[8 * ks], tw[8 * ks + 4]);
       finish_tile(t0, acc, sp);
     }
     };
