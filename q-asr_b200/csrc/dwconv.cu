@@ -242,21 +242,32 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
     };
     int t0 = 0, sp = 0;   // sp: which pair of staging lines this iteration uses
     if (EK != 2) {
-      // pairs of whole tiles below `full_end`: no mask, no row-end test, pointers advance by constants
+      // pairs of whole tiles below `full_end`: no mask, no row-end test, pointers advance by constants and the
+      // staging lines are compile-time constants (the loop body is two pairs: lines 0-1, then lines 2-3)
       const uint32_t* tw = xw;
       uint32_t* ow = orow_w;
-      uint8_t* const sb0 = sb;
-      for (; t0 + 2 * kTile <= full_end; t0 += 2 * kTile, sp ^= 2, tw += (2 * kTile * S) >> 2, ow += (2 * kTile) >> 2) {
+      constexpr int kPairIn = (2 * kTile * S) >> 2, kPairOut = (2 * kTile) >> 2;
+      auto pair_fast = [&](auto line_tag, const uint32_t* twp, uint32_t* owp) {
+        constexpr int LINE = decltype(line_tag)::value;
         int acc0[4], acc1[4];
-        mma_pair(tw, tw + ((kTile * S) >> 2), acc0, acc1);
-        uint8_t* const l0 = sb0 + 128 * sp;
+        mma_pair(twp, twp + ((kTile * S) >> 2), acc0, acc1);
+        uint8_t* const l0 = sb + 128 * LINE;
         l0[o0] = code(acc0[0]); l0[o1] = code(acc0[1]); l0[o2] = code(acc0[2]); l0[o3] = code(acc0[3]);
         l0[128 + o0] = code(acc1[0]); l0[128 + o1] = code(acc1[1]); l0[128 + o2] = code(acc1[2]); l0[128 + o3] = code(acc1[3]);
         __syncwarp();
-        // no second barrier: the next iteration writes the OTHER pair of lines (see finish_tile)
-        const uint32_t w0 = stage[warp][32 * sp + lane], w1 = stage[warp][32 * sp + 32 + lane];
-        ow[0] = w0;
-        ow[kTile >> 2] = w1;
+        // no second barrier: the next pair writes the OTHER two lines (see finish_tile)
+        const uint32_t w0 = stage[warp][32 * LINE + lane], w1 = stage[warp][32 * LINE + 32 + lane];
+        owp[0] = w0;
+        owp[kTile >> 2] = w1;
+      };
+      for (; t0 + 4 * kTile <= full_end; t0 += 4 * kTile, tw += 2 * kPairIn, ow += 2 * kPairOut) {
+        pair_fast(std::integral_constant<int, 0>{}, tw, ow);
+        pair_fast(std::integral_constant<int, 2>{}, tw + kPairIn, ow + kPairOut);
+      }
+      if (t0 + 2 * kTile <= full_end) {
+        pair_fast(std::integral_constant<int, 0>{}, tw, ow);
+        t0 += 2 * kTile;
+        sp = 2;
       }
     }
     for (; t0 + kTile < a.T_out; t0 += 2 * kTile, sp ^= 2) {
