@@ -11,7 +11,11 @@
 //       D[16 x 8],  D[i][j] = out[t0 + 16 j + i]
 //       A[16 x K],  A[i][kk] = w[(kk - S i - d) / dil]      (banded; depends on the channel only)
 //       B[K  x 8],  B[kk][j] = x[P + 16 S j + kk],  P = S t0 - pad - d   (4-byte aligned)
-//   K = 32 * KS covers 15 S + d + (k-1) dil + 1 taps; d = (-pad) mod 4 absorbs the misalignment.
+//   K = 32 * KS covers 15 S + d + (k-1) dil + 1 taps; d = (-pad) mod 8 absorbs the misalignment.
+//   The K index of the MMA is a PERMUTATION of the window bytes, chosen so that the 2 KS words a lane needs are
+//   contiguous: k' = 32 ks + 16 h + 4 tg + e  <->  window byte v(k') = 4 (2 KS tg + 2 ks + h) + e; A is packed with
+//   the same permutation, so the sum over k is unchanged and every K step costs one 8-byte LDS instead of two
+//   4-byte ones.
 //   * A fragments (KS x 4 registers per lane) are packed once per layer by qasr_pack_dw_weights and
 //     loaded with KS*4 coalesced words per warp, then reused for every tile of that channel
 //     (several utterances per warp).
@@ -19,9 +23,8 @@
 //     row, completion on an mbarrier), kBufs rows per warp in flight, with zero halos on both sides
 //     of the row standing in for the conv padding: the HBM read is one coalesced stream per row and
 //     is issued two rows ahead of its use.
-//   * B fragments are plain aligned 32-bit words of the staged row: lane L needs words
-//     (P/4 + 4 S (L>>2) + (L&3) + 8 ks [+4]) -> for S = 1 consecutive lanes read consecutive words
-//     (conflict-free LDS), no bounds checks.
+//   * B fragments are plain aligned 64-bit words of the staged row: lane (g, tg) needs the word pairs
+//     (P/4 + 4 S g + 2 KS tg + 2 ks, +1), no bounds checks.
 //   * D (int32, 4 per lane) goes through the fused epilogue, the 4 result bytes are transposed
 //     through a 128-byte per-warp shared-memory line so the warp stores 128 contiguous bytes.
 // mma.sync m16n8k32 (IMMA) was measured at 0.48 instr/clk/SM (1.14 POPS) on B200: the MMA part of
@@ -43,7 +46,7 @@ struct DwArgs {
   const int8_t* w;
   void* out;
   int x_ld, out_ld, B, C, T_in, T_out, k, stride, dil, pad;
-  int d;          // (-pad) mod 4
+  int d;          // (-pad) mod 8
   int bchunk;     // utterances per warp work item
   int nbg;        // ceil(B / bchunk)
   int halo;       // zero bytes in front of the row inside a staging buffer (multiple of 16, >= pad + d)
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
   const int o0 = 32 * tg + g, o1 = o0 + 16, o2 = o0 + 8, o3 = o0 + 24;
   uint8_t* sb = reinterpret_cast<uint8_t*>(stage[warp]);
   // word offset of this lane's first B word relative to a tile: window start = halo - pad - d (bytes)
-  const int lane_w = ((a.halo - a.pad - a.d) >> 2) + 4 * S * g + tg;
+  const int lane_w = ((a.halo - a.pad - a.d) >> 2) + 4 * S * g + 2 * KS * tg;   // even: 8-byte aligned pairs
   const int out_words = ((a.T_out + 15) >> 4) << 2;  // stores cover T_out rounded up to 16 (zero filled)
 
   // per-row bookkeeping is carried incrementally (no modulo / 64-bit multiplies on the row path)
@@ -232,12 +235,17 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
     // two tiles per iteration: their dependent MMA chains interleave (no issue slots lost to the MMA latency) and
     // their epilogues give the scheduler independent work
     auto mma_pair = [&](const uint32_t* tw0, const uint32_t* tw1, int (&acc0)[4], int (&acc1)[4]) {
-      imma_16832_init<XS>(acc0, af[0], tw0[0], tw0[4], acc_init);
-      imma_16832_init<XS>(acc1, af[0], tw1[0], tw1[4], acc_init);
+      const uint2* p0 = reinterpret_cast<const uint2*>(tw0);
+      const uint2* p1 = reinterpret_cast<const uint2*>(tw1);
+      uint2 b0 = p0[0], b1 = p1[0];
+      imma_16832_init<XS>(acc0, af[0], b0.x, b0.y, acc_init);
+      imma_16832_init<XS>(acc1, af[0], b1.x, b1.y, acc_init);
 #pragma unroll
       for (int ks = 1; ks < KS; ++ks) {
-        imma_16832<XS>(acc0, af[ks], tw0[8 * ks], tw0[8 * ks + 4]);
-        imma_16832<XS>(acc1, af[ks], tw1[8 * ks], tw1[8 * ks + 4]);
+        b0 = p0[ks];
+        b1 = p1[ks];
+        imma_16832<XS>(acc0, af[ks], b0.x, b0.y);
+        imma_16832<XS>(acc1, af[ks], b1.x, b1.y);
       }
     };
     int t0 = 0, sp = 0;   // sp: which pair of staging lines this iteration uses
@@ -279,10 +287,15 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
     }
     if (t0 < a.T_out) {   // odd tile count: the last one alone
       const uint32_t* tw = xw + ((t0 * S) >> 2);
+      const uint2* pw2 = reinterpret_cast<const uint2*>(tw);
       int acc[4];
-      imma_16832_init<XS>(acc, af[0], tw[0], tw[4], acc_init);
+      uint2 bw = pw2[0];
+      imma_16832_init<XS>(acc, af[0], bw.x, bw.y, acc_init);
 #pragma unroll
-      for (int ks = 1; ks < KS; ++ks) imma_16832<XS>(acc, af[ks], tw[8 * ks], tw[8 * ks + 4]);
+      for (int ks = 1; ks < KS; ++ks) {
+        bw = pw2[ks];
+        imma_16832<XS>(acc, af[ks], bw.x, bw.y);
+      }
       finish_tile(t0, acc, sp);
     }
     };
@@ -327,10 +340,11 @@ __global__ void pack_dw_kernel(const int8_t* __restrict__ w, uint32_t* __restric
     const int lane = i & 31, r = (i >> 5) & 3, ks = (i >> 7) % KS, c = i / (KS * 128);
     const int g = lane >> 2, tg = lane & 3;
     const int row = g + 8 * (r & 1);
-    const int kk0 = 32 * ks + 16 * (r >> 1) + 4 * tg;
+    // MMA k index 32 ks + 16 (r >> 1) + 4 tg + bb <-> window byte 4 (2 KS tg + 2 ks + (r >> 1)) + bb (see the header)
+    const int v0 = 4 * (2 * KS * tg + 2 * ks + (r >> 1));
     uint32_t word = 0;
     for (int bb = 0; bb < 4; ++bb) {
-      const int u = kk0 + bb - S * row - d;
+      const int u = v0 + bb - S * row - d;
       int v = 0;
       if (u >= 0) {
         const int tap = u / dil;
@@ -342,8 +356,10 @@ __global__ void pack_dw_kernel(const int8_t* __restrict__ w, uint32_t* __restric
   }
 }
 
+inline int dw_misalign(int pad) { return ((-pad) % 8 + 8) % 8; }
+
 int dw_ksteps(int k, int stride, int dilation, int pad) {
-  const int d = ((-pad) % 4 + 4) % 4;
+  const int d = dw_misalign(pad);
   return (15 * stride + d + (k - 1) * dilation + 1 + 31) / 32;
 }
 
@@ -380,7 +396,7 @@ extern "C" int qasr_pack_dw_weights(const int8_t* w, void* wp, int32_t C, int32_
   if (table == 0) return QASR_OK;
   const int total = C * ks * 128;
   pack_dw_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      w, static_cast<uint32_t*>(wp), C, k, stride, dilation, ((-pad) % 4 + 4) % 4, ks);
+      w, static_cast<uint32_t*>(wp), C, k, stride, dilation, dw_misalign(pad), ks);
   return qasr_check_launch("pack_dw_kernel");
 }
 
@@ -402,8 +418,8 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
   int rc = qasr_validate_epilogue(epi, false);
   if (rc) return rc;
 
-  // engine choice (tools/dw_bench.py, batch 64 x 800 frames x 512 channels, float epilogue): IMMA 19.8 / 21.7 / 28.6 us
-  // for k = 33 / 75 / 87-dilated against 22.2 / 24.5 / 28.1 us on tcgen05 with TMA-fetched windows (its input
+  // engine choice (tools/dw_bench.py, batch 64 x 800 frames x 512 channels, float epilogue): IMMA 16.6 / 18.3 / 30.9 us
+  // for k = 33 / 75 / 87-dilated against 21.8 / 23.7 / 27.5 us on tcgen05 with TMA-fetched windows (its input
   // delivery costs 6.5 clk per 128-byte row per SM at 1.6x window overlap = 11 us, which the 20 epilogue warps'
   // drain does not yet hide).  The IMMA kernel runs wherever its 6 x 32-tap window reaches, the tcgen05 kernel
   // covers the longer windows.  Bring-up knob 8 forces one engine (0 = IMMA, 1 = tcgen05).
@@ -414,6 +430,9 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
   if (knob == 0 && table_bytes > 0) use_tc = false;
   if (knob == 1 && tc_ok) use_tc = true;
   if (table_bytes == 0) use_tc = true;   // only the tensor-core kernel covers this tap window
+  // 6 K steps (k = 87 dilated): the lanes' 8-byte fragment loads are 12 words apart and collide on banks
+  // (30.9 us against 27.5 us on tcgen05, 512 channels, batch 64 x 800 frames)
+  if (knob < 0 && tc_ok && dw_ksteps(k, stride, dilation, pad) >= 6) use_tc = true;
   if (use_tc) {
     if (!tc_ok) {
       qasr_set_error("dwconv: tap span (k=%d, dilation=%d, stride=%d) exceeds both kernels' windows", k, dilation, stride);
@@ -429,7 +448,7 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
   a.out = out;
   a.x_ld = x_ld; a.out_ld = out_ld; a.B = B; a.C = C; a.T_in = T_in; a.T_out = T_out;
   a.k = k; a.stride = stride; a.dil = dilation; a.pad = pad;
-  a.d = ((-pad) % 4 + 4) % 4;
+  a.d = dw_misalign(pad);
   const int span = (k - 1) * dilation + 1;
   const int ksteps = (15 * stride + a.d + span + 31) / 32;
   if (ksteps > 6) {
