@@ -483,6 +483,31 @@ def test_dwconv_requant(case, fast, dw_engine):
     assert int(out[:, :, T_out:].abs().sum()) == 0
 
 
+MERGED_TAIL_CASES = [
+    # several utterances per warp (forced with bring-up knob 10) and a T_out that leaves <= 32 frames after the whole
+    # 128-frame tiles: the row-ring / last-tile mask path of the IMMA kernel (and the case the merged-row-tail
+    # experiment, tools/experiments/dwconv_merged_row_tails.patch, was written for)
+    ("k33_T800_b10", 10, 64, 800, 33, 1, 1, False),
+    ("k63_T288_b7", 7, 32, 288, 63, 1, 1, True),
+    ("k75_T150_b9", 9, 48, 150, 75, 1, 1, False),
+    ("k39_T20_b5", 5, 40, 20, 39, 1, 1, False),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fast", [False, True, "f32"], ids=["exact", "fast", "f32"])
+@pytest.mark.parametrize("case", MERGED_TAIL_CASES, ids=lambda c: c[0])
+def test_dwconv_merged_row_tails(case, fast):
+    lib = L.lib()
+    lib.qasr_debug_set(8, 0)     # IMMA engine
+    lib.qasr_debug_set(10, 1)    # one warp per SM wanted -> several utterances per warp
+    try:
+        test_dwconv_requant(case, fast, 0)
+    finally:
+        lib.qasr_debug_set(8, -1)
+        lib.qasr_debug_set(10, -1)
+
+
 def test_dwconv_raw_and_dequant(dw_engine):
     B, Cn, T, k = 2, 48, 100, 33
     r = rng(6)
