@@ -143,7 +143,7 @@ def kernel_breakdown(plan, flush, iters=5):
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of each dominant-kernel class, from the committed
 # `ncu --set full` capture (bench workload, a 512-channel layer: 52.4 MB algorithmic bytes per launch)
 NCU_TRAFFIC = {
-    "dwconv": dict(bytes=27098112, note="512-channel depthwise layer, 52.4 MB algorithmic per launch; the 26 MB output "
+    "dwconv": dict(bytes=27065344, note="512-channel depthwise layer, 52.4 MB algorithmic per launch; the 26 MB output "
                                         "stays in the 126 MB L2 (profiles/r01_ncu_dw512_gemm512.txt)"),
     "gemm_i8_tc": dict(bytes=26753024, note="512x512 pointwise layer, 52.4 MB algorithmic per launch; output stays in L2 "
                                             "(profiles/r01_ncu_dw512_gemm512.txt)"),
