@@ -3,7 +3,8 @@
 set_percentile -> bn_folding -> calibrate on synthetic batches -> evaluate (-> set_dynamic) -> test loop
 with greedy CTC decoding and WER.
 
-Differences forced by the environment (no network, no NeMo core): `--asr_model` is a topology name
+Differences forced by the environment (no network, no NeMo core): `--asr_model` is a local `.nemo` archive
+(EncDecCTCModel.restore_from, like the reference's :72-74) or, instead of an NGC name, a topology name
 (`quartznet15x5`, `jasper10x5dr`, ...) optionally followed by `:checkpoint.pt` (a torch state_dict with the
 reference's key names, loaded with strict=False exactly like ModelPT.restore_from does), and `--dataset` is
 either `synthetic:<batches>:<frames>` or a torch file holding a list of
@@ -84,13 +85,17 @@ def main():
     args = parser.parse_args()
     torch.set_grad_enabled(False)
 
-    name, _, ckpt = args.asr_model.partition(":")
     torch.manual_seed(0)
-    asr_model = EncDecCTCModel.from_topology(name.lower().replace("-", ""))
-    if ckpt:
-        asr_model.load_state_dict(torch.load(ckpt, map_location="cpu"), strict=False)
+    if args.asr_model.endswith(".nemo"):   # reference inference.py:72-74
+        print("Using local ASR model from %s" % args.asr_model)
+        asr_model = EncDecCTCModel.restore_from(restore_path=args.asr_model)
     else:
-        reestimate_bn_(asr_model.encoder)  # random init needs healthy BN statistics
+        name, _, ckpt = args.asr_model.partition(":")
+        asr_model = EncDecCTCModel.from_topology(name.lower().replace("-", ""))
+        if ckpt:
+            asr_model.load_state_dict(torch.load(ckpt, map_location="cpu"), strict=False)
+        else:
+            reestimate_bn_(asr_model.encoder)  # random init needs healthy BN statistics
     asr_model = asr_model.cuda()
     test_data = load_dataset(args.dataset, args.batch_size)
 

@@ -2,11 +2,20 @@
 constructor :88-120 forces quant_mode 'symmetric', forward :384-406, set_quant_bit/mode :141-147)
 without the PyTorch-Lightning / NeMo-core substrate: preprocessor (optional) -> encoder ->
 decoder -> greedy argmax."""
+import inspect
+import os
+import tarfile
+import tempfile
+
 import torch
 import torch.nn as nn
 
 from nemo.collections.asr.modules.conv_asr import ConvASRDecoder, ConvASREncoder
 from qasr import topology as _topology
+
+# names inside a .nemo archive (reference nemo/core/classes/modelPT.py:40-41)
+_MODEL_CONFIG_YAML = "model_config.yaml"
+_MODEL_WEIGHTS = "model_weights.ckpt"
 
 __all__ = ["EncDecCTCModel"]
 
@@ -17,8 +26,10 @@ EN_VOCABULARY = [" ", "a", "b", "c", "d", "e", "f", "g", "h", "i", "j", "k", "l"
 class EncDecCTCModel(nn.Module):
     def __init__(self, jasper, feat_in=64, vocabulary=None, preprocessor=None, quant_bit=8):
         super().__init__()
-        vocabulary = EN_VOCABULARY if vocabulary is None else vocabulary
+        vocabulary = EN_VOCABULARY if vocabulary is None else list(vocabulary)
         self.preprocessor = preprocessor
+        self._cfg = dict(jasper=[dict(b) for b in jasper], feat_in=int(feat_in), vocabulary=list(vocabulary),
+                         preprocessor=getattr(preprocessor, "_cfg", None))
         self.spec_augmentation = None
         # the reference overrides the configs to quant_mode 'symmetric' (ctc_models.py:103-107)
         self.encoder = ConvASREncoder(jasper=jasper, activation="relu", feat_in=feat_in, conv_mask=True,
@@ -31,6 +42,92 @@ class EncDecCTCModel(nn.Module):
     @classmethod
     def from_topology(cls, name, **kw):
         return cls(_topology.TOPOLOGIES[name](), **kw)
+
+    # ---- .nemo checkpoints (reference nemo/core/classes/modelPT.py:254-296 save, :343-405 restore) -------------
+    def to_config_dict(self):
+        """The `model:` subtree the reference stores as model_config.yaml (examples/asr/conf/quartznet_15x5.yaml:3-240)."""
+        c = self._cfg
+        cfg = dict(
+            sample_rate=16000, labels=list(c["vocabulary"]),
+            encoder=dict(_target_="nemo.collections.asr.modules.ConvASREncoder", feat_in=c["feat_in"], activation="relu",
+                         conv_mask=True, jasper=[dict(b) for b in c["jasper"]]),
+            decoder=dict(_target_="nemo.collections.asr.modules.ConvASRDecoder", feat_in=c["jasper"][-1]["filters"],
+                         num_classes=len(c["vocabulary"]), vocabulary=list(c["vocabulary"])))
+        if c["preprocessor"] is not None:
+            cfg["preprocessor"] = dict(_target_="nemo.collections.asr.modules.AudioToMelSpectrogramPreprocessor",
+                                       **c["preprocessor"])
+        return cfg
+
+    @classmethod
+    def from_config_dict(cls, config, **kw):
+        """Builds the model from a reference-style config (the `model:` subtree, or a top-level file holding it).
+        Encoder / decoder / preprocessor entries follow the reference's yaml; both the `_target_` and the older
+        `cls` + `params` spellings are accepted.  Entries the quantised path has no use for (datasets, optimiser,
+        spec_augment) are ignored, exactly like the reference's inference script never touches them."""
+        cfg = config["model"] if "model" in config and "encoder" not in config else config
+
+        def params(node):
+            node = dict(node)
+            if "params" in node and isinstance(node["params"], dict):
+                node = dict(node["params"])
+            return {k: v for k, v in node.items() if k not in ("_target_", "cls")}
+
+        enc, dec = params(cfg["encoder"]), params(cfg["decoder"])
+        for key in ("activation", "conv_mask"):
+            enc.pop(key, None)   # fixed by the quantised path (relu, masked convs: ctc_models.py:103-107)
+        vocabulary = dec.get("vocabulary") or cfg.get("labels")
+        if vocabulary is None:
+            raise ValueError("config has neither decoder.vocabulary nor labels")
+        if "num_classes" in dec and dec["num_classes"] != len(vocabulary):
+            raise ValueError("If vocabulary is specified, it's length should be equal to the num_classes. "
+                             f"Instead got: num_classes={dec['num_classes']} and len(vocabulary)={len(vocabulary)}")
+        preprocessor = None
+        if cfg.get("preprocessor") is not None:
+            from nemo.collections.asr.modules.audio_preprocessing import AudioToMelSpectrogramPreprocessor
+            pp = params(cfg["preprocessor"])
+            known = inspect.signature(AudioToMelSpectrogramPreprocessor.__init__).parameters
+            pp = {k: v for k, v in pp.items() if k in known}
+            preprocessor = AudioToMelSpectrogramPreprocessor(**pp)
+            preprocessor._cfg = pp
+        return cls([dict(b) for b in enc["jasper"]], feat_in=int(enc.get("feat_in", 64)), vocabulary=list(vocabulary),
+                   preprocessor=preprocessor, **kw)
+
+    def save_to(self, save_path):
+        """Writes a .nemo archive: tar.gz of model_config.yaml + model_weights.ckpt (modelPT.py:254-296)."""
+        import yaml
+        with tempfile.TemporaryDirectory() as tmpdir:
+            with open(os.path.join(tmpdir, _MODEL_CONFIG_YAML), "w") as f:
+                yaml.safe_dump(self.to_config_dict(), f, sort_keys=False)
+            torch.save(self.state_dict(), os.path.join(tmpdir, _MODEL_WEIGHTS))
+            with tarfile.open(save_path, "w:gz") as tar:
+                tar.add(os.path.join(tmpdir, _MODEL_CONFIG_YAML), arcname="./" + _MODEL_CONFIG_YAML)
+                tar.add(os.path.join(tmpdir, _MODEL_WEIGHTS), arcname="./" + _MODEL_WEIGHTS)
+
+    @classmethod
+    def restore_from(cls, restore_path, override_config_path=None, map_location=None, strict=False, **kw):
+        """Restores weights and configuration from a .nemo archive (modelPT.py:343-405): model_config.yaml (or the
+        override yaml, whose `model:` subtree is taken) builds the module tree, model_weights.ckpt is loaded with
+        strict=False exactly like the reference does whatever `strict` says (:401), and the model moves to
+        `map_location` (CUDA when available)."""
+        import yaml
+        if not os.path.exists(restore_path):
+            raise FileNotFoundError(f"Can't find {restore_path}")
+        if map_location is None:
+            map_location = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+        with tempfile.TemporaryDirectory() as tmpdir:
+            with tarfile.open(restore_path, "r:*") as tar:
+                members = [m for m in tar.getmembers()
+                           if os.path.basename(m.name) in (_MODEL_CONFIG_YAML, _MODEL_WEIGHTS) and m.isfile()]
+                for m in members:   # flat extraction of the two known files only (no path traversal)
+                    m.name = os.path.basename(m.name)
+                    tar.extract(m, tmpdir, filter="data")
+            config_yaml = override_config_path or os.path.join(tmpdir, _MODEL_CONFIG_YAML)
+            with open(config_yaml) as f:
+                conf = yaml.safe_load(f)
+            instance = cls.from_config_dict(conf, **kw)
+            state = torch.load(os.path.join(tmpdir, _MODEL_WEIGHTS), map_location="cpu")
+            instance.load_state_dict(state, strict=False)
+        return instance.to(map_location)
 
     def set_quant_bit(self, quant_bit, mode="all"):
         self.encoder.set_quant_bit(quant_bit, mode)

@@ -166,3 +166,77 @@ def test_f32_ok_brute_force():
     # low byte of the float bit pattern is the two's complement code byte
     y = (magic + np.arange(-128, 128).astype(np.float32)).astype(np.float32)
     assert np.array_equal((y.view(np.uint32) & 0xff).astype(np.uint8), np.arange(-128, 128).astype(np.int8).view(np.uint8))
+
+
+REFERENCE_STYLE_YAML = """
+name: &name "QuartzNetTiny"
+model:
+  sample_rate: &sample_rate 16000
+  repeat: &repeat 2
+  dropout: &dropout 0.0
+  separable: &separable true
+  labels: &labels [" ", "a", "b", "c", "'"]
+  train_ds:
+    manifest_filepath: ???
+    batch_size: 32
+  preprocessor:
+    _target_: nemo.collections.asr.modules.AudioToMelSpectrogramPreprocessor
+    normalize: "per_feature"
+    window_size: 0.02
+    sample_rate: *sample_rate
+    window_stride: 0.01
+    window: "hann"
+    features: &n_mels 64
+    n_fft: 512
+    frame_splicing: 1
+    dither: 0.00001
+    stft_conv: false
+  spec_augment: {_target_: nemo.collections.asr.modules.SpectrogramAugmentation, rect_freq: 50}
+  encoder:
+    _target_: nemo.collections.asr.modules.ConvASREncoder
+    feat_in: *n_mels
+    activation: relu
+    conv_mask: true
+    jasper:
+    - {dilation: [1], dropout: *dropout, filters: 32, kernel: [9], repeat: 1, residual: false, separable: *separable, stride: [2]}
+    - {dilation: [1], dropout: *dropout, filters: 32, kernel: [11], repeat: *repeat, residual: true, separable: *separable, stride: [1]}
+    - {dilation: [2], dropout: *dropout, filters: 48, kernel: [13], repeat: 1, residual: false, separable: *separable, stride: [1]}
+    - {dilation: [1], dropout: *dropout, filters: 64, kernel: [1], repeat: 1, residual: false, stride: [1]}
+  decoder:
+    _target_: nemo.collections.asr.modules.ConvASRDecoder
+    feat_in: 64
+    num_classes: 5
+    vocabulary: *labels
+  optim: {name: novograd, lr: 0.01}
+"""
+
+
+def test_nemo_archive_round_trip(tmp_path):
+    """.nemo checkpoints (reference modelPT.py:254-296 / :343-405): tar.gz of model_config.yaml + model_weights.ckpt;
+    a reference-style yaml builds the same module tree, save_to -> restore_from gives back config and weights."""
+    import tarfile
+    import yaml
+    from nemo.collections.asr.models.ctc_models import EncDecCTCModel
+    torch.manual_seed(3)
+    model = EncDecCTCModel.from_config_dict(yaml.safe_load(REFERENCE_STYLE_YAML))
+    assert model.preprocessor is not None and len(model.encoder.encoder) == 4
+    assert model.decoder.vocabulary == [" ", "a", "b", "c", "'"]
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(torch.randn_like(p) * 0.01)
+    path = str(tmp_path / "tiny.nemo")
+    model.save_to(path)
+    with tarfile.open(path, "r:gz") as tar:
+        assert sorted(os.path.basename(n) for n in tar.getnames()) == ["model_config.yaml", "model_weights.ckpt"]
+    back = EncDecCTCModel.restore_from(restore_path=path, map_location=torch.device("cpu"))
+    assert back.to_config_dict() == model.to_config_dict()
+    sd0, sd1 = model.state_dict(), back.state_dict()
+    assert sd0.keys() == sd1.keys()
+    for k in sd0:
+        assert torch.equal(sd0[k], sd1[k]), k
+    with pytest.raises(FileNotFoundError):
+        EncDecCTCModel.restore_from(restore_path=str(tmp_path / "missing.nemo"))
+    bad = yaml.safe_load(REFERENCE_STYLE_YAML)
+    bad["model"]["decoder"]["num_classes"] = 7
+    with pytest.raises(ValueError):
+        EncDecCTCModel.from_config_dict(bad)
