@@ -152,7 +152,9 @@ class EncDecCTCModel(nn.Module):
         """Serving loop: the evaluation loop of examples/asr/quantization/inference.py:127-149 (for batch in the
         loader: .cuda() -> forward -> greedy argmax -> .cpu()) with the copies taken off the critical path.
         `batches` yields (processed_signal (B, C, T) float32, length (B,) int) HOST tensors, pinned for asynchronous
-        copies; greedy label tensors (B, T') int64 come back on the host, in order.  The host->device copy of batch
+        copies, or (input_signal (B, samples) float32 audio, length (B,) int samples) when the model has a
+        preprocessor (BASELINE config 5's chain: the mel featurizer runs on the device in front of the encoder);
+        greedy label tensors (B, T') int64 come back on the host, in order.  The host->device copy of batch
         i+1 runs on a copy stream into the other of two staging buffers while the kernels of batch i run, and the
         labels of batch i are read back asynchronously and handed out while batch i+1 is in flight.  Falls back to
         forward() per batch when the model is not in the fused static state."""
@@ -188,16 +190,26 @@ class EncDecCTCModel(nn.Module):
                 prefetch(j ^ 1, nxt)
             compute.wait_event(copied[j])
             x, n = stage[j]
+            raw_audio = x.dim() == 2
+            if raw_audio:
+                if self.preprocessor is None:
+                    raise ValueError("raw audio given but the model has no preprocessor")
+                x, n = self.preprocessor(input_signal=x, length=n)
+                consumed[j] = torch.cuda.Event()       # the featurizer has read the staging buffer
+                consumed[j].record(compute)
+                n = n.to(torch.int32)
             if self._fusable(x):
                 p = self.plan_for(x.shape, device)
                 p.run(x, n)                               # device copy into the plan's input + one graph replay
-                consumed[j] = torch.cuda.Event()
-                consumed[j].record(compute)
+                if not raw_audio:
+                    consumed[j] = torch.cuda.Event()
+                    consumed[j].record(compute)
                 labels = p.greedy()
             else:
                 labels = self.forward(processed_signal=x, processed_signal_length=n)[2].to(torch.int32)
-                consumed[j] = torch.cuda.Event()
-                consumed[j].record(compute)
+                if not raw_audio:
+                    consumed[j] = torch.cuda.Event()
+                    consumed[j].record(compute)
             if host_out[j] is None or host_out[j].shape != labels.shape:
                 host_out[j] = torch.empty(labels.shape, dtype=torch.int32).pin_memory()
             host_out[j].copy_(labels, non_blocking=True)   # in stream order: before the next replay overwrites it

@@ -85,3 +85,9 @@ def test_audio_to_labels_end_to_end():
     want = O.model_forward(spec, feats.cpu().numpy(), seq_len.cpu().numpy())   # same features in: integer parity
     assert np.array_equal(greedy.cpu().numpy(), want["greedy"])
     assert np.array_equal(enc_len.cpu().numpy(), want["lens"])
+    # the serving loop takes the same chain from pinned host audio: labels equal forward()'s, batch after batch
+    host = [(torch.from_numpy(audio).pin_memory(), torch.from_numpy(lengths).to(torch.int32).pin_memory())] * 3
+    outs = list(model.transcribe_stream(iter(host)))
+    assert len(outs) == 3
+    for o in outs:
+        assert np.array_equal(o.numpy(), want["greedy"])
