@@ -214,6 +214,18 @@ int qasr_dyadic_from_scales(const float* pre_sf, int32_t n, const float* z_sf,
 int qasr_codes_from_f32(const float* x, int32_t x_ld, const float* scale, int8_t* codes,
                         int32_t codes_ld, int32_t B, int32_t C, int32_t T, void* stream);
 
+/* Float-noise emulation of the module-level QuantConv1d (the reference never rounds x_int = x / s_x,
+ * quant_modules.py:301, so code q enters its float64 conv as q + eps(q)):
+ *   noise_codes:   out[i] = rne((f64(f32(f32(q) * s) / s) - q) * 2^22) for every code q of the buffer (n bytes,
+ *                  a multiple of 4; signed or unsigned codes); |.| <= 64.
+ *   combine_noise: out[b,c,t] = f32(f64(acc) + f64(bias[c]) + f64(dacc) * 2^-22) * s_out[c]   (:305-307), acc / dacc
+ *                  the raw int32 accumulators of the conv over the codes / over the noise codes; bias may be NULL. */
+int qasr_noise_codes_i8(const int8_t* codes, int32_t in_unsigned, const float* scale, int8_t* out, int64_t n,
+                        void* stream);
+int qasr_combine_noise_f32(const int32_t* acc, const int32_t* dacc, int32_t in_ld, const float* bias,
+                           const float* s_out, float* out, int32_t out_ld, int32_t B, int32_t C, int32_t T,
+                           void* stream);
+
 /* int8 -> int8 requantisation through a scalar dyadic (a QuantAct whose input already
  * has a scalar scale, e.g. a second consumer of a res_act output). */
 int qasr_requant_i8(const int8_t* in, int32_t in_ld, int32_t in_signed, int32_t m, int32_t e,

@@ -140,6 +140,39 @@ __global__ void codes_from_f32_kernel(const float* __restrict__ x, int x_ld, con
   }
 }
 
+// noise codes of the reference's un-rounded x_int (see include/qasr.h)
+__global__ void noise_codes_kernel(const uint32_t* __restrict__ codes, int in_unsigned, const float* scale,
+                                   uint32_t* __restrict__ out, long long n_words) {
+  __shared__ uint8_t lut[256];
+  {
+    const float s = scale[0];
+    const int q = in_unsigned ? (int)threadIdx.x : (int)(int8_t)threadIdx.x;
+    const float r = __fdiv_rn(__fmul_rn((float)q, s), s);
+    lut[threadIdx.x] = (uint8_t)(int8_t)(int)rint(((double)r - (double)q) * 4194304.0);
+  }
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_words; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t w = codes[i];
+    out[i] = (uint32_t)lut[w & 0xff] | ((uint32_t)lut[(w >> 8) & 0xff] << 8) | ((uint32_t)lut[(w >> 16) & 0xff] << 16) |
+             ((uint32_t)lut[w >> 24] << 24);
+  }
+}
+
+__global__ void combine_noise_kernel(const int32_t* __restrict__ acc, const int32_t* __restrict__ dacc, int in_ld,
+                                     const float* __restrict__ bias, const float* __restrict__ s_out,
+                                     float* __restrict__ out, int out_ld, int B, int C, int T) {
+  const long long total = (long long)B * C * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % T);
+    const long long row = i / T;
+    const int c = (int)(row % C);
+    double tot = (double)acc[row * in_ld + t];
+    if (bias) tot += (double)bias[c];
+    tot += (double)dacc[row * in_ld + t] * (1.0 / 4194304.0);
+    out[row * out_ld + t] = __fmul_rn((float)tot, s_out[c]);
+  }
+}
+
 __global__ void requant_i8_kernel(const int8_t* __restrict__ in, int in_ld, int in_signed, int m, int e,
                                   int qmin, int qmax, int8_t* out, int out_ld, int B, int C, int T,
                                   const int32_t* lens) {
@@ -449,6 +482,26 @@ extern "C" int qasr_codes_from_f32(const float* x, int32_t x_ld, const float* sc
   codes_from_f32_kernel<<<grid_for(work, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
       x, x_ld, scale, codes, codes_ld, B, C, T);
   return qasr_check_launch("codes_from_f32_kernel");
+}
+
+extern "C" int qasr_noise_codes_i8(const int8_t* codes, int32_t in_unsigned, const float* scale, int8_t* out, int64_t n,
+                                   void* stream) {
+  QASR_CHECK_ARG(codes && scale && out, "noise_codes: null pointer");
+  QASR_CHECK_ARG(n > 0 && n % 4 == 0 && (reinterpret_cast<uintptr_t>(codes) & 3) == 0 &&
+                 (reinterpret_cast<uintptr_t>(out) & 3) == 0, "noise_codes: size / alignment must be a multiple of 4");
+  noise_codes_kernel<<<grid_for(n / 4, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint32_t*>(codes), in_unsigned, scale, reinterpret_cast<uint32_t*>(out), n / 4);
+  return qasr_check_launch("noise_codes_kernel");
+}
+
+extern "C" int qasr_combine_noise_f32(const int32_t* acc, const int32_t* dacc, int32_t in_ld, const float* bias,
+                                      const float* s_out, float* out, int32_t out_ld, int32_t B, int32_t C, int32_t T,
+                                      void* stream) {
+  QASR_CHECK_ARG(acc && dacc && s_out && out, "combine_noise: null pointer");
+  QASR_CHECK_ARG(B > 0 && C > 0 && T > 0 && in_ld >= T && out_ld >= T, "combine_noise: bad shape");
+  combine_noise_kernel<<<grid_for((long long)B * C * T, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+      acc, dacc, in_ld, bias, s_out, out, out_ld, B, C, T);
+  return qasr_check_launch("combine_noise_kernel");
 }
 
 extern "C" int qasr_requant_i8(const int8_t* in, int32_t in_ld, int32_t in_signed, int32_t m, int32_t e,

@@ -345,20 +345,16 @@ class QuantConv1d(Module):
             # (|.| <= 64): delta is one more integer conv over LUT-mapped codes.  Reproducing it makes the
             # float outputs -- and every range statistic taken on them in calibration / dynamic mode --
             # bit-identical to the reference.
-            q = torch.arange(-256, 256, device=x.device, dtype=torch.float32)
-            eps = ((q * s_x) / s_x).double() - q.double()
-            lut = torch.round(eps * float(2 ** 22)).to(torch.int8)
-            idx = (codes.view(torch.uint8).to(torch.int64) if input_unsigned else codes.to(torch.int64)) + 256
-            rcodes = lut[idx]
+            rcodes = _ops.noise_codes(codes, s_x, input_unsigned)
             tab0 = torch.stack([s_out.contiguous().view(torch.int32), torch.zeros_like(b_i32), one, thirty],
                                dim=1).contiguous()
             acc = run_conv(codes, not input_unsigned, tab0, _L.EPI_RAW_I32,
                            torch.empty((B, self.out_channels, ld), dtype=torch.int32, device=x.device))
             dacc = run_conv(rcodes, True, tab0, _L.EPI_RAW_I32,
                             torch.empty((B, self.out_channels, ld), dtype=torch.int32, device=x.device))
-            bias64 = self.bias_integer.double() if p["bias"] is not None else torch.zeros_like(s_out).double()
-            tot = acc[:, :, :T_out].double() + bias64.view(1, -1, 1) + dacc[:, :, :T_out].double() * (2.0 ** -22)
-            conv_output = tot.float() * s_out.view(1, -1, 1)            # .type(torch.float) :305, rescale :307
+            # f32(f64(acc) + bias + f64(dacc) * 2^-22) * s_out: .type(torch.float) :305, rescale :307 (one kernel)
+            conv_output = _ops.combine_noise(acc, dacc, T_out, self.bias_integer if p["bias"] is not None else None,
+                                             s_out)
             return conv_output, s_out.view(1, -1, 1)
         if out.shape[-1] != T_out:
             conv_output = conv_output.contiguous()

@@ -66,6 +66,8 @@ _SIGS = {
                                    _i32, _i32, _i32, _vp, _vp]),
     "qasr_dyadic_from_scales": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp]),
     "qasr_codes_from_f32": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "qasr_noise_codes_i8": (C.c_int, [_vp, _i32, _vp, _vp, C.c_int64, _vp]),
+    "qasr_combine_noise_f32": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "qasr_requant_i8": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32,
                                   _vp, _vp]),
     "qasr_minmax_workspace_bytes": (_i64, []),

@@ -165,6 +165,26 @@ def codes_from_f32(x, scale):
     return codes
 
 
+def noise_codes(codes, scale, in_unsigned):
+    """LUT-mapped codes of the reference's un-rounded x_int (quant_modules.py:301): eps(q) * 2^22 as int8, same layout."""
+    codes = codes.contiguous()
+    out = torch.empty_like(codes)
+    L.check(L.lib().qasr_noise_codes_i8(L.ptr(codes), int(bool(in_unsigned)), L.ptr(scale), L.ptr(out), codes.numel(),
+                                        L.stream_ptr()))
+    return out
+
+
+def combine_noise(acc, dacc, T, bias_f32, s_out):
+    """f32(f64(acc) + bias + f64(dacc) * 2^-22) * s_out[c] (quant_modules.py:305-307) -> (B, C, T) float32."""
+    B, Cn, ld = acc.shape
+    out = torch.empty((B, Cn, T), dtype=torch.float32, device=acc.device)
+    s_out = s_out.reshape(-1).float().contiguous()
+    bias = None if bias_f32 is None else bias_f32.reshape(-1).float().contiguous()
+    L.check(L.lib().qasr_combine_noise_f32(L.ptr(acc), L.ptr(dacc), ld, L.ptr(bias), L.ptr(s_out), L.ptr(out), T,
+                                           B, Cn, T, L.stream_ptr()))
+    return out
+
+
 def requant_i8(x, T, in_signed, m, e, qmin, qmax, lens=None):
     B, Cn, ld = x.shape
     out = torch.zeros_like(x)
