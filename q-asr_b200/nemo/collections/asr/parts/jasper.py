@@ -99,12 +99,24 @@ class MaskedConv1d(nn.Module):
         # The reference's `assert not (float(x.min()) < -1e-5 and self.asymmetric)` (jasper.py:176)
         # costs a host sync per call; the invariant (asymmetric inputs are post-ReLU) holds by
         # construction of the block and is not re-checked on the hot path.
+        fused_mask = False
         if self.use_mask:
             lens = lens.to(dtype=torch.long)
-            mask = torch.arange(x.size(2), device=x.device).unsqueeze(0) >= lens.to(x.device).unsqueeze(1)
-            x = x.masked_fill(mask.unsqueeze(1), 0)
+            # The reference zeroes x[b, :, t >= lens[b]] with masked_fill (jasper.py:177-181) and hands the copy to
+            # QuantAct.  On the quantised CUDA path the range and requantisation kernels take the lengths instead
+            # (masked positions count as 0 there: same statistics, same outputs, one pass over x less).
+            fused_mask = (x.is_cuda and x.dim() == 3 and self.act.quant_mode == "symmetric" and not self.act.per_channel)
+            if fused_mask:
+                self.act._mask_lens = lens.to(device=x.device, dtype=torch.int32).contiguous()
+            else:
+                mask = torch.arange(x.size(2), device=x.device).unsqueeze(0) >= lens.to(x.device).unsqueeze(1)
+                x = x.masked_fill(mask.unsqueeze(1), 0)
             lens = self.get_seq_len(lens)
-        x, x_scaling_factor = self.act(x, scaling_factor)
+        try:
+            x, x_scaling_factor = self.act(x, scaling_factor)
+        finally:
+            if fused_mask:
+                self.act._mask_lens = None
         if self.conv.quant_mode == "none":
             out, out_scaling_factor = self.conv(x, x_scaling_factor)
         else:

@@ -102,12 +102,13 @@ class QuantAct(Module):
             if self.per_channel:
                 x_act = x3 if id3 is None else id3 + x3
                 return x_act.amin(dim=(0, 2)), x_act.amax(dim=(0, 2))
+            lens = getattr(self, "_mask_lens", None)   # set by MaskedConv1d: positions t >= lens[b] count as 0
             if percentile is None:
-                mm = _ops.minmax_f32(x3, id3)
+                mm = _ops.minmax_f32(x3, id3, lens=lens)
             else:
                 q_hi = torch.tensor(percentile / 100).item()       # float32 rounding of the level,
                 q_lo = torch.tensor(1 - percentile / 100).item()   # as torch.tensor(...) does (:122-123)
-                mm = _ops.quantile2_f32(x3, q_lo, q_hi, id3)
+                mm = _ops.quantile2_f32(x3, q_lo, q_hi, id3, lens=lens)
             return mm[0:1], mm[1:2]
         # quant_mode 'none' on CPU tensors (FP32 pass-through state only)
         x_act = x if identity is None else identity + x
@@ -165,12 +166,13 @@ class QuantAct(Module):
             # first layer: SymmetricQuantFunction, then the identity dyadic product (:180-190)
             if self.activation_bit > 8:
                 raise NotImplementedError("first-layer activation_bit > 8")
-            _, xq = _ops.quantize_f32(x3, z_sf, self.activation_bit, want_codes=False)
+            _, xq = _ops.quantize_f32(x3, z_sf, self.activation_bit, lens=getattr(self, "_mask_lens", None),
+                                      want_codes=False)
         else:
             id3 = None if identity is None else identity.reshape(x3.shape)
             _, xq = _ops.requant_f32(x3, pre_act_scaling_factor.float(), z_sf, -n - 1, n, identity=id3,
                                      id_sf=None if identity is None else identity_scaling_factor.float(),
-                                     want_codes=False)
+                                     lens=getattr(self, "_mask_lens", None), want_codes=False)
         return xq.view(x.shape), act_scaling_factor
 
     def _forward_per_channel(self, x, pre_sf, identity, identity_sf, act_sf, n):
