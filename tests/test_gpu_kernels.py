@@ -425,6 +425,8 @@ DW_CASES = [
     ("k63", 1, 128, 333, 63, 1, 1, False),
     ("k75", 2, 64, 250, 75, 1, 1, False),
     ("k87_dil2", 1, 64, 400, 87, 1, 2, False),
+    ("k99_4steps", 2, 32, 300, 99, 1, 1, False),      # 4 / 5 K steps of the IMMA window (permuted 8-byte fragment loads)
+    ("k121_5steps", 2, 32, 300, 121, 1, 1, True),
     ("k9_tiny", 3, 32, 32, 9, 1, 1, False),
     ("k9_s2_tiny", 3, 64, 64, 9, 2, 1, True),
     ("k13_dil2_tiny", 2, 32, 40, 13, 1, 2, False),
