@@ -29,18 +29,11 @@ if not torch.cuda.is_available():
     raise Exception("Current implementation only supports GPU")
 
 
-def ctc_decoder_predictions_tensor(predictions, vocabulary):
-    """Greedy CTC collapse (reference metrics/wer.py:117-136): merge repeats, drop blanks."""
-    blank_id = len(vocabulary)
-    hyps = []
-    for row in predictions.long().cpu().tolist():
-        out, previous = [], blank_id
-        for p in row:
-            if (p != previous or previous == blank_id) and p != blank_id:
-                out.append(p)
-            previous = p
-        hyps.append("".join(vocabulary[c] for c in out))
-    return hyps
+def hypotheses_from_tokens(tokens, counts, vocabulary):
+    """Strings of the greedy CTC hypotheses.  The collapse itself (reference metrics/wer.py:117-136: merge
+    repeats, drop blanks) ran on the device (qasr_ctc_collapse, through EncDecCTCModel.transcribe_stream);
+    `tokens` (B, T') holds each utterance's label ids compacted to the front, `counts` (B,) how many."""
+    return ["".join(vocabulary[c] for c in row[:n]) for row, n in zip(tokens.tolist(), counts.tolist())]
 
 
 def word_error_rate(hypotheses, references):
@@ -145,8 +138,8 @@ def main():
             meta.append((transcripts, float(lens.sum()) / 100.0))
             yield feats.float().pin_memory(), lens.to(torch.int32).pin_memory()
 
-    for k, greedy in enumerate(asr_model.transcribe_stream(host_batches())):
-        hypotheses += ctc_decoder_predictions_tensor(greedy, vocabulary)
+    for k, (tokens, counts) in enumerate(asr_model.transcribe_stream(host_batches(), collapse=True)):
+        hypotheses += hypotheses_from_tokens(tokens, counts, vocabulary)
         transcripts, secs = meta[k]
         if transcripts is not None:
             references += list(transcripts)
@@ -157,6 +150,7 @@ def main():
           (len(hypotheses), audio_s, dt, audio_s / dt))
     if references:
         print("WER:", word_error_rate(hypotheses=hypotheses, references=references))
+    return dict(hypotheses=hypotheses, model=asr_model, test_data=test_data, args=args)
 
 
 if __name__ == "__main__":

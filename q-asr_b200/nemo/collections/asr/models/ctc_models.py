@@ -144,11 +144,24 @@ class EncDecCTCModel(nn.Module):
                 and not (self.decoder.act.running_stat or self.decoder.act.dynamic or self.decoder.act.per_channel))
 
     def plan_for(self, shape, device):
+        """The compiled int8 plan for inputs of `shape` (frames rounded up to a bucket, qasr.plan.bucket_frames;
+        at most qasr.plan.MAX_PLANS are kept, least recently used first out)."""
         from qasr import plan as _plan
         return _plan.get_plan(self.encoder, self.decoder, shape, device, self._plan_cache)
 
+    def _plan_or_none(self, x):
+        """The fused plan when the model is in the fixed static state AND its structure can be compiled; None sends
+        the caller down the module-level path (configurations the plan compiler does not cover, e.g. strided
+        residual branches: it remembers the refusal, so the symbolic walk is not retried per call)."""
+        if not self._fusable(x):
+            return None
+        try:
+            return self.plan_for(x.shape, x.device)
+        except NotImplementedError:
+            return None
+
     @torch.no_grad()
-    def transcribe_stream(self, batches, device=None):
+    def transcribe_stream(self, batches, device=None, collapse=False):
         """Serving loop: the evaluation loop of examples/asr/quantization/inference.py:127-149 (for batch in the
         loader: .cuda() -> forward -> greedy argmax -> .cpu()) with the copies taken off the critical path.
         `batches` yields (processed_signal (B, C, T) float32, length (B,) int) HOST tensors, pinned for asynchronous
@@ -157,7 +170,10 @@ class EncDecCTCModel(nn.Module):
         greedy label tensors (B, T') int64 come back on the host, in order.  The host->device copy of batch
         i+1 runs on a copy stream into the other of two staging buffers while the kernels of batch i run, and the
         labels of batch i are read back asynchronously and handed out while batch i+1 is in flight.  Falls back to
-        forward() per batch when the model is not in the fused static state."""
+        forward() per batch when the model is not in the fused static state.
+        collapse=True additionally runs the greedy CTC collapse (reference metrics/wer.py:117-136: merge repeats, drop
+        blanks, over the whole row like the reference) on the device (qasr_ctc_collapse) and yields
+        (tokens (B, T') int64 padded with -1, counts (B,) int64) instead of the frame labels."""
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         compute = torch.cuda.current_stream(device)
         copier = torch.cuda.Stream(device)
@@ -170,6 +186,10 @@ class EncDecCTCModel(nn.Module):
             if stage[j] is None or stage[j][0].shape != x.shape:
                 stage[j] = (torch.empty(x.shape, dtype=torch.float32, device=device),
                             torch.empty(n.shape, dtype=torch.int32, device=device))
+                consumed[j] = None
+                # the block may be one the compute stream's queued kernels still use (caching allocator):
+                # order the first copy into it after everything already queued there
+                copier.wait_stream(compute)
             with torch.cuda.stream(copier):
                 if consumed[j] is not None:
                     copier.wait_event(consumed[j])       # the kernels that read this staging buffer are done with it
@@ -177,6 +197,10 @@ class EncDecCTCModel(nn.Module):
                 stage[j][1].copy_(n.to(torch.int32), non_blocking=True)
                 copied[j] = torch.cuda.Event()
                 copied[j].record(copier)
+
+        def _result(host):
+            host = host.to(torch.long)
+            return (host[:, :-1], host[:, -1]) if collapse else host
 
         nxt = next(it, None)
         if nxt is None:
@@ -198,8 +222,8 @@ class EncDecCTCModel(nn.Module):
                 consumed[j] = torch.cuda.Event()       # the featurizer has read the staging buffer
                 consumed[j].record(compute)
                 n = n.to(torch.int32)
-            if self._fusable(x):
-                p = self.plan_for(x.shape, device)
+            p = self._plan_or_none(x)
+            if p is not None:
                 p.run(x, n)                               # device copy into the plan's input + one graph replay
                 if not raw_audio:
                     consumed[j] = torch.cuda.Event()
@@ -210,6 +234,10 @@ class EncDecCTCModel(nn.Module):
                 if not raw_audio:
                     consumed[j] = torch.cuda.Event()
                     consumed[j].record(compute)
+            if collapse:
+                from qasr import ops as _ops
+                tokens, counts = _ops.ctc_collapse(labels, self.decoder.num_classes_with_blank - 1)
+                labels = torch.cat([tokens, counts.view(-1, 1)], dim=1)   # one read-back: [tokens | count]
             if host_out[j] is None or host_out[j].shape != labels.shape:
                 host_out[j] = torch.empty(labels.shape, dtype=torch.int32).pin_memory()
             host_out[j].copy_(labels, non_blocking=True)   # in stream order: before the next replay overwrites it
@@ -217,11 +245,11 @@ class EncDecCTCModel(nn.Module):
             out_ready[j].record(compute)
             if pending is not None:
                 out_ready[pending].synchronize()
-                yield host_out[pending].to(torch.long)
+                yield _result(host_out[pending])
             pending = j
             i += 1
         out_ready[pending].synchronize()
-        yield host_out[pending].to(torch.long)
+        yield _result(host_out[pending])
 
     def forward(self, input_signal=None, input_signal_length=None, processed_signal=None,
                 processed_signal_length=None):
@@ -235,8 +263,8 @@ class EncDecCTCModel(nn.Module):
                 raise ValueError("raw audio given but the model has no preprocessor")
             processed_signal, processed_signal_length = self.preprocessor(
                 input_signal=input_signal, length=input_signal_length)
-        if self._fusable(processed_signal):
-            p = self.plan_for(processed_signal.shape, processed_signal.device)
+        p = self._plan_or_none(processed_signal)
+        if p is not None:
             p.run(processed_signal, processed_signal_length)
             return p.log_probs(), p.out_lens().to(torch.long), p.greedy().to(torch.long)
         encoded, encoded_len, encoded_sf = self.encoder(audio_signal=processed_signal,

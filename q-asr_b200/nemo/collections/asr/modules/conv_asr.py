@@ -29,6 +29,8 @@ class ConvASREncoder(nn.Module):
                  quant_mode: Optional[str] = "none", quant_bit: Optional[int] = 8):
         super().__init__()
         jasper = [dict(c) for c in jasper]
+        self._activation_name = activation
+        self._check_activation(quant_mode)
         act = jasper_activations[activation]()
         feat_in = feat_in * frame_splicing
         self._feat_in = feat_in
@@ -68,12 +70,12 @@ class ConvASREncoder(nn.Module):
 
     # -- fused plan -----------------------------------------------------------------------
     def _fusable(self, audio_signal):
-        if not (self.use_fused_plan and self.quant_mode == "symmetric" and audio_signal.is_cuda):
+        if not (self.use_fused_plan and self.quant_mode == "symmetric" and audio_signal.is_cuda and not self.training):
             return False
         for m in self.modules():
             if type(m) is QuantAct and (m.running_stat or m.dynamic or m.per_channel):
                 return False
-            if type(m) is QuantConv1d and (m.quant_mode != "symmetric" or (m.bn is not None and not m.fix_bn)):
+            if isinstance(m, QuantConv1d) and (m.quant_mode != "symmetric" or (m.bn is not None and not m.fix_bn)):
                 return False
         return True
 
@@ -83,8 +85,12 @@ class ConvASREncoder(nn.Module):
     def forward(self, audio_signal, length=None, audio_signal_scaling_factor=None):
         if length is not None and audio_signal_scaling_factor is None and self._fusable(audio_signal):
             from qasr import plan as _plan
-            p = _plan.get_plan(self, None, audio_signal.shape, audio_signal.device, self._plan_cache)
-            return p.run_encoder(audio_signal, length)
+            try:
+                p = _plan.get_plan(self, None, audio_signal.shape, audio_signal.device, self._plan_cache)
+            except NotImplementedError:
+                p = None   # a structure the plan compiler does not cover (remembered): module-level path below
+            if p is not None:
+                return p.run_encoder(audio_signal, length)
         s_input = [(audio_signal, audio_signal_scaling_factor)]
         for layer in self.encoder_layers:
             s_input, length = layer((s_input, length))
@@ -105,7 +111,18 @@ class ConvASREncoder(nn.Module):
             l.set_quant_bit(quant_bit, mode)
         self.invalidate_plan()
 
+    def _check_activation(self, quant_mode):
+        """Every depthwise / dense / residual conv after the first quantises its input with an UNSIGNED range
+        (act_bit + 1, jasper.py:159-164), which is only right behind a non-negative activation: the reference
+        asserts it on every call (`assert not (x.min() < -1e-5 and self.asymmetric)`, jasper.py:176, one host
+        sync each).  Here the condition is checked once, where it is decided."""
+        if quant_mode == "symmetric" and self._activation_name != "relu":
+            raise NotImplementedError("quantised execution needs a non-negative block activation (relu): '%s' would "
+                                      "feed negative values to the unsigned activation quantisers "
+                                      "(reference assertion jasper.py:176)" % self._activation_name)
+
     def set_quant_mode(self, quant_mode):
+        self._check_activation(quant_mode)
         self.quant_mode = quant_mode
         for l in self.encoder_layers:
             l.set_quant_mode(self.quant_mode)

@@ -99,6 +99,10 @@ class MaskedConv1d(nn.Module):
         # The reference's `assert not (float(x.min()) < -1e-5 and self.asymmetric)` (jasper.py:176)
         # costs a host sync per call; the invariant (asymmetric inputs are post-ReLU) holds by
         # construction of the block and is not re-checked on the hot path.
+        if self.conv.quant_mode == "symmetric" and self.act.activation_bit > (9 if self.asymmetric else 8):
+            # codes travel as 8-bit tensors: signed inputs fit 8 bits, the unsigned (act_bit + 1) inputs 9
+            raise NotImplementedError("act_bit %d: the integer kernels carry activation codes in 8 bits (act_bit <= 8)"
+                                      % (self.act.activation_bit - (1 if self.asymmetric else 0)))
         fused_mask = False
         if self.use_mask:
             lens = lens.to(dtype=torch.long)

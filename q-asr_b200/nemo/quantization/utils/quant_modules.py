@@ -30,6 +30,17 @@ logger = logging.getLogger(__name__)
 __all__ = ["QuantAct", "QuantConv1d", "QuantBnConv1d", "QuantLinear"]
 
 
+_STATE_COUNTER = [0]
+
+
+def _bump(module):
+    """Monotonic state stamp: compiled plans (qasr.plan) key on it, so any change of a range buffer, bit width,
+    mode flag, weight / bias tensor or folded BatchNorm through attribute assignment invalidates them (an id()
+    of a reassigned tensor can be recycled; a stamp cannot)."""
+    _STATE_COUNTER[0] += 1
+    object.__setattr__(module, "_state_version", _STATE_COUNTER[0])
+
+
 def _require_cuda(t, what):
     if not t.is_cuda:
         raise RuntimeError("%s: quantised execution needs CUDA tensors (sm_100a kernels; there is no "
@@ -69,6 +80,14 @@ class QuantAct(Module):
             raise NotImplementedError("unsupported quant mode: {}".format(quant_mode))
         else:
             raise ValueError("unknown quant mode: {}".format(quant_mode))
+
+    _STAMPED = frozenset(("x_min", "x_max", "activation_bit", "dynamic", "running_stat", "per_channel", "quant_mode",
+                          "percentile", "act_range_momentum"))
+
+    def __setattr__(self, name, value):
+        super().__setattr__(name, value)
+        if name in QuantAct._STAMPED:
+            _bump(self)
 
     def __repr__(self):
         return "{0}(activation_bit={1}, quant_mode: {2}, Act_min: {3:.2f}, Act_max: {4:.2f})".format(
@@ -219,6 +238,22 @@ class QuantConv1d(Module):
         # conv per call; the fused static plan does not need it).  False = noise-free integer recipe.
         self.exact_float_noise = True
 
+    _STAMPED = frozenset(("bn", "fix_bn", "weight_bit", "quant_mode", "weight", "bias", "per_channel", "bias_bit"))
+
+    def __setattr__(self, name, value):
+        super().__setattr__(name, value)
+        if name in QuantConv1d._STAMPED:
+            _bump(self)
+
+    def state_signature(self):
+        """Everything a compiled plan bakes in from this module: the assignment stamp plus the in-place version
+        and address of every tensor the folded integer parameters are derived from."""
+        def tv(t):
+            return None if t is None else (t.data_ptr(), t._version)
+        bn = self.bn
+        return (self._state_version, tv(self.weight), tv(self.bias),
+                None if bn is None else (tv(bn.weight), tv(bn.bias), tv(bn.running_mean), tv(bn.running_var), bn.eps))
+
     def set_param(self, conv):
         self.in_channels = conv.in_channels
         self.out_channels = conv.out_channels
@@ -267,11 +302,7 @@ class QuantConv1d(Module):
         return weight, bias
 
     def _prepare(self):
-        key = (self.weight._version, self.weight.data_ptr(), self.weight_bit, self.per_channel,
-               None if self.bias is None else self.bias._version,
-               None if self.bn is None else (self.bn.weight._version, self.bn.bias._version,
-                                             self.bn.running_mean._version, self.bn.running_var._version,
-                                             self.fix_bn))
+        key = (self.state_signature(), self.weight_bit, self.per_channel, self.fix_bn)
         if key != self._prep_key:
             weight, bias = self.folded_params()
             if self.per_channel:

@@ -5,9 +5,12 @@ nn.Module attribute reachable through dir(model)."""
 import torch.nn as nn
 
 from nemo.quantization.utils.quant_modules import *  # noqa: F401,F403
-from nemo.quantization.utils.quant_modules import QuantAct, QuantConv1d, QuantLinear
+from nemo.quantization.utils.quant_modules import QuantAct, QuantBnConv1d, QuantConv1d, QuantLinear
 
-list_all = [QuantAct, QuantLinear, QuantConv1d]
+# the reference's list (quantize_model.py:3) plus QuantBnConv1d, the north-star name for QuantConv1d with its
+# BatchNorm folded at set_param time: the traversal matches on exact type(), so the subclass has to be listed
+# to be fixed / unfixed with the rest
+list_all = [QuantAct, QuantLinear, QuantConv1d, QuantBnConv1d]
 
 
 def _visit(model, leaf_fn):
@@ -56,4 +59,4 @@ def train(model):
 
 def calibrate(model):
     """Calibration mode - only QuantAct is unfixed (range tracking on)."""
-    freeze_model(model, [QuantConv1d, QuantLinear])
+    freeze_model(model, [QuantConv1d, QuantBnConv1d, QuantLinear])

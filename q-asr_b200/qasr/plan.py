@@ -229,7 +229,10 @@ class FusedPlan:
         self.x_in = torch.zeros((B, self.C_in, self.T), dtype=torch.float32, device=self.device)
         self.lens = [torch.zeros(B, dtype=torch.int32, device=self.device)]   # per length stage
         self._lens_fns = []
+        self._len_stages = []   # (k, stride, dilation, pad) of every conv that changes the frame count
+        self.cur_T = self.T
         self._build()
+        self.cur_T_out = self.out_frames(self.T)
         self.graph = None
         self.use_graph = use_graph
         self._warm = False
@@ -240,7 +243,7 @@ class FusedPlan:
         from nemo.quantization.utils.quant_modules import QuantConv1d
         dense = depthwise = False
         for m in self.encoder.modules():
-            if type(m) is QuantConv1d:
+            if isinstance(m, QuantConv1d):
                 dw = m.groups == m.in_channels == m.out_channels and m.groups > 1
                 depthwise |= dw
                 dense |= (not dw) and (m.kernel_size[0] > 1 or m.stride[0] > 1)
@@ -301,6 +304,7 @@ class FusedPlan:
 
     def _new_len_stage(self, stage, k, s, d, p):
         prev = self.lens[stage]
+        self._len_stages.append((k, s, d, p))
         self.lens.append(torch.zeros_like(prev))
         idx = len(self.lens) - 1
 
@@ -542,10 +546,24 @@ class FusedPlan:
             self.graph = g
         self.graph.replay()
 
+    def out_frames(self, T):
+        """Encoder frames of a T-frame input (MaskedConv1d.get_seq_len, jasper.py:170-173, through every length stage)."""
+        for (k, s, d, p) in self._len_stages:
+            T = (T + 2 * p - d * (k - 1) - 1) // s + 1
+        return T
+
     def load_inputs(self, x, lens):
-        if tuple(x.shape) != (self.B, self.C_in, self.T):
+        """x: (B, C, T) with T <= the plan's frame bucket (see bucket_frames); the tail of the bucket is zero."""
+        B, C, T = x.shape
+        if (B, C) != (self.B, self.C_in) or T > self.T:
             raise ValueError("plan compiled for input %s, got %s" % ((self.B, self.C_in, self.T), tuple(x.shape)))
-        self.x_in.copy_(x, non_blocking=True)
+        if T == self.T:
+            self.x_in.copy_(x, non_blocking=True)
+        else:
+            self.x_in[:, :, :T].copy_(x, non_blocking=True)
+            if self.cur_T != T:
+                self.x_in[:, :, T:].zero_()
+        self.cur_T, self.cur_T_out = T, self.out_frames(T)
         self.lens[0].copy_(lens.to(torch.int32), non_blocking=True)
 
     def run(self, x=None, lens=None):
@@ -553,24 +571,20 @@ class FusedPlan:
         if x is not None:
             self.load_inputs(x, lens)
         self._replay()
-        return self.logits[:, :, :self.logits_T] if self.logits is not None else None
+        return self.logits[:, :, :self.cur_T_out] if self.logits is not None else None
 
     def run_encoder(self, x, lens):
         """ConvASREncoder.forward contract: (encoded float32 (B,C,T'), encoded_len, scale (1,C,1))."""
         self.load_inputs(x, lens)
         self._replay()
-        enc = self.encoded[:, :, :self.encoded_T]
-        if self.encoded.shape[-1] != self.encoded_T:
-            enc = enc.contiguous()
-        else:
-            enc = enc.clone()
+        enc = self.encoded[:, :, :self.cur_T_out].clone()
         return enc, self.out_lens().to(torch.long), self.encoded_scale
 
     def greedy(self):
-        return ops.ctc_argmax(self.logits, self.logits_T)
+        return ops.ctc_argmax(self.logits, self.cur_T_out)
 
     def log_probs(self):
-        return ops.log_softmax_tv(self.logits, self.logits_T)
+        return ops.log_softmax_tv(self.logits, self.cur_T_out)
 
     def out_lens(self):
         return self.lens[self.enc_stage]
@@ -580,23 +594,57 @@ class FusedPlan:
 
 
 def _signature(encoder, decoder):
+    """Everything the compiled plan bakes in.  Quant modules stamp every attribute assignment (ranges, bit widths,
+    flags, weights, folded BN: quant_modules._bump), in-place edits show in the tensors' version counters."""
     from nemo.quantization.utils.quant_modules import QuantAct, QuantConv1d
     sig = []
     mods = list(encoder.modules()) + (list(decoder.modules()) if decoder is not None else [])
     for m in mods:
         if type(m) is QuantAct:
-            sig.append((m.activation_bit, id(m.x_min), m.x_min._version, id(m.x_max), m.x_max._version))
-        elif type(m) is QuantConv1d:
-            sig.append((m.weight_bit, m.weight._version, id(m.bn), m.quant_mode))
+            sig.append((m._state_version, m.x_min.data_ptr(), m.x_min._version, m.x_max.data_ptr(), m.x_max._version))
+        elif isinstance(m, QuantConv1d):
+            sig.append(m.state_signature())
     return tuple(sig)
 
 
+MAX_PLANS = 4   # compiled plans kept per model (LRU): each holds every int8 activation tensor of its shape + a CUDA graph
+
+
+def bucket_frames(T):
+    """Frame-count bucket a plan is compiled for: inputs are zero-padded up to it.  Every conv input is length-masked
+    (jasper.py:177-181) and the conv's own padding is zeros too, so every output frame below the unpadded T' is
+    bit-identical to an unbucketed run; ragged evaluation sets then share a handful of plans instead of compiling
+    one per distinct length."""
+    step = 128 if T <= 1024 else 256
+    return (int(T) + step - 1) // step * step
+
+
+class PlanUnsupported(Exception):
+    """Negative cache entry: this model state cannot be compiled (the module-level path serves it)."""
+
+
 def get_plan(encoder, decoder, in_shape, device, cache, **kw):
-    key = (tuple(in_shape), str(device), id(decoder))
+    """Plan for (batch, channels, bucket_frames(T)); `cache` is an ordered dict used as an LRU of MAX_PLANS entries.
+    Raises NotImplementedError when the model cannot be fused (remembered per signature, so the symbolic walk is not
+    retried on every forward)."""
+    B, C, T = (int(v) for v in in_shape)
+    key = ((B, C, bucket_frames(T)), str(device), id(decoder))
     sig = _signature(encoder, decoder)
     hit = cache.get(key)
     if hit is not None and hit[0] == sig:
+        cache[key] = cache.pop(key)            # most recently used last
+        if isinstance(hit[1], PlanUnsupported):
+            raise NotImplementedError(str(hit[1]))
         return hit[1]
-    plan = FusedPlan(encoder, decoder, in_shape, device, **kw)
+    cache.pop(key, None)
+    for k in [k for k, v in cache.items() if v[0] != sig]:
+        del cache[k]                           # plans of an older model state are dead weight
+    try:
+        plan = FusedPlan(encoder, decoder, key[0], device, **kw)
+    except NotImplementedError as exc:
+        cache[key] = (sig, PlanUnsupported(str(exc)))
+        raise
     cache[key] = (sig, plan)
+    while len(cache) > MAX_PLANS:
+        cache.pop(next(iter(cache)))
     return plan

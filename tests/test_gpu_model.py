@@ -141,7 +141,7 @@ def test_golden_network_fused_plan(path):
                 continue
             n = names[id(qt.info.module)].replace("encoder.encoder.", "encoder.")
             ref = case["trace"][n][0]["codes"]
-            assert np.array_equal(qt.codes_bct(), ref), n
+            assert np.array_equal(qt.codes_bct()[:, :, :ref.shape[-1]], ref), n   # the plan is compiled for the frame bucket
             checked += 1
         assert checked > 8
     # public API path (EncDecCTCModel.forward picks the plan up by itself)
@@ -278,7 +278,7 @@ def test_quartznet15x5_static_vs_oracle(quartznet, wbit, abit, percentile):
             ref = by_name["decoder"]["in_codes"]
         else:
             continue
-        assert np.array_equal(qt.codes_bct(), ref), n
+        assert np.array_equal(qt.codes_bct()[:, :, :ref.shape[-1]], ref), n   # the plan is compiled for the frame bucket
         checked += 1
     assert checked >= 150
     print("plan stats", plan.stats)
@@ -352,7 +352,8 @@ def test_jasper10x5dr_static_vs_oracle():
             continue
         n = names[id(qt.info.module)].replace("encoder.encoder.", "encoder.")
         if n.endswith(".act") and n[:-4] in by_name:
-            assert np.array_equal(qt.codes_bct(), by_name[n[:-4]][0]["in_codes"]), n
+            ref = by_name[n[:-4]][0]["in_codes"]
+            assert np.array_equal(qt.codes_bct()[:, :, :ref.shape[-1]], ref), n
             checked += 1
     assert checked >= 50
     print("jasper plan stats", plan.stats)

@@ -141,3 +141,65 @@ def test_ctc_collapse_known_answers():
     assert O.ctc_greedy_collapse([28, 2, 2, 28, 2, 0, 0, 19, 28], 28) == [2, 2, 0, 19]
     assert O.ctc_greedy_collapse([28, 28], 28) == []
     assert O.ctc_greedy_collapse([3, 3, 3], 28) == [3]
+
+
+# ------------------------------------------------------------------------------------------
+# round-2 fixtures (tests/golden/gen_golden_extra.py): QuantAct(per_channel=True), QuantLinear,
+# QuantConv1d with a folded, un-fixed BatchNorm
+# ------------------------------------------------------------------------------------------
+EXTRA = specio.load(os.path.join(GOLDEN, "ops_extra.npz"))
+
+
+@pytest.mark.parametrize("case", [c for c in EXTRA if c["kind"] == "act_per_channel"], ids=lambda c: c["tag"])
+def test_quant_act_per_channel(case):
+    act = O.ActStatePC(case["bit"], case["x_min0"], case["x_max0"], case["momentum"], case["dynamic"],
+                       case["running_stat"])
+    for call in case["calls"]:
+        pre = None if call["pre_sf"] is None else call["pre_sf"].reshape(1, -1, 1)
+        isf = None if call["identity_sf"] is None else call["identity_sf"].reshape(1, -1, 1)
+        out, s, codes = O.act_forward_per_channel(act, call["x"], pre, call["identity"], isf)
+        assert np.array_equal(s, call["scale"])
+        assert np.array_equal(codes, call["codes"])
+        assert np.array_equal(out, call["out"])
+        assert np.array_equal(act.x_min, call["x_min"]) and np.array_equal(act.x_max, call["x_max"])
+
+
+@pytest.mark.parametrize("case", [c for c in EXTRA if c["kind"] == "linear"], ids=lambda c: c["tag"])
+def test_quant_linear(case):
+    y, s_out, acc, w_int, b_int = O.linear_forward(case["weight"], case["bias"], case["weight_bit"], case["in_codes"],
+                                                   case["s_x"].reshape(()))
+    assert np.array_equal(w_int, case["weight_integer"])
+    assert np.array_equal(b_int.astype(np.float64), case["bias_integer"])
+    assert np.array_equal(s_out, case["out_scale"])
+    assert np.abs(acc).max() < 2 ** 24          # the float32 F.linear of the reference is exact here
+    assert np.array_equal(acc, case["acc"])
+    assert np.allclose(y, case["out"], rtol=0, atol=1e-6 * np.abs(case["out"]).max())
+
+
+def test_quant_linear_per_row_intent():
+    """per_channel=True (per-row weight ranges): the reference cannot run this branch (see gen_golden_extra.py);
+    the oracle's intent restatement must reduce to the global case when all rows share one range."""
+    rng = np.random.default_rng(3)
+    w = rng.normal(size=(12, 20)).astype(np.float32) * 0.1
+    w[:, 0], w[:, 1] = 0.5, -0.5                 # every row has the same extrema
+    codes = rng.integers(-128, 128, size=(9, 20))
+    a = O.linear_forward(w, None, 8, codes, np.float32(0.02), per_channel=False)
+    b = O.linear_forward(w, None, 8, codes, np.float32(0.02), per_channel=True)
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[0], b[0])
+    w[3] *= 0.25                                  # a row with its own range gets its own scale
+    c = O.linear_forward(w, None, 8, codes, np.float32(0.02), per_channel=True)
+    assert c[1][3] == np.float32(np.float32(0.125 / 127) * np.float32(0.02)) and np.abs(c[3][3]).max() == 127
+
+
+@pytest.mark.parametrize("case", [c for c in EXTRA if c["kind"] == "conv_unfixed_bn"], ids=lambda c: c["tag"])
+def test_quant_conv_unfixed_bn(case):
+    bn = {k: (np.array(v) if isinstance(v, np.ndarray) else v) for k, v in case["bn"].items()}
+    conv = dict(weight=case["weight"], bias=None, bn=None, stride=1, pad=case["pad"], dil=1, groups=case["groups"],
+                weight_bit=8)
+    for call in case["calls"]:
+        out, sf = O.conv_forward_unfixed_bn(conv, bn, call["in_codes"], call["s_x"].reshape(()))
+        # float statistics (mean / unbiased variance, sqrt): 1e-5 relative, the tolerance of the float outputs
+        assert np.allclose(bn["mean"], call["mean"], rtol=1e-5, atol=1e-6)
+        assert np.allclose(bn["var"], call["var"], rtol=1e-5, atol=1e-6)
+        assert np.allclose(sf.reshape(-1), call["out_scale"], rtol=1e-5, atol=0)
+        assert np.abs(out - call["out"]).max() <= 1e-5 * np.abs(call["out"]).max()
