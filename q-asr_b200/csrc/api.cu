@@ -17,6 +17,12 @@ extern "C" int qasr_debug_set(int key, long long value) {
   return QASR_OK;
 }
 long long qasr_debug_get(int key) { return key >= 0 && key < 16 ? g_dbg[key] : -1; }
+// how many bring-up knobs are set: bench.py refuses to time the kernels unless this is 0
+extern "C" int qasr_debug_knobs_set(void) {
+  int n = 0;
+  for (int i = 0; i < 16; ++i) n += g_dbg[i] != -1;
+  return n;
+}
 
 void qasr_set_error(const char* fmt, ...) {
   va_list ap;

@@ -81,9 +81,11 @@ _SIGS = {
     "qasr_normalize_features_f32": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "qasr_ctc_collapse": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
     "qasr_debug_set": (C.c_int, [C.c_int, C.c_longlong]),
+    "qasr_debug_knobs_set": (C.c_int, []),
 }
 
-EXPORTED_SYMBOLS = [s for s in _SIGS if s != "qasr_debug_set"]
+# bring-up hooks are not part of include/qasr.h
+EXPORTED_SYMBOLS = [s for s in _SIGS if s not in ("qasr_debug_set", "qasr_debug_knobs_set")]
 
 
 def load_library():
