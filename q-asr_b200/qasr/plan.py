@@ -615,7 +615,7 @@ def bucket_frames(T):
     (jasper.py:177-181) and the conv's own padding is zeros too, so every output frame below the unpadded T' is
     bit-identical to an unbucketed run; ragged evaluation sets then share a handful of plans instead of compiling
     one per distinct length."""
-    step = 128 if T <= 1024 else 256
+    step = 32 if T <= 512 else (64 if T <= 2048 else 256)
     return (int(T) + step - 1) // step * step
 
 
