@@ -70,8 +70,21 @@ enum {
   QASR_EPI_REQUANT_I8 = 0, /* int8/uint8 codes out                                     */
   QASR_EPI_DEQUANT_F32 = 1,/* y = f32(acc+bias) * s_out[c] (+relu): the module-level
                               QuantConv1d return value, quant_modules.py:307-309       */
-  QASR_EPI_RAW_I32 = 2     /* acc + bias as int32 (dynamic / calibration passes)       */
+  QASR_EPI_RAW_I32 = 2,    /* acc + bias as int32 (dynamic / calibration passes)       */
+  QASR_EPI_STATS = 3       /* no tensor is written: the STATISTICS pass of dynamic quantisation
+                              (quant_modules.py:149-156).  `out` is a per-channel record table
+                              qasr_stats[C_out], updated with atomics:
+                                one operand : min / max of acc + bias over the counted frames (int64)
+                                two operands: min / max of f32(acc1+b1)*s1 + f32(acc0+b0)*s0, the x_act of
+                                              res_act (quant_modules.py:108), as order-preserving uint32
+                              frames t >= out_lens[b] are not counted when QASR_F_MASK is set     */
 };
+
+/* One record per output channel of a QASR_EPI_STATS pass.  Reset state: lo = INT64_MAX, hi = INT64_MIN
+ * (one operand) or lo32 = 0xffffffff, hi32 = 0 (two operands, float keys: bits ^ sign-dependent mask). */
+typedef struct {
+  int64_t lo, hi;
+} qasr_stats;
 
 /* flags */
 #define QASR_F_RELU0      1   /* ReLU between conv 0 and the activation quantiser          */
@@ -86,6 +99,10 @@ enum {
 #define QASR_F_B_SIGNED   64  /* conv-0 input codes are signed (else unsigned)              */
 #define QASR_F_B1_SIGNED  128 /* conv-1 (residual branch) input codes are signed            */
 #define QASR_F_BIAS64     256 /* add the bias in 64-bit (|b_int| close to 2^31)             */
+#define QASR_F_DEVICE_TABLES 1024 /* ch0 / ch1 are written by preceding work on the same stream (dynamic
+                                 quantisation: scales exist on the device only): the kernel is launched
+                                 WITHOUT programmatic dependent launch, so it starts after its predecessor
+                                 has completed and its pre-wait prologue may read the tables            */
 #define QASR_F_FAST_F32   512 /* single-operand REQUANT only: the host proved that
                                  clamp(rint(f32(acc+bias) * f32(m*2^-e))), one float FMA
                                  with a single rounding, equals the dyadic result for every
@@ -250,6 +267,83 @@ int64_t qasr_quantile_workspace_bytes(void);
 int qasr_quantile2_f32(const float* x, const float* identity, int32_t ld, int32_t B, int32_t C,
                        int32_t T, const int32_t* lens, float q_lo, float q_hi, float* out2,
                        void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K4b  dynamic quantisation on the device (quant_modules.py:149-167 with running ranges off): the range of
+ *      every QuantAct is a function of the batch, so scales, dyadic multipliers and integer biases exist on
+ *      the device only and the whole forward stays one CUDA graph.  Per conv -> consumer QuantAct:
+ *        1. qasr_conv* with QASR_EPI_STATS        per-channel extremes of the integer accumulators
+ *        2. qasr_dyn_select                        which channels can hold max |y| (rigorous float bounds)
+ *        3. qasr_dyn_refine                        those channels again, position by position, WITH the float
+ *                                                  noise of the reference's un-rounded x / s (quant_modules.py:301):
+ *                                                  the exact max |y| the reference's x.min() / x.max() see
+ *        4. qasr_dyn_finalize                      range -> scale (quant_utils.py:47-52) -> (m, e) of the producers
+ *                                                  (quant_utils.py:188-193, 121-147) -> s_out / b_int of the
+ *                                                  consumer convs (quant_modules.py:293-297)
+ *        5. qasr_conv* with QASR_EPI_REQUANT_I8 | QASR_F_DEVICE_TABLES
+ *      Only max(|x_min|, |x_max|) enters the scale, so one extreme is tracked: absmax = max |x_act|.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  const void*   x;        /* [B][C_in][x_ld] input codes of the conv                                  */
+  const int8_t* w;        /* RAW int8 weights [C_out][C_in / groups][k] (not the packed layouts)       */
+  const float*  s_x;      /* device scalar: scale of the input codes                                   */
+  const qasr_chan* ch;    /* [C_out] table holding s_out and bias                                      */
+  const int32_t* wabs;    /* [C_out] sum of |w| per output channel                                     */
+  int32_t x_ld, C_in, T_in, k, stride, dilation, pad;
+  int32_t depthwise;      /* groups == C_in == C_out                                                   */
+  int32_t in_unsigned;    /* input codes are unsigned                                                  */
+} qasr_dyn_operand;
+
+#define QASR_DYN_MAX_CAND 4
+/* cand[0..3] = candidate channels (-1 = none), cand[4] = how many channels qualified (> 4: refused, the caller
+ * checks it after the forward).  Resets `stats` to its initial state. */
+int qasr_dyn_select(qasr_stats* stats, const qasr_dyn_operand* op0, const qasr_dyn_operand* op1, int32_t relu,
+                    int32_t C_out, int32_t* cand, void* stream);
+/* absmax_bits: uint32 bit pattern of a non-negative float, updated with atomicMax (reset value 0). */
+int qasr_dyn_refine(const qasr_dyn_operand* op0, const qasr_dyn_operand* op1, int32_t relu, const int32_t* out_lens,
+                    int32_t B, int32_t C_out, int32_t T_out, const int32_t* cand, uint32_t* absmax_bits, void* stream);
+
+typedef struct {
+  int32_t src_kind;          /* 0: *src = absmax bits (uint32, reset to 0 after reading)
+                                1: src = float[2] (min, max) of a float tensor (qasr_minmax_f32)
+                                2: src = int32[2] (min, max) of int8 codes (qasr_minmax_i8, reset after reading),
+                                   times *src_scale                                                       */
+  void* src;
+  const float* src_scale;
+  int32_t n_levels;          /* 2^(activation_bit - 1) - 1                                                */
+  float* act_scale;          /* out: the QuantAct's scale                                                 */
+  int32_t n_prod;            /* producer conv tables whose (m, e) = dyadic(s_out[c] / scale) are written  */
+  qasr_chan* prod[2];
+  int32_t prod_C[2];
+  const float* prev_scale;   /* optional scalar producer (int8 codes with scale *prev_scale) ...          */
+  int32_t* prev_me;          /* ... (m, e) written here (qasr_requant_i8_dev)                              */
+  int32_t n_cons;            /* consumer conv tables whose s_out = s_w[c] * scale and bias are written    */
+  qasr_chan* cons[2];
+  const float* cons_sw[2];
+  const float* cons_bias[2]; /* folded float bias [C] or NULL                                             */
+  int32_t cons_C[2];
+  /* data parallelism: exchange of absmax between the ranks of one node (NULL / 0: single rank)          */
+  uint64_t* const* peer_slots;   /* device array [world]: every rank's slot table (peer-mapped)           */
+  int32_t rank, world, slot;
+  uint32_t* seq;                 /* device counter of this finalize node                                  */
+} qasr_dyn_finalize_args;
+int qasr_dyn_finalize(const qasr_dyn_finalize_args* a, void* stream);
+
+/* min / max of int8 codes after the block ReLU and length mask (the float tensor relu(q * s) the next
+ * QuantAct sees, jasper.py:687 + :177-181): out2 int32 (min, max), updated with atomics (reset: INT32_MAX, INT32_MIN). */
+int qasr_minmax_i8(const int8_t* codes, int32_t ld, int32_t relu, int32_t B, int32_t C, int32_t T,
+                   const int32_t* lens, int32_t* out2, void* stream);
+/* qasr_requant_i8 with the dyadic (m, e) read from device memory and an optional ReLU in front. */
+int qasr_requant_i8_dev(const int8_t* in, int32_t in_ld, int32_t relu, const int32_t* me, int32_t qmin,
+                        int32_t qmax, int8_t* out, int32_t out_ld, int32_t B, int32_t C, int32_t T,
+                        const int32_t* lens, void* stream);
+
+/* peer-memory plumbing of the range exchange: a device buffer that other processes of the node can map.
+ * handle_out: 64 bytes (cudaIpcMemHandle_t).  qasr_comm_open maps a peer's buffer, qasr_comm_close unmaps. */
+int qasr_comm_alloc(int64_t bytes, void** ptr, void* handle_out);
+int qasr_comm_open(const void* handle, void** ptr);
+int qasr_comm_close(void* ptr);
+int qasr_comm_free(void* ptr);
 
 /* ------------------------------------------------------------------------------------
  * K5  decoder tail: greedy CTC labels from integer logits

@@ -24,6 +24,10 @@ extern "C" int qasr_debug_knobs_set(void) {
   return n;
 }
 
+namespace { thread_local bool g_plain_launch = false; }
+void qasr_set_plain_launch(bool plain) { g_plain_launch = plain; }
+bool qasr_plain_launch() { return g_plain_launch; }
+
 void qasr_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -47,7 +51,7 @@ extern "C" int qasr_sm_count(void) {
 }
 
 int qasr_validate_epilogue(const qasr_epilogue* e, bool allow_second_operand) {
-  QASR_CHECK_ARG(e->mode >= QASR_EPI_REQUANT_I8 && e->mode <= QASR_EPI_RAW_I32, "epilogue: unknown mode %d", e->mode);
+  QASR_CHECK_ARG(e->mode >= QASR_EPI_REQUANT_I8 && e->mode <= QASR_EPI_STATS, "epilogue: unknown mode %d", e->mode);
   QASR_CHECK_ARG(e->ch0 != nullptr && qasr_aligned16(e->ch0), "epilogue: ch0 missing or not 16-byte aligned");
   QASR_CHECK_ARG(allow_second_operand || e->ch1 == nullptr, "epilogue: this kernel takes one conv operand");
   QASR_CHECK_ARG(e->ch1 == nullptr || qasr_aligned16(e->ch1), "epilogue: ch1 not 16-byte aligned");
@@ -66,6 +70,9 @@ int qasr_validate_epilogue(const qasr_epilogue* e, bool allow_second_operand) {
     QASR_CHECK_ARG(!s2 || (e->e2 >= 1 && e->e2 <= 62 && e->m2 > 0), "epilogue: stage-2 dyadic (m2=%d, e2=%d)", e->m2, e->e2);
     QASR_CHECK_ARG(!(e->flags & QASR_F_MASK) || e->out_lens != nullptr, "epilogue: MASK needs out_lens");
     QASR_CHECK_ARG(e->prev == nullptr || (e->prev_ld % 16 == 0 && qasr_aligned16(e->prev)), "epilogue: prev pitch/alignment");
+  } else if (e->mode == QASR_EPI_STATS) {
+    QASR_CHECK_ARG(e->prev == nullptr, "epilogue: STATS takes conv operands only");
+    QASR_CHECK_ARG(!(e->flags & QASR_F_MASK) || e->out_lens != nullptr, "epilogue: MASK needs out_lens");
   } else {
     QASR_CHECK_ARG(e->ch1 == nullptr && e->prev == nullptr, "epilogue: residual operands need REQUANT mode");
   }

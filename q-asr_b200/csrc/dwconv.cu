@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
   const uint8_t* x_next = xbase + (size_t)(kBufs - 1) * xstep;       // row r + kBufs - 1
   int buf = 0, nb = kBufs - 1;
   uint32_t par = 0;
+  long long st_lo = 0x7fffffffffffffffLL, st_hi = -0x7fffffffffffffffLL - 1;   // QASR_EPI_STATS: this lane's extremes
   for (int r = 0; r < nrows; ++r, out_row += out_row_step, x_next += xstep) {
     // keep kBufs-1 rows in flight: the buffer being refilled was consumed in iteration r-1
     if (lane == 0 && r + kBufs - 1 < nrows) {
@@ -217,6 +218,17 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
             word &= nvalid <= 0 ? 0u : (0xffffffffu >> (8 * (4 - nvalid)));
           }
           if ((tl >> 2) < out_words) orow_w[t0 >> 2] = word;
+        }
+      } else if (a.ep.mode == QASR_EPI_STATS) {
+        // statistics pass of dynamic quantisation: extremes of acc + bias over the counted frames of this channel
+        const int offs[4] = {o0, o1, o2, o3};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (t0 + offs[i] < len) {
+            const long long z = qasr_acc_bias64(acc[i], c0.bias);
+            st_lo = z < st_lo ? z : st_lo;
+            st_hi = z > st_hi ? z : st_hi;
+          }
         }
       } else if (a.ep.mode == QASR_EPI_DEQUANT_F32) {
         float* orow = reinterpret_cast<float*>(out_row);
@@ -301,6 +313,19 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
     };
     if (EK == 3 || (EK == 0 && f32_path)) tiles(std::true_type{}); else tiles(std::false_type{});
     __syncwarp();  // every lane is done reading this buffer before lane 0 refills it
+  }
+  if (EK == 2 && a.ep.mode == QASR_EPI_STATS) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const long long l2 = __shfl_xor_sync(0xffffffffu, st_lo, o), h2 = __shfl_xor_sync(0xffffffffu, st_hi, o);
+      st_lo = l2 < st_lo ? l2 : st_lo;
+      st_hi = h2 > st_hi ? h2 : st_hi;
+    }
+    if (lane == 0 && st_hi >= st_lo) {
+      qasr_stats* st = reinterpret_cast<qasr_stats*>(a.out) + c;
+      atomicMin(reinterpret_cast<long long*>(&st->lo), st_lo);
+      atomicMax(reinterpret_cast<long long*>(&st->hi), st_hi);
+    }
   }
 }
 
@@ -417,6 +442,7 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
   QASR_CHECK_ARG(epi->mode != QASR_EPI_REQUANT_I8 || out_ld % 16 == 0, "dwconv: out pitch % 16");
   int rc = qasr_validate_epilogue(epi, false);
   if (rc) return rc;
+  qasr_set_plain_launch((epi->flags & QASR_F_DEVICE_TABLES) != 0);
 
   // engine choice (tools/dw_bench.py, batch 64 x 800 frames x 512 channels, float epilogue): IMMA 16.6 / 18.3 / 30.9 us
   // for k = 33 / 75 / 87-dilated against 21.8 / 23.7 / 27.5 us on tcgen05 with TMA-fetched windows (its input
@@ -433,6 +459,13 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
   // 6 K steps (k = 87 dilated): the lanes' 8-byte fragment loads are 12 words apart and collide on banks
   // (30.9 us against 27.5 us on tcgen05, 512 channels, batch 64 x 800 frames)
   if (knob < 0 && tc_ok && dw_ksteps(k, stride, dilation, pad) >= 6) use_tc = true;
+  if (epi->mode == QASR_EPI_STATS) {   // the statistics epilogue lives in the IMMA engine
+    if (table_bytes == 0) {
+      qasr_set_error("dwconv: STATS pass needs the IMMA engine (tap window of k=%d dilation=%d exceeds 6 x 32)", k, dilation);
+      return QASR_ERR_UNSUPPORTED;
+    }
+    use_tc = false;
+  }
   if (use_tc) {
     if (!tc_ok) {
       qasr_set_error("dwconv: tap span (k=%d, dilation=%d, stride=%d) exceeds both kernels' windows", k, dilation, stride);

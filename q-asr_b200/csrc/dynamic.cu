@@ -1,0 +1,546 @@
+// K4b: dynamic quantisation on the device (reference QuantAct.forward with dynamic=True,
+// nemo/quantization/utils/quant_modules.py:149-167).  The range of every QuantAct is min / max of the float tensor
+// it receives, i.e. of the producing conv's output y = f32(acc + b + delta) * s_out[c] (quant_modules.py:301-309),
+// where delta = sum w * eps(q) is the float noise of the reference's un-rounded x_int = x / s_x (:301).  Only
+// max(|min|, |max|) enters the scale (quant_utils.py:47-52), so one number per QuantAct is needed EXACTLY:
+// absmax = max |x_act|.  The statistics pass of the conv kernels (QASR_EPI_STATS) leaves per-channel extremes of the
+// noise-free integer accumulators; here
+//   dyn_select   bounds every channel's max |y| from both sides (|delta| <= sum|w| * max|eps|) and lists the
+//                channels that can hold the global maximum (almost always one),
+//   dyn_refine   recomputes those channels position by position with the noise term, bit for bit as the
+//                reference's float64 conv + float32 rescale does, and reduces the exact absmax,
+//   dyn_finalize turns absmax (optionally exchanged between the ranks of a data-parallel job through peer memory)
+//                into the scale, the producers' dyadic multipliers and the consumers' s_out / integer bias,
+// so no scale ever visits the host and the whole dynamic forward replays as one CUDA graph.
+#include <float.h>
+
+#include "qasr_common.cuh"
+
+namespace {
+
+constexpr int kSelThreads = 256;
+constexpr int kRefThreads = 128;
+constexpr int kMaxWRow = 8192;   // weights of one output channel kept in shared memory by dyn_refine
+
+struct DynOp {   // by-value kernel copy of qasr_dyn_operand
+  const uint8_t* x;
+  const int8_t* w;
+  const float* s_x;
+  const qasr_chan* ch;
+  const int32_t* wabs;
+  int x_ld, C_in, T_in, k, stride, dil, pad, depthwise, in_unsigned;
+};
+
+DynOp make_op(const qasr_dyn_operand* o) {
+  DynOp d;
+  memset(&d, 0, sizeof(d));
+  if (o) {
+    d.x = static_cast<const uint8_t*>(o->x);
+    d.w = o->w;
+    d.s_x = o->s_x;
+    d.ch = o->ch;
+    d.wabs = o->wabs;
+    d.x_ld = o->x_ld; d.C_in = o->C_in; d.T_in = o->T_in; d.k = o->k; d.stride = o->stride; d.dil = o->dilation;
+    d.pad = o->pad; d.depthwise = o->depthwise; d.in_unsigned = o->in_unsigned;
+  }
+  return d;
+}
+
+// eps(q) * 2^22 of the reference's x_int = (f32(q) * s) / s  (quant_modules.py:301): a small integer, |.| <= 64
+__device__ __forceinline__ int noise_code(int q, float s) {
+  const float r = __fdiv_rn(__fmul_rn((float)q, s), s);
+  return (int)rint(((double)r - (double)q) * 4194304.0);
+}
+
+__device__ __forceinline__ float block_max(float v, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, sh[w]);
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// select
+// ---------------------------------------------------------------------------------------------
+__global__ void dyn_select_kernel(qasr_stats* stats, const DynOp op0, const DynOp op1, int dual, int relu, int C,
+                                  int32_t* cand) {
+  __shared__ float sh[kSelThreads / 32];
+  __shared__ int s_count;
+  __shared__ int s_list[QASR_DYN_MAX_CAND];
+  const int tid = threadIdx.x;
+  // largest |eps| * 2^22 over the 256 codes of each operand's input scale
+  const float s0 = op0.s_x[0];
+  const int q0 = op0.in_unsigned ? tid : (int)(int8_t)tid;
+  const float emax0 = block_max((float)abs(noise_code(q0, s0)), sh) * (1.0f / 4194304.0f);
+  float emax1 = 0.0f;
+  if (dual) {
+    const float s1 = op1.s_x[0];
+    const int q1 = op1.in_unsigned ? tid : (int)(int8_t)tid;
+    emax1 = block_max((float)abs(noise_code(q1, s1)), sh) * (1.0f / 4194304.0f);
+  }
+  if (tid == 0) s_count = 0;
+  // per-channel bounds  L_c <= max_t |y| <= U_c
+  float lmax = 0.0f;
+  for (int c = tid; c < C; c += kSelThreads) {
+    float U = 0.0f, L = 0.0f;
+    if (!dual) {
+      const long long lo = stats[c].lo, hi = stats[c].hi;
+      if (hi >= lo) {
+        const double d = (double)op0.wabs[c] * (double)emax0;     // |delta| <= sum|w| * max|eps|
+        const float sc = __int_as_float(((const int*)(op0.ch + c))[0]);
+        double a_hi, a_lo;
+        if (relu) {
+          a_hi = fmax((double)hi + d, 0.0);
+          a_lo = fmax((double)hi - d, 0.0);
+        } else {
+          const double a = fmax(fabs((double)lo), fabs((double)hi));
+          a_hi = a + d;
+          a_lo = fmax(a - d, 0.0);
+        }
+        U = __fmul_rn(__double2float_ru(a_hi), sc);    // f32(.) and * s are monotone
+        L = __fmul_rn(__double2float_rd(a_lo), sc);
+      }
+    } else {
+      const unsigned klo = reinterpret_cast<const unsigned*>(&stats[c].lo)[0];
+      const unsigned khi = reinterpret_cast<const unsigned*>(&stats[c].hi)[0];
+      if (khi >= klo) {
+        const float a = fmaxf(fabsf(qasr_key_f32(klo)), fabsf(qasr_key_f32(khi)));
+        const float sc0 = __int_as_float(((const int*)(op0.ch + c))[0]);
+        const float sc1 = __int_as_float(((const int*)(op1.ch + c))[0]);
+        // |v - v^|: each operand's float differs by at most (|delta_i| + ulp(A_i) / 2) * s_i plus the rounding of the
+        // product, the sum adds one more rounding.  With |A_i| <= sum|w| * 255 + |b_i| =: Amax_i and Y_i = Amax_i * s_i:
+        //   |v - v^| <= 2 (d0 s0 + d1 s1) + (2^-23 + 2^-21) (Y0 + Y1)        (generous constants)
+        const double y0 = ((double)op0.wabs[c] * 255.0 + fabs((double)op0.ch[c].bias)) * sc0;
+        const double y1 = ((double)op1.wabs[c] * 255.0 + fabs((double)op1.ch[c].bias)) * sc1;
+        const double e = 2.0 * ((double)op0.wabs[c] * emax0 * sc0 + (double)op1.wabs[c] * emax1 * sc1) +
+                         (1.1920929e-7 + 4.76837158e-7) * (y0 + y1);
+        U = __double2float_ru((double)a + e);
+        L = __double2float_rd(fmax((double)a - e, 0.0));
+      }
+    }
+    // park the bounds in the record (it is reset below, after the second sweep)
+    reinterpret_cast<float*>(&stats[c].lo)[1] = U;
+    reinterpret_cast<float*>(&stats[c].hi)[1] = L;
+    lmax = fmaxf(lmax, L);
+  }
+  const float lstar = block_max(lmax, sh);
+  for (int c = tid; c < C; c += kSelThreads) {
+    const float U = reinterpret_cast<const float*>(&stats[c].lo)[1];
+    if (U > 0.0f && U >= lstar) {
+      const int slot = atomicAdd(&s_count, 1);
+      if (slot < QASR_DYN_MAX_CAND) s_list[slot] = c;
+    }
+    // reset for the next forward
+    if (!dual) {
+      stats[c].lo = 0x7fffffffffffffffLL;
+      stats[c].hi = -0x7fffffffffffffffLL - 1;
+    } else {
+      stats[c].lo = 0xffffffffLL;
+      stats[c].hi = 0;
+    }
+  }
+  __syncthreads();
+  if (tid < QASR_DYN_MAX_CAND) cand[tid] = tid < s_count ? s_list[tid] : -1;
+  if (tid == 0) cand[QASR_DYN_MAX_CAND] = s_count;
+}
+
+// ---------------------------------------------------------------------------------------------
+// refine: one candidate channel per blockIdx.y, one output position per thread
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void refine_operand(const DynOp& op, const int8_t* wrow, const int8_t* lut, int c, int b,
+                                               int t, bool valid, int C_out, long long& acc, long long& dacc) {
+  acc = 0;
+  dacc = 0;
+  if (!valid) return;
+  const int tin0 = t * op.stride - op.pad;
+  if (op.depthwise) {
+    const uint8_t* row = op.x + ((size_t)b * op.C_in + c) * op.x_ld;
+    for (int j = 0; j < op.k; ++j) {
+      const int ti = tin0 + j * op.dil;
+      if (ti >= 0 && ti < op.T_in) {
+        const unsigned code = row[ti];
+        const int q = op.in_unsigned ? (int)code : (int)(int8_t)code;
+        const int w = wrow[j];
+        acc += w * q;
+        dacc += w * (int)lut[code];
+      }
+    }
+  } else {
+    for (int ci = 0; ci < op.C_in; ++ci) {
+      const uint8_t* row = op.x + ((size_t)b * op.C_in + ci) * op.x_ld;
+      for (int j = 0; j < op.k; ++j) {
+        const int ti = tin0 + j * op.dil;
+        if (ti >= 0 && ti < op.T_in) {
+          const unsigned code = row[ti];
+          const int q = op.in_unsigned ? (int)code : (int)(int8_t)code;
+          const int w = wrow[ci * op.k + j];
+          acc += w * q;
+          dacc += w * (int)lut[code];
+        }
+      }
+    }
+  }
+}
+
+__global__ void dyn_refine_kernel(const DynOp op0, const DynOp op1, int dual, int relu, const int32_t* out_lens, int B,
+                                  int C_out, int T_out, const int32_t* cand, uint32_t* absmax_bits) {
+  extern __shared__ int8_t wsm[];    // [2][wrow_len]
+  __shared__ int8_t lut[2][256];
+  __shared__ float sh[kRefThreads / 32];
+  const int c = cand[blockIdx.y];
+  if (c < 0) return;
+  const int tid = threadIdx.x;
+  const int n0 = op0.depthwise ? op0.k : op0.C_in * op0.k;
+  const int n1 = dual ? (op1.depthwise ? op1.k : op1.C_in * op1.k) : 0;
+  for (int i = tid; i < n0; i += kRefThreads) wsm[i] = op0.w[(size_t)c * n0 + i];
+  for (int i = tid; i < n1; i += kRefThreads) wsm[n0 + i] = op1.w[(size_t)c * n1 + i];
+  for (int i = tid; i < 256; i += kRefThreads) {
+    lut[0][i] = (int8_t)noise_code(op0.in_unsigned ? i : (int)(int8_t)i, op0.s_x[0]);
+    lut[1][i] = dual ? (int8_t)noise_code(op1.in_unsigned ? i : (int)(int8_t)i, op1.s_x[0]) : 0;
+  }
+  __syncthreads();
+  const qasr_chan p0 = op0.ch[c];
+  qasr_chan p1 = p0;
+  if (dual) p1 = op1.ch[c];
+  float best = 0.0f;
+  const long long total = (long long)B * T_out;
+  for (long long pos = blockIdx.x * (long long)kRefThreads + tid; pos < total; pos += (long long)gridDim.x * kRefThreads) {
+    const int b = (int)(pos / T_out), t = (int)(pos - (long long)b * T_out);
+    const bool valid = !out_lens || t < out_lens[b];
+    long long acc, dacc;
+    refine_operand(op0, wsm, lut[0], c, b, t, valid, C_out, acc, dacc);
+    if (!valid) continue;
+    // f32(f64(acc) + bias + delta) * s_out  (quant_modules.py:305-307; .type(torch.float) of the float64 conv)
+    const long long b0 = p0.bias == 2147483647 ? 2147483648LL : (long long)p0.bias;
+    float y = __fmul_rn((float)((double)(acc + b0) + (double)dacc * (1.0 / 4194304.0)), p0.s_out);
+    if (dual) {
+      long long acc1, dacc1;
+      refine_operand(op1, wsm + n0, lut[1], c, b, t, true, C_out, acc1, dacc1);
+      const long long b1 = p1.bias == 2147483647 ? 2147483648LL : (long long)p1.bias;
+      const float y1 = __fmul_rn((float)((double)(acc1 + b1) + (double)dacc1 * (1.0 / 4194304.0)), p1.s_out);
+      y = __fadd_rn(y1, y);                       // identity + x, quant_modules.py:108
+    } else if (relu) {
+      y = fmaxf(y, 0.0f);                         // jasper.py:661 / :687
+    }
+    best = fmaxf(best, fabsf(y));
+  }
+  best = block_max(best, sh);
+  if (tid == 0 && best > 0.0f) atomicMax(absmax_bits, __float_as_uint(best));
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dyadic_dev(float pre, float zsf, int& m, int& e) {   // batch_frexp, quant_utils.py:121-147
+  const double r = (double)pre / (double)zsf;
+  int ex;
+  const double mant = frexp(r, &ex);
+  long long mm = (long long)floor(mant * 2147483648.0 + 0.5);
+  int ee = 31 - ex;
+  if (mm >= 2147483648LL) { mm >>= 1; ee -= 1; }
+  if (!(r > 0.0) || !isfinite(r)) { mm = 0; ee = 1; }
+  m = (int)mm;
+  e = ee;
+}
+
+struct DynFin {
+  int src_kind;
+  void* src;
+  const float* src_scale;
+  int n_levels;
+  float* act_scale;
+  int n_prod;
+  qasr_chan* prod[2];
+  int prod_C[2];
+  const float* prev_scale;
+  int32_t* prev_me;
+  int n_cons;
+  qasr_chan* cons[2];
+  const float* cons_sw[2];
+  const float* cons_bias[2];
+  int cons_C[2];
+  unsigned long long* const* peer_slots;
+  int rank, world, slot;
+  uint32_t* seq;
+};
+
+__global__ void dyn_finalize_kernel(const DynFin a) {
+  __shared__ float s_scale;
+  if (threadIdx.x == 0) {
+    float absmax;
+    if (a.src_kind == 0) {
+      uint32_t* p = static_cast<uint32_t*>(a.src);
+      absmax = __uint_as_float(*p);
+      *p = 0u;
+    } else if (a.src_kind == 1) {
+      const float* p = static_cast<const float*>(a.src);
+      absmax = fmaxf(fabsf(p[0]), fabsf(p[1]));
+    } else {
+      int32_t* p = static_cast<int32_t*>(a.src);
+      const int lo = p[0], hi = p[1];
+      absmax = hi >= lo ? fmaxf(fabsf(__fmul_rn((float)lo, a.src_scale[0])), fabsf(__fmul_rn((float)hi, a.src_scale[0]))) : 0.0f;
+      p[0] = 2147483647;
+      p[1] = -2147483647 - 1;
+    }
+    if (a.world > 1) {
+      // one-shot all-reduce(MAX) over peer memory: write (sequence, value) into this rank's slot of EVERY rank's
+      // table, then wait until all ranks' entries of this sequence number have arrived here.  A rank can run ahead
+      // of a peer by less than one forward (every exchange waits for all ranks), so the sequence number in the
+      // entry tells this forward's value from the previous one.
+      const uint32_t seq = ++(*a.seq);
+      const unsigned long long word = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(absmax);
+      for (int r = 0; r < a.world; ++r) {
+        unsigned long long* dst = a.peer_slots[r] + (size_t)a.slot * a.world + a.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+      }
+      const unsigned long long* mine = a.peer_slots[a.rank] + (size_t)a.slot * a.world;
+      for (int r = 0; r < a.world; ++r) {
+        unsigned long long v;
+        unsigned spin = 0;
+        do {
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + r) : "memory");
+          if (++spin > (1u << 28)) __trap();   // a lost peer must not hang the GPU
+        } while ((uint32_t)(v >> 32) != seq);
+        absmax = fmaxf(absmax, __uint_as_float((uint32_t)v));
+      }
+    }
+    // symmetric_linear_quantization_params, quant_utils.py:51-52: clamp(max(|min|, |max|), 1e-8) / n
+    const float s = __fdiv_rn(fmaxf(absmax, 1e-8f), (float)a.n_levels);
+    a.act_scale[0] = s;
+    s_scale = s;
+    if (a.prev_me != nullptr) {
+      int m, e;
+      dyadic_dev(a.prev_scale[0], s, m, e);
+      a.prev_me[0] = m;
+      a.prev_me[1] = e;
+    }
+  }
+  __syncthreads();
+  const float s = s_scale;
+  for (int i = 0; i < a.n_prod; ++i) {
+    for (int c = threadIdx.x; c < a.prod_C[i]; c += blockDim.x) {
+      int m, e;
+      dyadic_dev(a.prod[i][c].s_out, s, m, e);
+      a.prod[i][c].m = m;
+      a.prod[i][c].e = e;
+    }
+  }
+  for (int i = 0; i < a.n_cons; ++i) {
+    for (int c = threadIdx.x; c < a.cons_C[i]; c += blockDim.x) {
+      const float so = __fmul_rn(a.cons_sw[i][c], s);                          // quant_modules.py:293
+      int bias = 0;
+      if (a.cons_bias[i] != nullptr) {
+        // SymmetricQuantFunction(bias, 32, s_out), float32: clamp(rne((1 / s_out) * b), -(2^31 - 1), 2^31 - 2), both
+        // bounds rounding to +-2^31 in float32 (quant_modules.py:296-297, quant_utils.py:74-76)
+        float q = rintf(__fmul_rn(__fdiv_rn(1.0f, so), a.cons_bias[i][c]));
+        q = fminf(fmaxf(q, -2147483648.0f), 2147483648.0f);
+        bias = q >= 2147483648.0f ? 2147483647 : (int)q;                       // INT32_MAX = sentinel of 2^31
+      }
+      a.cons[i][c].s_out = so;
+      a.cons[i][c].bias = bias;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// int8 statistics / requantisation of the block outputs
+// ---------------------------------------------------------------------------------------------
+__global__ void minmax_i8_kernel(const int8_t* __restrict__ codes, int ld, int relu, int B, int C, int T,
+                                 const int32_t* lens, int32_t* out2) {
+  int lo = 2147483647, hi = -2147483647 - 1;
+  const int tq = (T + 15) / 16;
+  const long long total = (long long)B * C * tq;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % tq);
+    const long long row = i / tq;
+    const int b = (int)(row / C);
+    const int len = lens ? min(lens[b], T) : T;
+    const uint4 v = *reinterpret_cast<const uint4*>(codes + row * ld + 16 * j);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = 16 * j + 4 * g + u;
+        if (t < T) {
+          int q = t < len ? (int)(int8_t)((w[g] >> (8 * u)) & 0xff) : 0;     // masked frames count as 0 (jasper.py:177-181)
+          if (relu) q = max(q, 0);
+          lo = min(lo, q);
+          hi = max(hi, q);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0 && hi >= lo) {
+    atomicMin(out2, lo);
+    atomicMax(out2 + 1, hi);
+  }
+}
+
+__global__ void requant_i8_dev_kernel(const int8_t* __restrict__ in, int in_ld, int relu, const int32_t* me, int qmin,
+                                      int qmax, int8_t* out, int out_ld, int B, int C, int T, const int32_t* lens) {
+  __shared__ int8_t lut[256];
+  {
+    int code = (int)(int8_t)threadIdx.x;
+    if (relu) code = max(code, 0);
+    double o = rint(__dmul_rn((double)code, scalbn((double)me[0], -me[1])));   // quant_utils.py:195-196
+    o = fmin(fmax(o, (double)qmin), (double)qmax);
+    lut[threadIdx.x] = (int8_t)(int)o;
+  }
+  __syncthreads();
+  const int tq = (T + 15) / 16;
+  const long long total = (long long)B * C * tq;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % tq);
+    const long long row = i / tq;
+    const int b = (int)(row / C);
+    const int len = lens ? min(lens[b], T) : T;
+    const uint4 v = *reinterpret_cast<const uint4*>(in + row * in_ld + 16 * j);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint32_t acc = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = 16 * j + 4 * g + u;
+        const uint32_t code = (w[g] >> (8 * u)) & 0xff;
+        const uint32_t q = t < len ? (uint8_t)lut[code] : 0u;
+        acc |= q << (8 * u);
+      }
+      r[g] = acc;
+    }
+    *reinterpret_cast<uint4*>(out + row * out_ld + 16 * j) = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+int check_operand(const qasr_dyn_operand* o, const char* what) {
+  QASR_CHECK_ARG(o->x && o->w && o->s_x && o->ch && o->wabs, "%s: null pointer in operand", what);
+  QASR_CHECK_ARG(o->C_in > 0 && o->T_in > 0 && o->k > 0 && o->stride >= 1 && o->dilation >= 1 && o->pad >= 0 &&
+                 o->x_ld >= o->T_in, "%s: bad operand shape", what);
+  return QASR_OK;
+}
+
+}  // namespace
+
+extern "C" int qasr_dyn_select(qasr_stats* stats, const qasr_dyn_operand* op0, const qasr_dyn_operand* op1,
+                               int32_t relu, int32_t C_out, int32_t* cand, void* stream) {
+  QASR_CHECK_ARG(stats && op0 && cand && C_out > 0, "dyn_select: bad arguments");
+  int rc = check_operand(op0, "dyn_select");
+  if (rc) return rc;
+  if (op1 && (rc = check_operand(op1, "dyn_select"))) return rc;
+  dyn_select_kernel<<<1, kSelThreads, 0, (cudaStream_t)stream>>>(stats, make_op(op0), make_op(op1), op1 != nullptr, relu,
+                                                                 C_out, cand);
+  return qasr_check_launch("dyn_select_kernel");
+}
+
+extern "C" int qasr_dyn_refine(const qasr_dyn_operand* op0, const qasr_dyn_operand* op1, int32_t relu,
+                               const int32_t* out_lens, int32_t B, int32_t C_out, int32_t T_out, const int32_t* cand,
+                               uint32_t* absmax_bits, void* stream) {
+  QASR_CHECK_ARG(op0 && cand && absmax_bits && B > 0 && C_out > 0 && T_out > 0, "dyn_refine: bad arguments");
+  int rc = check_operand(op0, "dyn_refine");
+  if (rc) return rc;
+  if (op1 && (rc = check_operand(op1, "dyn_refine"))) return rc;
+  const int n0 = op0->depthwise ? op0->k : op0->C_in * op0->k;
+  const int n1 = op1 ? (op1->depthwise ? op1->k : op1->C_in * op1->k) : 0;
+  if (n0 + n1 > kMaxWRow) {
+    qasr_set_error("dyn_refine: %d weights per output channel exceed the %d the kernel keeps in shared memory", n0 + n1, kMaxWRow);
+    return QASR_ERR_UNSUPPORTED;
+  }
+  long long blocks = ((long long)B * T_out + kRefThreads - 1) / kRefThreads;
+  const long long cap = 8LL * qasr_sm_count();
+  if (blocks > cap) blocks = cap;
+  dyn_refine_kernel<<<dim3((unsigned)blocks, QASR_DYN_MAX_CAND), kRefThreads, (size_t)(n0 + n1), (cudaStream_t)stream>>>(
+      make_op(op0), make_op(op1), op1 != nullptr, relu, out_lens, B, C_out, T_out, cand, absmax_bits);
+  return qasr_check_launch("dyn_refine_kernel");
+}
+
+extern "C" int qasr_dyn_finalize(const qasr_dyn_finalize_args* a, void* stream) {
+  QASR_CHECK_ARG(a && a->src && a->act_scale && a->n_levels > 0, "dyn_finalize: bad arguments");
+  QASR_CHECK_ARG(a->src_kind >= 0 && a->src_kind <= 2 && (a->src_kind != 2 || a->src_scale), "dyn_finalize: source");
+  QASR_CHECK_ARG(a->n_prod >= 0 && a->n_prod <= 2 && a->n_cons >= 0 && a->n_cons <= 2, "dyn_finalize: table counts");
+  QASR_CHECK_ARG((a->prev_me == nullptr) == (a->prev_scale == nullptr), "dyn_finalize: prev_scale and prev_me come together");
+  QASR_CHECK_ARG(a->world <= 1 || (a->peer_slots && a->seq && a->rank >= 0 && a->rank < a->world && a->slot >= 0),
+                 "dyn_finalize: data-parallel exchange needs peer_slots / seq / rank");
+  DynFin f;
+  memset(&f, 0, sizeof(f));
+  f.src_kind = a->src_kind; f.src = a->src; f.src_scale = a->src_scale; f.n_levels = a->n_levels;
+  f.act_scale = a->act_scale; f.n_prod = a->n_prod; f.prev_scale = a->prev_scale; f.prev_me = a->prev_me;
+  f.n_cons = a->n_cons;
+  for (int i = 0; i < 2; ++i) {
+    f.prod[i] = a->prod[i]; f.prod_C[i] = a->prod_C[i];
+    f.cons[i] = a->cons[i]; f.cons_sw[i] = a->cons_sw[i]; f.cons_bias[i] = a->cons_bias[i]; f.cons_C[i] = a->cons_C[i];
+    QASR_CHECK_ARG(i >= a->n_prod || (a->prod[i] && a->prod_C[i] > 0), "dyn_finalize: producer table %d", i);
+    QASR_CHECK_ARG(i >= a->n_cons || (a->cons[i] && a->cons_sw[i] && a->cons_C[i] > 0), "dyn_finalize: consumer table %d", i);
+  }
+  f.peer_slots = reinterpret_cast<unsigned long long* const*>(a->peer_slots);
+  f.rank = a->rank; f.world = a->world; f.slot = a->slot; f.seq = a->seq;
+  dyn_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(f);
+  return qasr_check_launch("dyn_finalize_kernel");
+}
+
+extern "C" int qasr_minmax_i8(const int8_t* codes, int32_t ld, int32_t relu, int32_t B, int32_t C, int32_t T,
+                              const int32_t* lens, int32_t* out2, void* stream) {
+  QASR_CHECK_ARG(codes && out2 && B > 0 && C > 0 && T > 0, "minmax_i8: bad arguments");
+  QASR_CHECK_ARG(ld % 16 == 0 && ld >= T && qasr_aligned16(codes), "minmax_i8: pitch/alignment");
+  long long blocks = ((long long)B * C * ((T + 15) / 16) + 255) / 256;
+  const long long cap = 8LL * qasr_sm_count();
+  if (blocks > cap) blocks = cap;
+  minmax_i8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(codes, ld, relu, B, C, T, lens, out2);
+  return qasr_check_launch("minmax_i8_kernel");
+}
+
+extern "C" int qasr_requant_i8_dev(const int8_t* in, int32_t in_ld, int32_t relu, const int32_t* me, int32_t qmin,
+                                   int32_t qmax, int8_t* out, int32_t out_ld, int32_t B, int32_t C, int32_t T,
+                                   const int32_t* lens, void* stream) {
+  QASR_CHECK_ARG(in && out && me, "requant_i8_dev: null pointer");
+  QASR_CHECK_ARG(in_ld % 16 == 0 && out_ld % 16 == 0 && in_ld >= T && out_ld >= T && qasr_aligned16(in) &&
+                     qasr_aligned16(out), "requant_i8_dev: pitch/alignment");
+  QASR_CHECK_ARG(qmin < qmax && qmin >= -256 && qmax <= 255, "requant_i8_dev: clamp range");
+  long long blocks = ((long long)B * C * ((T + 15) / 16) + 255) / 256;
+  const long long cap = 8LL * qasr_sm_count();
+  if (blocks > cap) blocks = cap;
+  requant_i8_dev_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, in_ld, relu, me, qmin, qmax, out, out_ld, B,
+                                                                           C, T, lens);
+  return qasr_check_launch("requant_i8_dev_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// peer-mapped buffers (CUDA IPC) for the range exchange
+// ---------------------------------------------------------------------------------------------
+extern "C" int qasr_comm_alloc(int64_t bytes, void** ptr, void* handle_out) {
+  QASR_CHECK_ARG(bytes > 0 && ptr && handle_out, "comm_alloc: bad arguments");
+  QASR_CHECK_CUDA(cudaMalloc(ptr, (size_t)bytes));
+  QASR_CHECK_CUDA(cudaMemset(*ptr, 0, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  QASR_CHECK_CUDA(cudaIpcGetMemHandle(&h, *ptr));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &h, sizeof(h));
+  return QASR_OK;
+}
+extern "C" int qasr_comm_open(const void* handle, void** ptr) {
+  QASR_CHECK_ARG(handle && ptr, "comm_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  QASR_CHECK_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return QASR_OK;
+}
+extern "C" int qasr_comm_close(void* ptr) {
+  QASR_CHECK_ARG(ptr, "comm_close: null pointer");
+  QASR_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return QASR_OK;
+}
+extern "C" int qasr_comm_free(void* ptr) {
+  QASR_CHECK_ARG(ptr, "comm_free: null pointer");
+  QASR_CHECK_CUDA(cudaFree(ptr));
+  return QASR_OK;
+}

@@ -151,6 +151,40 @@ __device__ __forceinline__ void finish32(const GemmArgs& g, const EpiConsts& kc,
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (row_ok && tv + j < g.T_out) orow[tv + j] = epilogue_dequant(g.ep, a0[j], c0);
+    } else if (g.ep.mode == QASR_EPI_STATS) {
+      // statistics pass of dynamic quantisation: this lane's channel, the counted frames of its 32 columns
+      qasr_stats* st = reinterpret_cast<qasr_stats*>(g.out) + cc;
+      if (g.nseg == 1) {
+        long long lo = 0x7fffffffffffffffLL, hi = -0x7fffffffffffffffLL - 1;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (tv + j < len) {
+            const long long z = qasr_acc_bias64(a0[j], c0.bias);
+            lo = z < lo ? z : lo;
+            hi = z > hi ? z : hi;
+          }
+        }
+        if (row_ok && hi >= lo) {
+          atomicMin(reinterpret_cast<long long*>(&st->lo), lo);
+          atomicMax(reinterpret_cast<long long*>(&st->hi), hi);
+        }
+      } else {
+        unsigned lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (tv + j < len) {
+            const float y0 = __fmul_rn((float)qasr_acc_bias64(a0[j], c0.bias), c0.s);
+            const float y1 = __fmul_rn((float)qasr_acc_bias64(a1[j], c1.bias), c1.s);
+            const unsigned key = qasr_f32_key(__fadd_rn(y1, y0));     // identity + x, quant_modules.py:108
+            lo = key < lo ? key : lo;
+            hi = key > hi ? key : hi;
+          }
+        }
+        if (row_ok && hi >= lo) {
+          atomicMin(reinterpret_cast<unsigned*>(&st->lo), lo);
+          atomicMax(reinterpret_cast<unsigned*>(&st->hi), hi);
+        }
+      }
     } else {
       int32_t* orow = reinterpret_cast<int32_t*>(g.out) + row * g.out_ld;
 #pragma unroll
@@ -789,7 +823,9 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   int rc = qasr_validate_epilogue(epi, true);
   if (rc) return rc;
   QASR_CHECK_ARG((op1 != nullptr) == (epi->ch1 != nullptr), "conv1d_gemm: second operand and epi->ch1 must come together");
-  QASR_CHECK_ARG(!op1 || epi->mode == QASR_EPI_REQUANT_I8, "conv1d_gemm: second operand needs REQUANT mode");
+  QASR_CHECK_ARG(!op1 || epi->mode == QASR_EPI_REQUANT_I8 || epi->mode == QASR_EPI_STATS,
+                 "conv1d_gemm: second operand needs REQUANT or STATS mode");
+  qasr_set_plain_launch((epi->flags & QASR_F_DEVICE_TABLES) != 0);
 
   GemmArgs g;
   memset(&g, 0, sizeof(g));

@@ -75,6 +75,10 @@ static inline EpiArgs make_epi_args(const qasr_epilogue* e) {
 }
 
 int qasr_validate_epilogue(const qasr_epilogue* e, bool allow_second_operand);
+// Launch policy of the entry point that is running on this thread: true = plain stream order (no programmatic
+// dependent launch), set from QASR_F_DEVICE_TABLES for every conv launch.
+void qasr_set_plain_launch(bool plain);
+bool qasr_plain_launch();
 long long qasr_debug_get(int key);   // bring-up knobs, see api.cu
 extern "C" int qasr_debug_set(int key, long long value);
 
@@ -99,7 +103,7 @@ static inline cudaError_t qasr_launch_pdl(Kern kern, dim3 grid, dim3 block, size
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = qasr_debug_get(9) == 0 ? 0 : 1;   // knob 9 = 0: plain launches
+  attr[0].val.programmaticStreamSerializationAllowed = (qasr_debug_get(9) == 0 || qasr_plain_launch()) ? 0 : 1;   // knob 9 = 0: plain launches
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, args...);
@@ -115,7 +119,7 @@ static inline cudaError_t qasr_launch_pdl_pair(Kern kern, dim3 grid, dim3 block,
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = qasr_debug_get(9) == 0 ? 0 : 1;
+  attr[0].val.programmaticStreamSerializationAllowed = (qasr_debug_get(9) == 0 || qasr_plain_launch()) ? 0 : 1;
   attr[1].id = cudaLaunchAttributeClusterDimension;
   attr[1].val.clusterDim.x = 2;
   attr[1].val.clusterDim.y = 1;
@@ -286,6 +290,19 @@ __device__ __forceinline__ float epilogue_dequant(const EpiArgs& ep, int acc, co
   float y = __fmul_rn(a, c.s);
   if (ep.flags & QASR_F_RELU0) y = fmaxf(y, 0.0f);
   return y;
+}
+
+// order-preserving map float -> uint32 (statistics kernels: atomicMin / atomicMax on the keys)
+__device__ __forceinline__ unsigned qasr_f32_key(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float qasr_key_f32(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// accumulator + bias as the reference's conv sees it (64-bit: INT32_MAX is the sentinel of b_int == 2^31)
+__device__ __forceinline__ long long qasr_acc_bias64(int acc, int bias) {
+  return (long long)acc + (bias == 2147483647 ? 2147483648LL : (long long)bias);
 }
 
 // low bytes of four ints -> one word (3 PRMT)

@@ -149,6 +149,61 @@ class EncDecCTCModel(nn.Module):
         from qasr import plan as _plan
         return _plan.get_plan(self.encoder, self.decoder, shape, device, self._plan_cache)
 
+    # ---- dynamic quantisation (quant_modules.py:149-167) on the fused device-side plan (qasr.dynplan) ----------------
+    def _dynamic_fusable(self, x):
+        from nemo.quantization.utils.quant_modules import QuantAct, QuantConv1d
+        if not (self.use_fused_plan and x.is_cuda and not self.training and self.decoder.quant_mode == "symmetric"
+                and self.encoder.quant_mode == "symmetric"):
+            return False
+        for m in self.modules():
+            if type(m) is QuantAct and (m.running_stat or not m.dynamic or m.percentile or m.per_channel):
+                return False
+            if isinstance(m, QuantConv1d) and (m.quant_mode != "symmetric" or (m.bn is not None and not m.fix_bn)):
+                return False
+        return True
+
+    def _dynamic_plan_or_none(self, x):
+        """The device-side dynamic plan for this exact input shape (a dynamic range depends on every frame of the batch,
+        so there are no frame buckets), None when the model is not in the fixed dynamic state or its structure is not
+        covered (module-level path then).  Under qasr.dist data parallelism the plan exchanges every range between the
+        ranks through peer memory; all ranks must run the same batches in lockstep."""
+        if not self._dynamic_fusable(x):
+            return None
+        from qasr import dist as _dist
+        from qasr import dynplan as _dyn
+        from qasr import plan as _plan
+        dp_on = _dist.is_enabled()
+        key = ("dynamic", tuple(x.shape), str(x.device), dp_on)
+        sig = _plan._signature(self.encoder, self.decoder)
+        hit = self._plan_cache.get(key)
+        if hit is not None and hit[0] == sig:
+            self._plan_cache[key] = self._plan_cache.pop(key)
+            return None if isinstance(hit[1], _plan.PlanUnsupported) else hit[1]
+        self._plan_cache.pop(key, None)
+        try:
+            dp = None
+            if dp_on:
+                dp = _dist.peer_slots(x.device)
+            p = _dyn.DynamicPlan(self.encoder, self.decoder, x.shape, x.device, dp=dp)
+        except NotImplementedError as exc:
+            self._plan_cache[key] = (sig, _plan.PlanUnsupported(str(exc)))
+            return None
+        self._plan_cache[key] = (sig, p)
+        while len(self._plan_cache) > _plan.MAX_PLANS:
+            self._plan_cache.pop(next(iter(self._plan_cache)))
+        return p
+
+    def forward_dynamic(self, processed_signal, processed_signal_length):
+        """Dynamic-mode forward on the fused plan: (float32 logits (B, V, T'), greedy labels (B, T') int64), or None
+        when the plan does not apply (the caller runs the module-level path)."""
+        p = self._dynamic_plan_or_none(processed_signal)
+        if p is None:
+            return None
+        p.run(processed_signal, processed_signal_length)
+        if p.overflowed():      # more near-tied channels than the refinement covers: practically never
+            return None
+        return p.logits[:, :, :p.cur_T_out], p.greedy().to(torch.long)
+
     def _plan_or_none(self, x):
         """The fused plan when the model is in the fixed static state AND its structure can be compiled; None sends
         the caller down the module-level path (configurations the plan compiler does not cover, e.g. strided
@@ -267,6 +322,12 @@ class EncDecCTCModel(nn.Module):
         if p is not None:
             p.run(processed_signal, processed_signal_length)
             return p.log_probs(), p.out_lens().to(torch.long), p.greedy().to(torch.long)
+        p = self._dynamic_plan_or_none(processed_signal)
+        if p is not None:
+            p.run(processed_signal, processed_signal_length)
+            if not p.overflowed():
+                self.decoder.last_logits = p.logits[:, :, :p.cur_T_out]
+                return p.log_probs(), p.out_lens().to(torch.long), p.greedy().to(torch.long)
         encoded, encoded_len, encoded_sf = self.encoder(audio_signal=processed_signal,
                                                         length=processed_signal_length)
         log_probs = self.decoder(encoder_output=encoded, encoder_output_scaling_factor=encoded_sf)

@@ -12,10 +12,12 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QASR_LIB_PATH", os.path.join(_HERE, "libqasr.so"))  # override: kernel experiments
 
-EPI_REQUANT_I8, EPI_DEQUANT_F32, EPI_RAW_I32 = 0, 1, 2
+EPI_REQUANT_I8, EPI_DEQUANT_F32, EPI_RAW_I32, EPI_STATS = 0, 1, 2, 3
 F_RELU0, F_RELU1, F_STAGE2, F_MASK = 1, 2, 4, 8
 F_EXACT_F32, F_EXACT_DYAD, F_B_SIGNED, F_B1_SIGNED, F_BIAS64 = 16, 32, 64, 128, 256
 F_FAST_F32 = 512
+F_DEVICE_TABLES = 1024
+DYN_MAX_CAND = 4
 
 
 class QasrError(RuntimeError):
@@ -40,6 +42,25 @@ class GemmOperand(C.Structure):
         ("x", C.c_void_p), ("wp", C.c_void_p),
         ("x_ld", C.c_int32), ("C_in", C.c_int32), ("T_in", C.c_int32), ("k", C.c_int32),
         ("stride", C.c_int32), ("dilation", C.c_int32), ("pad", C.c_int32),
+    ]
+
+
+class DynOperand(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w", C.c_void_p), ("s_x", C.c_void_p), ("ch", C.c_void_p), ("wabs", C.c_void_p),
+        ("x_ld", C.c_int32), ("C_in", C.c_int32), ("T_in", C.c_int32), ("k", C.c_int32), ("stride", C.c_int32),
+        ("dilation", C.c_int32), ("pad", C.c_int32), ("depthwise", C.c_int32), ("in_unsigned", C.c_int32),
+    ]
+
+
+class DynFinalizeArgs(C.Structure):
+    _fields_ = [
+        ("src_kind", C.c_int32), ("src", C.c_void_p), ("src_scale", C.c_void_p), ("n_levels", C.c_int32),
+        ("act_scale", C.c_void_p), ("n_prod", C.c_int32), ("prod", C.c_void_p * 2), ("prod_C", C.c_int32 * 2),
+        ("prev_scale", C.c_void_p), ("prev_me", C.c_void_p), ("n_cons", C.c_int32), ("cons", C.c_void_p * 2),
+        ("cons_sw", C.c_void_p * 2), ("cons_bias", C.c_void_p * 2), ("cons_C", C.c_int32 * 2),
+        ("peer_slots", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32), ("slot", C.c_int32),
+        ("seq", C.c_void_p),
     ]
 
 
@@ -80,6 +101,16 @@ _SIGS = {
                                    _i32, _i32, _vp]),
     "qasr_normalize_features_f32": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "qasr_ctc_collapse": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "qasr_dyn_select": (C.c_int, [_vp, C.POINTER(DynOperand), C.POINTER(DynOperand), _i32, _i32, _vp, _vp]),
+    "qasr_dyn_refine": (C.c_int, [C.POINTER(DynOperand), C.POINTER(DynOperand), _i32, _vp, _i32, _i32, _i32, _vp, _vp,
+                                  _vp]),
+    "qasr_dyn_finalize": (C.c_int, [C.POINTER(DynFinalizeArgs), _vp]),
+    "qasr_minmax_i8": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "qasr_requant_i8_dev": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "qasr_comm_alloc": (C.c_int, [_i64, C.POINTER(C.c_void_p), _vp]),
+    "qasr_comm_open": (C.c_int, [_vp, C.POINTER(C.c_void_p)]),
+    "qasr_comm_close": (C.c_int, [_vp]),
+    "qasr_comm_free": (C.c_int, [_vp]),
     "qasr_debug_set": (C.c_int, [C.c_int, C.c_longlong]),
     "qasr_debug_knobs_set": (C.c_int, []),
 }

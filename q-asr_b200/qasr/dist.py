@@ -55,3 +55,23 @@ def gather_predictions(labels):
     out = [torch.zeros_like(pad) for _ in range(world)]
     dist.all_gather(out, pad, group=_state["group"])
     return torch.cat([o[:int(s)] for o, s in zip(out, sizes)], dim=0)
+
+
+_slots = {}
+
+
+def peer_slots(device, n_slots=512):
+    """Peer-mapped slot tables of the fused dynamic plan's range exchange (qasr.dynplan.PeerSlots), one set per
+    device and process group; the CUDA IPC handles travel through all_gather_object."""
+    from . import dynplan
+    key = (str(device), id(_state["group"]))
+    if key not in _slots:
+        group = _state["group"]
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+
+        def gather(handle):
+            out = [None] * world
+            dist.all_gather_object(out, handle, group=group)
+            return out
+        _slots[key] = dict(rank=rank, world=world, slots=dynplan.PeerSlots(rank, world, n_slots, device, gather))
+    return _slots[key]
