@@ -356,9 +356,14 @@ def dynamic_dp(device, rank, world, distributed, steps=3):
     x = features(lo, hi).to(device)
     lens = torch.full((hi - lo,), T, dtype=torch.int32, device=device)
 
+    used = {"plan": 0, "modules": 0}
+
     def fwd(xx, ll):
-        if hasattr(model, "forward_dynamic"):
-            return model.forward_dynamic(xx, ll)
+        r = model.forward_dynamic(xx, ll)      # the fused device-side dynamic plan (qasr.dynplan)
+        if r is not None:
+            used["plan"] += 1
+            return r
+        used["modules"] += 1
         lp, el, gr = model(processed_signal=xx, processed_signal_length=ll)
         return model.decoder.last_logits, gr
 
@@ -394,6 +399,8 @@ def dynamic_dp(device, rank, world, distributed, steps=3):
         if rank == 0:
             # the reference's semantics: ONE process sees the whole batch.  Chunked over the batch it would not be the
             # same computation, so the whole global batch runs on this one GPU.
+            model._plan_cache.clear()
+            torch.cuda.empty_cache()
             xf = features(0, gb).to(device)
             lf = torch.full((gb,), T, dtype=torch.int32, device=device)
             logits_full, _ = fwd(xf, lf)
@@ -401,13 +408,16 @@ def dynamic_dp(device, rank, world, distributed, steps=3):
             del xf, logits_full
         dist.barrier()
     audio_s = gb * T / FRAMES_PER_AUDIO_SECOND
-    path = "fused dynamic plan (stats pass + requantising pass per layer, device-side ranges)" \
-        if hasattr(model, "forward_dynamic") else "module-level QuantAct / QuantConv1d calls"
+    path = ("fused dynamic plan: statistics pass + requantising pass per conv, ranges / scales / dyadic tables on the "
+            "device, one CUDA graph" if used["modules"] == 0 else
+            "module-level QuantAct / QuantConv1d calls (%d of %d forwards)" % (used["modules"], used["modules"] + used["plan"]))
     out = dict(workload=wl["name"] if world > 1 else wl["name"].replace("b1024", "b%d" % gb), global_batch=gb,
                per_rank_batch=hi - lo, ms_per_step=round(ms_dp, 3), value=round(audio_s / (ms_dp / 1e3), 1),
                unit="audio-s/s", allreduce_share=round(max(0.0, (ms_dp - ms_local) / ms_dp), 4) if distributed else 0.0,
                ms_per_step_without_allreduce=round(ms_local, 3), bit_exact_vs_single_rank=bit_exact,
-               collective="one MAX all-reduce of [-min, max] per QuantAct (186 per forward)" if distributed else "none (one rank)",
+               collective=("one-shot MAX exchange of every QuantAct's absmax through peer-mapped memory (CUDA IPC over "
+                           "NVLink), inside the finalize kernel of the graph" if used["modules"] == 0 else
+                           "one NCCL MAX all-reduce of [-min, max] per QuantAct") if distributed else "none (one rank)",
                path=path)
     del model
     torch.cuda.empty_cache()
