@@ -273,14 +273,14 @@ int qasr_quantile2_f32(const float* x, const float* identity, int32_t ld, int32_
  *      every QuantAct is a function of the batch, so scales, dyadic multipliers and integer biases exist on
  *      the device only and the whole forward stays one CUDA graph.  Per conv -> consumer QuantAct:
  *        1. qasr_conv* with QASR_EPI_STATS        per-channel extremes of the integer accumulators
- *        2. qasr_dyn_select                        which channels can hold max |y| (rigorous float bounds)
- *        3. qasr_dyn_refine                        those channels again, position by position, WITH the float
+ *        2. qasr_dyn_refine                        which channels can hold max |y| (rigorous float bounds), then
+ *                                                  those channels again, position by position, WITH the float
  *                                                  noise of the reference's un-rounded x / s (quant_modules.py:301):
  *                                                  the exact max |y| the reference's x.min() / x.max() see
- *        4. qasr_dyn_finalize                      range -> scale (quant_utils.py:47-52) -> (m, e) of the producers
+ *        3. qasr_dyn_finalize                      range -> scale (quant_utils.py:47-52) -> (m, e) of the producers
  *                                                  (quant_utils.py:188-193, 121-147) -> s_out / b_int of the
  *                                                  consumer convs (quant_modules.py:293-297)
- *        5. qasr_conv* with QASR_EPI_REQUANT_I8 | QASR_F_DEVICE_TABLES
+ *        4. qasr_conv* with QASR_EPI_REQUANT_I8 | QASR_F_DEVICE_TABLES
  *      Only max(|x_min|, |x_max|) enters the scale, so one extreme is tracked: absmax = max |x_act|.
  * ---------------------------------------------------------------------------------- */
 typedef struct {
@@ -295,13 +295,14 @@ typedef struct {
 } qasr_dyn_operand;
 
 #define QASR_DYN_MAX_CAND 4
-/* cand[0..3] = candidate channels (-1 = none), cand[4] = how many channels qualified (> 4: refused, the caller
- * checks it after the forward).  Resets `stats` to its initial state. */
-int qasr_dyn_select(qasr_stats* stats, const qasr_dyn_operand* op0, const qasr_dyn_operand* op1, int32_t relu,
-                    int32_t C_out, int32_t* cand, void* stream);
-/* absmax_bits: uint32 bit pattern of a non-negative float, updated with atomicMax (reset value 0). */
-int qasr_dyn_refine(const qasr_dyn_operand* op0, const qasr_dyn_operand* op1, int32_t relu, const int32_t* out_lens,
-                    int32_t B, int32_t C_out, int32_t T_out, const int32_t* cand, uint32_t* absmax_bits, void* stream);
+/* Reads the records the QASR_EPI_STATS pass left in `stats` (qasr_dyn_finalize resets them afterwards), picks the
+ * candidate channels, recomputes them with the float noise and folds the exact max |x_act| into *absmax_bits: the
+ * uint32 bit pattern of a non-negative float, updated with atomicMax (reset value 0).
+ * cand[0..3] = candidate channels (-1 = none), cand[4] = how many channels qualified (> 4: refused, the caller checks
+ * it after the forward).  relu: a ReLU sits between the conv and the QuantAct (one operand only). */
+int qasr_dyn_refine(const qasr_stats* stats, const qasr_dyn_operand* op0, const qasr_dyn_operand* op1, int32_t relu,
+                    const int32_t* out_lens, int32_t B, int32_t C_out, int32_t T_out, int32_t* cand,
+                    uint32_t* absmax_bits, void* stream);
 
 typedef struct {
   int32_t src_kind;          /* 0: *src = absmax bits (uint32, reset to 0 after reading)
@@ -326,6 +327,12 @@ typedef struct {
   uint64_t* const* peer_slots;   /* device array [world]: every rank's slot table (peer-mapped)           */
   int32_t rank, world, slot;
   uint32_t* seq;                 /* device counter of this finalize node                                  */
+  /* per producer: sum |w| per channel and the largest |input code|, for the device-side proof that the all-integer
+   * epilogue equals the literal float recipe on that channel (else bit 31 of the record's e is set)      */
+  const int32_t* prod_wabs[2];
+  int32_t prod_qabs[2];
+  qasr_stats* stats;             /* optional: statistics records to put back into their reset state       */
+  int32_t stats_C, stats_dual;
 } qasr_dyn_finalize_args;
 int qasr_dyn_finalize(const qasr_dyn_finalize_args* a, void* stream);
 

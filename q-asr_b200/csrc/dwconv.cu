@@ -102,8 +102,9 @@ __device__ __forceinline__ void row_copy_async(uint32_t dst, const void* src, ui
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// EK: 0 = REQUANT all-integer fast path, 1 = REQUANT literal path, 2 = DEQUANT_F32 / RAW_I32,
-//     3 = REQUANT float fast path (QASR_F_FAST_F32)
+// EK: 0 = REQUANT all-integer fast path, 1 = REQUANT literal path, 2 = DEQUANT_F32 / RAW_I32 / STATS,
+//     3 = REQUANT float fast path (QASR_F_FAST_F32), 4 = REQUANT with device-written tables (QASR_F_DEVICE_TABLES):
+//     integer fast path for the channels qasr_dyn_finalize proved, literal path for the others
 template <int KS, int S, bool XS, int EK>
 #ifndef QASR_DW_MIN_BLOCKS
 #define QASR_DW_MIN_BLOCKS 1
@@ -184,8 +185,9 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
     const int b = b_begin + r;
     const int len = masked ? min(a.ep.out_lens[b], T_out) : T_out;
     // the tile loop exists twice, float and integer epilogue, chosen once per row (warp-uniform)
-    auto tiles = [&](auto f32_tag) {
-    constexpr bool F32 = decltype(f32_tag)::value;
+    auto tiles = [&](auto mode_tag) {
+    constexpr int MODE = decltype(mode_tag)::value;   // 0 = integer fast path, 1 = float fast path, 2 = literal recipe
+    constexpr bool F32 = MODE == 1;
     // float path: the MMA's initial accumulator is 0x4B400000 + bias, so the finished accumulator's BITS are the
     // float 1.5 * 2^23 + (acc + bias): the bias add and the int -> float conversion cost no instruction
     const int acc_init = F32 ? kF32MagicBits + c0.bias : 0;
@@ -194,8 +196,8 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
     uint32_t* const orow_w = reinterpret_cast<uint32_t*>(out_row) + lane;
     auto code = [&](int acc_v) -> uint8_t {
       if (F32) return (uint8_t)epilogue_f32_bits_biased(kc, acc_v, c0);
-      return (uint8_t)(EK == 0 ? epilogue_fast<false, false, false>(a.ep, kc, acc_v, c0, 0, c0, 0)
-                               : epilogue_exact(a.ep, kc, acc_v, c0, false, 0, c0, 0));
+      return (uint8_t)(MODE == 0 ? epilogue_fast<false, false, false>(a.ep, kc, acc_v, c0, 0, c0, 0)
+                                 : epilogue_exact(a.ep, kc, acc_v, c0, false, 0, c0, 0));
     };
     // finished accumulators of the tile at t0 -> codes -> (transpose through the warp's staging line `sl`) -> store
     auto finish_tile = [&](int t0, const int (&acc)[4], int sl) {
@@ -311,7 +313,9 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
       finish_tile(t0, acc, sp);
     }
     };
-    if (EK == 3 || (EK == 0 && f32_path)) tiles(std::true_type{}); else tiles(std::false_type{});
+    if (EK == 3 || (EK == 0 && f32_path)) tiles(std::integral_constant<int, 1>{});
+    else if (EK == 0 || (EK == 4 && !c0.literal)) tiles(std::integral_constant<int, 0>{});
+    else tiles(std::integral_constant<int, 2>{});
     __syncwarp();  // every lane is done reading this buffer before lane 0 refills it
   }
   if (EK == 2 && a.ep.mode == QASR_EPI_STATS) {
@@ -337,7 +341,8 @@ int launch(const DwArgs& a, cudaStream_t stream) {
   const bool xs = a.ep.flags & QASR_F_B_SIGNED;
   const bool fast = !(a.ep.flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64 | QASR_F_STAGE2)) &&
                     a.ep.prev == nullptr;
-  const int ek = a.ep.mode != QASR_EPI_REQUANT_I8 ? 2 : ((a.ep.flags & QASR_F_FAST_F32) ? 3 : (fast ? 0 : 1));
+  int ek = a.ep.mode != QASR_EPI_REQUANT_I8 ? 2 : ((a.ep.flags & QASR_F_FAST_F32) ? 3 : (fast ? 0 : 1));
+  if (ek == 1 && (a.ep.flags & QASR_F_DEVICE_TABLES) && !(a.ep.flags & QASR_F_STAGE2) && a.ep.prev == nullptr) ek = 4;
 #define QASR_DW_GO(XS_, EK_)                                                                         \
   do {                                                                                               \
     auto kern = dwconv_mma_kernel<KS, S, XS_, EK_>;                                                  \
@@ -349,9 +354,9 @@ int launch(const DwArgs& a, cudaStream_t stream) {
     QASR_CHECK_CUDA(qasr_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, a));             \
   } while (0)
   if (xs) {
-    if (ek == 0) QASR_DW_GO(true, 0); else if (ek == 1) QASR_DW_GO(true, 1); else if (ek == 2) QASR_DW_GO(true, 2); else QASR_DW_GO(true, 3);
+    if (ek == 0) QASR_DW_GO(true, 0); else if (ek == 1) QASR_DW_GO(true, 1); else if (ek == 2) QASR_DW_GO(true, 2); else if (ek == 3) QASR_DW_GO(true, 3); else QASR_DW_GO(true, 4);
   } else {
-    if (ek == 0) QASR_DW_GO(false, 0); else if (ek == 1) QASR_DW_GO(false, 1); else if (ek == 2) QASR_DW_GO(false, 2); else QASR_DW_GO(false, 3);
+    if (ek == 0) QASR_DW_GO(false, 0); else if (ek == 1) QASR_DW_GO(false, 1); else if (ek == 2) QASR_DW_GO(false, 2); else if (ek == 3) QASR_DW_GO(false, 3); else QASR_DW_GO(false, 4);
   }
 #undef QASR_DW_GO
   return qasr_check_launch("dwconv_mma_kernel");

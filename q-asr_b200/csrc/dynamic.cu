@@ -18,7 +18,6 @@
 
 namespace {
 
-constexpr int kSelThreads = 256;
 constexpr int kRefThreads = 128;
 constexpr int kMaxWRow = 8192;   // weights of one output channel kept in shared memory by dyn_refine
 
@@ -64,169 +63,217 @@ __device__ __forceinline__ float block_max(float v, float* sh) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// select
+// candidate channels: bounds  L_c <= max_t |y| <= U_c  from the noise-free statistics; every block of the refinement
+// repeats this (C records, a few KB from L2) instead of a separate one-block launch in front of it
 // ---------------------------------------------------------------------------------------------
-__global__ void dyn_select_kernel(qasr_stats* stats, const DynOp op0, const DynOp op1, int dual, int relu, int C,
-                                  int32_t* cand) {
-  __shared__ float sh[kSelThreads / 32];
-  __shared__ int s_count;
-  __shared__ int s_list[QASR_DYN_MAX_CAND];
-  const int tid = threadIdx.x;
-  // largest |eps| * 2^22 over the 256 codes of each operand's input scale
-  const float s0 = op0.s_x[0];
-  const int q0 = op0.in_unsigned ? tid : (int)(int8_t)tid;
-  const float emax0 = block_max((float)abs(noise_code(q0, s0)), sh) * (1.0f / 4194304.0f);
-  float emax1 = 0.0f;
-  if (dual) {
-    const float s1 = op1.s_x[0];
-    const int q1 = op1.in_unsigned ? tid : (int)(int8_t)tid;
-    emax1 = block_max((float)abs(noise_code(q1, s1)), sh) * (1.0f / 4194304.0f);
+struct Cand {
+  int c;
+  float thr_f;         // two operands: positions with |v^| >= thr_f can hold the maximum
+  long long thr_z;     // one operand : positions with |z| (ReLU: z) >= thr_z can
+};
+
+__device__ void select_candidates(const qasr_stats* stats, const DynOp& op0, const DynOp& op1, int dual, int relu, int C,
+                                  float* sh, int* s_count, Cand* s_list) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  // largest |eps| over the 256 codes of each operand's input scale
+  float e0 = 0.0f, e1 = 0.0f;
+  for (int i = tid; i < 256; i += nt) {
+    e0 = fmaxf(e0, (float)abs(noise_code(op0.in_unsigned ? i : (int)(int8_t)i, op0.s_x[0])));
+    if (dual) e1 = fmaxf(e1, (float)abs(noise_code(op1.in_unsigned ? i : (int)(int8_t)i, op1.s_x[0])));
   }
-  if (tid == 0) s_count = 0;
-  // per-channel bounds  L_c <= max_t |y| <= U_c
+  const float emax0 = block_max(e0, sh) * (1.0f / 4194304.0f);
+  const float emax1 = dual ? block_max(e1, sh) * (1.0f / 4194304.0f) : 0.0f;
+  if (tid == 0) *s_count = 0;
   float lmax = 0.0f;
-  for (int c = tid; c < C; c += kSelThreads) {
-    float U = 0.0f, L = 0.0f;
+  auto bounds = [&](int c, float& U, float& L, long long& thr_z, float& thr_f) {
+    U = 0.0f; L = 0.0f; thr_z = 0x7fffffffffffffffLL; thr_f = FLT_MAX;
     if (!dual) {
       const long long lo = stats[c].lo, hi = stats[c].hi;
-      if (hi >= lo) {
-        const double d = (double)op0.wabs[c] * (double)emax0;     // |delta| <= sum|w| * max|eps|
-        const float sc = __int_as_float(((const int*)(op0.ch + c))[0]);
-        double a_hi, a_lo;
-        if (relu) {
-          a_hi = fmax((double)hi + d, 0.0);
-          a_lo = fmax((double)hi - d, 0.0);
-        } else {
-          const double a = fmax(fabs((double)lo), fabs((double)hi));
-          a_hi = a + d;
-          a_lo = fmax(a - d, 0.0);
-        }
-        U = __fmul_rn(__double2float_ru(a_hi), sc);    // f32(.) and * s are monotone
-        L = __fmul_rn(__double2float_rd(a_lo), sc);
-      }
+      if (hi < lo) return;
+      const double d = (double)op0.wabs[c] * (double)emax0;     // |delta| <= sum|w| * max|eps|
+      const float sc = op0.ch[c].s_out;
+      const double a = relu ? (double)hi : fmax(fabs((double)lo), fabs((double)hi));
+      U = __fmul_rn(__double2float_ru(fmax(a + d, 0.0)), sc);    // f32(.) and * s are monotone
+      L = __fmul_rn(__double2float_rd(fmax(a - d, 0.0)), sc);
+      thr_z = (long long)floor(a - 2.0 * d) - 1;
     } else {
       const unsigned klo = reinterpret_cast<const unsigned*>(&stats[c].lo)[0];
       const unsigned khi = reinterpret_cast<const unsigned*>(&stats[c].hi)[0];
-      if (khi >= klo) {
-        const float a = fmaxf(fabsf(qasr_key_f32(klo)), fabsf(qasr_key_f32(khi)));
-        const float sc0 = __int_as_float(((const int*)(op0.ch + c))[0]);
-        const float sc1 = __int_as_float(((const int*)(op1.ch + c))[0]);
-        // |v - v^|: each operand's float differs by at most (|delta_i| + ulp(A_i) / 2) * s_i plus the rounding of the
-        // product, the sum adds one more rounding.  With |A_i| <= sum|w| * 255 + |b_i| =: Amax_i and Y_i = Amax_i * s_i:
-        //   |v - v^| <= 2 (d0 s0 + d1 s1) + (2^-23 + 2^-21) (Y0 + Y1)        (generous constants)
-        const double y0 = ((double)op0.wabs[c] * 255.0 + fabs((double)op0.ch[c].bias)) * sc0;
-        const double y1 = ((double)op1.wabs[c] * 255.0 + fabs((double)op1.ch[c].bias)) * sc1;
-        const double e = 2.0 * ((double)op0.wabs[c] * emax0 * sc0 + (double)op1.wabs[c] * emax1 * sc1) +
-                         (1.1920929e-7 + 4.76837158e-7) * (y0 + y1);
-        U = __double2float_ru((double)a + e);
-        L = __double2float_rd(fmax((double)a - e, 0.0));
-      }
+      if (khi < klo) return;
+      const float a = fmaxf(fabsf(qasr_key_f32(klo)), fabsf(qasr_key_f32(khi)));
+      const float sc0 = op0.ch[c].s_out, sc1 = op1.ch[c].s_out;
+      // |v - v^|: each operand's float differs by at most (|delta_i| + ulp(A_i) / 2) * s_i plus the rounding of the
+      // product, the sum adds one more rounding.  With |A_i| <= sum|w| * 255 + |b_i| =: Amax_i and Y_i = Amax_i * s_i:
+      //   |v - v^| <= 2 (d0 s0 + d1 s1) + (2^-23 + 2^-21) (Y0 + Y1)        (generous constants)
+      const double y0 = ((double)op0.wabs[c] * 255.0 + fabs((double)op0.ch[c].bias)) * sc0;
+      const double y1 = ((double)op1.wabs[c] * 255.0 + fabs((double)op1.ch[c].bias)) * sc1;
+      const double e = 2.0 * ((double)op0.wabs[c] * emax0 * sc0 + (double)op1.wabs[c] * emax1 * sc1) +
+                       (1.1920929e-7 + 4.76837158e-7) * (y0 + y1);
+      U = __double2float_ru((double)a + e);
+      L = __double2float_rd(fmax((double)a - e, 0.0));
+      thr_f = __double2float_rd((double)a - 2.0 * e - 1e-30);
     }
-    // park the bounds in the record (it is reset below, after the second sweep)
-    reinterpret_cast<float*>(&stats[c].lo)[1] = U;
-    reinterpret_cast<float*>(&stats[c].hi)[1] = L;
+  };
+  for (int c = tid; c < C; c += nt) {
+    float U, L, tf;
+    long long tz;
+    bounds(c, U, L, tz, tf);
     lmax = fmaxf(lmax, L);
   }
   const float lstar = block_max(lmax, sh);
-  for (int c = tid; c < C; c += kSelThreads) {
-    const float U = reinterpret_cast<const float*>(&stats[c].lo)[1];
+  for (int c = tid; c < C; c += nt) {
+    float U, L, tf;
+    long long tz;
+    bounds(c, U, L, tz, tf);
     if (U > 0.0f && U >= lstar) {
-      const int slot = atomicAdd(&s_count, 1);
-      if (slot < QASR_DYN_MAX_CAND) s_list[slot] = c;
-    }
-    // reset for the next forward
-    if (!dual) {
-      stats[c].lo = 0x7fffffffffffffffLL;
-      stats[c].hi = -0x7fffffffffffffffLL - 1;
-    } else {
-      stats[c].lo = 0xffffffffLL;
-      stats[c].hi = 0;
+      const int slot = atomicAdd(s_count, 1);
+      if (slot < QASR_DYN_MAX_CAND) { s_list[slot].c = c; s_list[slot].thr_z = tz; s_list[slot].thr_f = tf; }
     }
   }
   __syncthreads();
-  if (tid < QASR_DYN_MAX_CAND) cand[tid] = tid < s_count ? s_list[tid] : -1;
-  if (tid == 0) cand[QASR_DYN_MAX_CAND] = s_count;
 }
 
 // ---------------------------------------------------------------------------------------------
-// refine: one candidate channel per blockIdx.y, one output position per thread
+// refine: candidate channels again, position by position; the noise term only where the position can win
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void refine_operand(const DynOp& op, const int8_t* wrow, const int8_t* lut, int c, int b,
-                                               int t, bool valid, int C_out, long long& acc, long long& dacc) {
-  acc = 0;
-  dacc = 0;
-  if (!valid) return;
+// generic scalar conv of one output position (any k / stride / dilation, depthwise or dense)
+__device__ __forceinline__ int conv_at(const DynOp& op, const int8_t* wrow, int c, int b, int t) {
+  int acc = 0;
   const int tin0 = t * op.stride - op.pad;
-  if (op.depthwise) {
-    const uint8_t* row = op.x + ((size_t)b * op.C_in + c) * op.x_ld;
+  const int nci = op.depthwise ? 1 : op.C_in;
+  for (int ci = 0; ci < nci; ++ci) {
+    const uint8_t* row = op.x + ((size_t)b * op.C_in + (op.depthwise ? c : ci)) * op.x_ld;
     for (int j = 0; j < op.k; ++j) {
       const int ti = tin0 + j * op.dil;
       if (ti >= 0 && ti < op.T_in) {
         const unsigned code = row[ti];
-        const int q = op.in_unsigned ? (int)code : (int)(int8_t)code;
-        const int w = wrow[j];
-        acc += w * q;
-        dacc += w * (int)lut[code];
+        acc += (int)wrow[ci * op.k + j] * (op.in_unsigned ? (int)code : (int)(int8_t)code);
       }
     }
+  }
+  return acc;
+}
+__device__ __forceinline__ int noise_at(const DynOp& op, const int8_t* wrow, const int8_t* lut, int c, int b, int t) {
+  int dacc = 0;
+  const int tin0 = t * op.stride - op.pad;
+  const int nci = op.depthwise ? 1 : op.C_in;
+  for (int ci = 0; ci < nci; ++ci) {
+    const uint8_t* row = op.x + ((size_t)b * op.C_in + (op.depthwise ? c : ci)) * op.x_ld;
+    for (int j = 0; j < op.k; ++j) {
+      const int ti = tin0 + j * op.dil;
+      if (ti >= 0 && ti < op.T_in) dacc += (int)wrow[ci * op.k + j] * (int)lut[row[ti]];
+    }
+  }
+  return dacc;
+}
+// four consecutive output frames of a 1x1 stride-1 conv: one 32-bit load per input channel
+__device__ __forceinline__ void conv4_pointwise(const DynOp& op, const int8_t* wrow, int b, int t4, int (&acc)[4]) {
+  acc[0] = acc[1] = acc[2] = acc[3] = 0;
+  const uint8_t* p = op.x + (size_t)b * op.C_in * op.x_ld + t4;
+  if (op.in_unsigned) {
+#pragma unroll 4
+    for (int ci = 0; ci < op.C_in; ++ci, p += op.x_ld) {
+      const uint32_t w4 = *reinterpret_cast<const uint32_t*>(p);
+      const int w = wrow[ci];
+      acc[0] += w * (int)(w4 & 0xff);
+      acc[1] += w * (int)((w4 >> 8) & 0xff);
+      acc[2] += w * (int)((w4 >> 16) & 0xff);
+      acc[3] += w * (int)(w4 >> 24);
+    }
   } else {
-    for (int ci = 0; ci < op.C_in; ++ci) {
-      const uint8_t* row = op.x + ((size_t)b * op.C_in + ci) * op.x_ld;
-      for (int j = 0; j < op.k; ++j) {
-        const int ti = tin0 + j * op.dil;
-        if (ti >= 0 && ti < op.T_in) {
-          const unsigned code = row[ti];
-          const int q = op.in_unsigned ? (int)code : (int)(int8_t)code;
-          const int w = wrow[ci * op.k + j];
-          acc += w * q;
-          dacc += w * (int)lut[code];
-        }
-      }
+#pragma unroll 4
+    for (int ci = 0; ci < op.C_in; ++ci, p += op.x_ld) {
+      const uint32_t w4 = *reinterpret_cast<const uint32_t*>(p);
+      const int w = wrow[ci];
+      acc[0] += w * (int)(int8_t)(w4 & 0xff);
+      acc[1] += w * (int)(int8_t)((w4 >> 8) & 0xff);
+      acc[2] += w * (int)(int8_t)((w4 >> 16) & 0xff);
+      acc[3] += w * ((int)w4 >> 24);
     }
   }
 }
 
-__global__ void dyn_refine_kernel(const DynOp op0, const DynOp op1, int dual, int relu, const int32_t* out_lens, int B,
-                                  int C_out, int T_out, const int32_t* cand, uint32_t* absmax_bits) {
-  extern __shared__ int8_t wsm[];    // [2][wrow_len]
+__device__ __forceinline__ float literal_y(long long z, int dacc, float s_out) {
+  // f32(f64(acc) + bias + delta) * s_out  (quant_modules.py:305-307; .type(torch.float) of the float64 conv)
+  return __fmul_rn((float)((double)z + (double)dacc * (1.0 / 4194304.0)), s_out);
+}
+
+__global__ void dyn_refine_kernel(const qasr_stats* stats, const DynOp op0, const DynOp op1, int dual, int relu,
+                                  const int32_t* out_lens, int B, int C_out, int T_out, int32_t* cand_out,
+                                  uint32_t* absmax_bits) {
+  extern __shared__ int8_t wsm[];    // weights of the candidate channel: [n0][n1]
   __shared__ int8_t lut[2][256];
   __shared__ float sh[kRefThreads / 32];
-  const int c = cand[blockIdx.y];
-  if (c < 0) return;
+  __shared__ int s_count;
+  __shared__ Cand s_list[QASR_DYN_MAX_CAND];
   const int tid = threadIdx.x;
-  const int n0 = op0.depthwise ? op0.k : op0.C_in * op0.k;
-  const int n1 = dual ? (op1.depthwise ? op1.k : op1.C_in * op1.k) : 0;
-  for (int i = tid; i < n0; i += kRefThreads) wsm[i] = op0.w[(size_t)c * n0 + i];
-  for (int i = tid; i < n1; i += kRefThreads) wsm[n0 + i] = op1.w[(size_t)c * n1 + i];
+  select_candidates(stats, op0, op1, dual, relu, C_out, sh, &s_count, s_list);
+  const int ncand = min(s_count, QASR_DYN_MAX_CAND);
+  if (blockIdx.x == 0) {
+    if (tid < QASR_DYN_MAX_CAND) cand_out[tid] = tid < ncand ? s_list[tid].c : -1;
+    if (tid == 0) cand_out[QASR_DYN_MAX_CAND] = s_count;
+  }
+  if (ncand == 0) return;
   for (int i = tid; i < 256; i += kRefThreads) {
     lut[0][i] = (int8_t)noise_code(op0.in_unsigned ? i : (int)(int8_t)i, op0.s_x[0]);
     lut[1][i] = dual ? (int8_t)noise_code(op1.in_unsigned ? i : (int)(int8_t)i, op1.s_x[0]) : 0;
   }
-  __syncthreads();
-  const qasr_chan p0 = op0.ch[c];
-  qasr_chan p1 = p0;
-  if (dual) p1 = op1.ch[c];
+  const int n0 = op0.depthwise ? op0.k : op0.C_in * op0.k;
+  const int n1 = dual ? (op1.depthwise ? op1.k : op1.C_in * op1.k) : 0;
+  const bool pw0 = !op0.depthwise && op0.k == 1 && op0.stride == 1 && op0.pad == 0;
+  const bool pw1 = !dual || (!op1.depthwise && op1.k == 1 && op1.stride == 1 && op1.pad == 0);
+  const int tq = (T_out + 3) >> 2;
+  const long long groups = (long long)B * tq;
   float best = 0.0f;
-  const long long total = (long long)B * T_out;
-  for (long long pos = blockIdx.x * (long long)kRefThreads + tid; pos < total; pos += (long long)gridDim.x * kRefThreads) {
-    const int b = (int)(pos / T_out), t = (int)(pos - (long long)b * T_out);
-    const bool valid = !out_lens || t < out_lens[b];
-    long long acc, dacc;
-    refine_operand(op0, wsm, lut[0], c, b, t, valid, C_out, acc, dacc);
-    if (!valid) continue;
-    // f32(f64(acc) + bias + delta) * s_out  (quant_modules.py:305-307; .type(torch.float) of the float64 conv)
+  for (int ic = 0; ic < ncand; ++ic) {
+    const Cand cd = s_list[ic];
+    const int c = cd.c;
+    __syncthreads();
+    for (int i = tid; i < n0; i += kRefThreads) wsm[i] = op0.w[(size_t)c * n0 + i];
+    for (int i = tid; i < n1; i += kRefThreads) wsm[n0 + i] = op1.w[(size_t)c * n1 + i];
+    __syncthreads();
+    const qasr_chan p0 = op0.ch[c];
+    const qasr_chan p1 = dual ? op1.ch[c] : p0;
     const long long b0 = p0.bias == 2147483647 ? 2147483648LL : (long long)p0.bias;
-    float y = __fmul_rn((float)((double)(acc + b0) + (double)dacc * (1.0 / 4194304.0)), p0.s_out);
-    if (dual) {
-      long long acc1, dacc1;
-      refine_operand(op1, wsm + n0, lut[1], c, b, t, true, C_out, acc1, dacc1);
-      const long long b1 = p1.bias == 2147483647 ? 2147483648LL : (long long)p1.bias;
-      const float y1 = __fmul_rn((float)((double)(acc1 + b1) + (double)dacc1 * (1.0 / 4194304.0)), p1.s_out);
-      y = __fadd_rn(y1, y);                       // identity + x, quant_modules.py:108
-    } else if (relu) {
-      y = fmaxf(y, 0.0f);                         // jasper.py:661 / :687
+    const long long b1 = p1.bias == 2147483647 ? 2147483648LL : (long long)p1.bias;
+    for (long long gi = blockIdx.x * (long long)kRefThreads + tid; gi < groups; gi += (long long)gridDim.x * kRefThreads) {
+      const int b = (int)(gi / tq), t4 = 4 * (int)(gi - (long long)b * tq);
+      const int len = out_lens ? min(out_lens[b], T_out) : T_out;
+      if (t4 >= len) continue;
+      int a0[4], a1[4] = {0, 0, 0, 0};
+      if (pw0) conv4_pointwise(op0, wsm, b, t4, a0);
+      else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a0[u] = t4 + u < len ? conv_at(op0, wsm, c, b, t4 + u) : 0;
+      }
+      if (dual) {
+        if (pw1) conv4_pointwise(op1, wsm + n0, b, t4, a1);
+        else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) a1[u] = t4 + u < len ? conv_at(op1, wsm + n0, c, b, t4 + u) : 0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t4 + u;
+        if (t >= len) continue;
+        const long long z0 = (long long)a0[u] + b0;
+        if (!dual) {
+          const long long key = relu ? z0 : (z0 < 0 ? -z0 : z0);
+          if (key < cd.thr_z) continue;                       // cannot reach the channel's maximum even with the noise
+          float y = literal_y(z0, noise_at(op0, wsm, lut[0], c, b, t), p0.s_out);
+          if (relu) y = fmaxf(y, 0.0f);                       // jasper.py:661 / :687
+          best = fmaxf(best, fabsf(y));
+        } else {
+          const long long z1 = (long long)a1[u] + b1;
+          const float vh = __fadd_rn(__fmul_rn((float)z1, p1.s_out), __fmul_rn((float)z0, p0.s_out));
+          if (fabsf(vh) < cd.thr_f) continue;
+          const float y0 = literal_y(z0, noise_at(op0, wsm, lut[0], c, b, t), p0.s_out);
+          const float y1 = literal_y(z1, noise_at(op1, wsm + n0, lut[1], c, b, t), p1.s_out);
+          best = fmaxf(best, fabsf(__fadd_rn(y1, y0)));       // identity + x, quant_modules.py:108
+        }
+      }
     }
-    best = fmaxf(best, fabsf(y));
   }
   best = block_max(best, sh);
   if (tid == 0 && best > 0.0f) atomicMax(absmax_bits, __float_as_uint(best));
@@ -266,7 +313,24 @@ struct DynFin {
   unsigned long long* const* peer_slots;
   int rank, world, slot;
   uint32_t* seq;
+  const int32_t* prod_wabs[2];
+  int prod_qabs[2];
+  qasr_stats* stats;
+  int stats_C, stats_dual;
 };
+
+// May the all-integer epilogue ((z*m + 2^(e-1)) >> e) replace the literal float recipe for |z| <= bound?  Same proof as
+// qasr/plan.py fast_ok(): the float32 round trip of the accumulator is the identity (bound < 2^22), the shift is in the
+// fast path's range, the result fits, and no reachable z lands on an exact .5 tie.
+__device__ __forceinline__ bool fast_ok_dev(long long bound, int m, int e) {
+  if (bound >= (1 << 22)) return false;
+  if (m == 0) return true;
+  if (e < 32 || e > 62) return false;
+  if ((((unsigned long long)bound * (unsigned long long)m) >> e) >= (1ull << 30)) return false;
+  const int t = e - 1 - (__ffs(m) - 1);
+  if (t < 0) return false;
+  return t >= 62 || (1ll << t) > bound;
+}
 
 __global__ void dyn_finalize_kernel(const DynFin a) {
   __shared__ float s_scale;
@@ -325,8 +389,20 @@ __global__ void dyn_finalize_kernel(const DynFin a) {
     for (int c = threadIdx.x; c < a.prod_C[i]; c += blockDim.x) {
       int m, e;
       dyadic_dev(a.prod[i][c].s_out, s, m, e);
+      const int bias = a.prod[i][c].bias;
+      bool fast = false;
+      if (a.prod_wabs[i] != nullptr && bias != 2147483647) {
+        const long long bound = (long long)a.prod_wabs[i][c] * a.prod_qabs[i] + (bias < 0 ? -(long long)bias : (long long)bias);
+        fast = fast_ok_dev(bound, m, e);
+      }
       a.prod[i][c].m = m;
-      a.prod[i][c].e = e;
+      a.prod[i][c].e = fast ? e : (int)((unsigned)e | 0x80000000u);   // bit 31: literal recipe for this channel
+    }
+  }
+  if (a.stats != nullptr) {   // statistics records back to their reset state for the next forward
+    for (int c = threadIdx.x; c < a.stats_C; c += blockDim.x) {
+      a.stats[c].lo = a.stats_dual ? 0xffffffffLL : 0x7fffffffffffffffLL;
+      a.stats[c].hi = a.stats_dual ? 0LL : -0x7fffffffffffffffLL - 1;
     }
   }
   for (int i = 0; i < a.n_cons; ++i) {
@@ -432,21 +508,10 @@ int check_operand(const qasr_dyn_operand* o, const char* what) {
 
 }  // namespace
 
-extern "C" int qasr_dyn_select(qasr_stats* stats, const qasr_dyn_operand* op0, const qasr_dyn_operand* op1,
-                               int32_t relu, int32_t C_out, int32_t* cand, void* stream) {
-  QASR_CHECK_ARG(stats && op0 && cand && C_out > 0, "dyn_select: bad arguments");
-  int rc = check_operand(op0, "dyn_select");
-  if (rc) return rc;
-  if (op1 && (rc = check_operand(op1, "dyn_select"))) return rc;
-  dyn_select_kernel<<<1, kSelThreads, 0, (cudaStream_t)stream>>>(stats, make_op(op0), make_op(op1), op1 != nullptr, relu,
-                                                                 C_out, cand);
-  return qasr_check_launch("dyn_select_kernel");
-}
-
-extern "C" int qasr_dyn_refine(const qasr_dyn_operand* op0, const qasr_dyn_operand* op1, int32_t relu,
-                               const int32_t* out_lens, int32_t B, int32_t C_out, int32_t T_out, const int32_t* cand,
+extern "C" int qasr_dyn_refine(const qasr_stats* stats, const qasr_dyn_operand* op0, const qasr_dyn_operand* op1,
+                               int32_t relu, const int32_t* out_lens, int32_t B, int32_t C_out, int32_t T_out, int32_t* cand,
                                uint32_t* absmax_bits, void* stream) {
-  QASR_CHECK_ARG(op0 && cand && absmax_bits && B > 0 && C_out > 0 && T_out > 0, "dyn_refine: bad arguments");
+  QASR_CHECK_ARG(stats && op0 && cand && absmax_bits && B > 0 && C_out > 0 && T_out > 0, "dyn_refine: bad arguments");
   int rc = check_operand(op0, "dyn_refine");
   if (rc) return rc;
   if (op1 && (rc = check_operand(op1, "dyn_refine"))) return rc;
@@ -456,11 +521,11 @@ extern "C" int qasr_dyn_refine(const qasr_dyn_operand* op0, const qasr_dyn_opera
     qasr_set_error("dyn_refine: %d weights per output channel exceed the %d the kernel keeps in shared memory", n0 + n1, kMaxWRow);
     return QASR_ERR_UNSUPPORTED;
   }
-  long long blocks = ((long long)B * T_out + kRefThreads - 1) / kRefThreads;
-  const long long cap = 8LL * qasr_sm_count();
+  long long blocks = ((long long)B * ((T_out + 3) / 4) + kRefThreads - 1) / kRefThreads;
+  const long long cap = 4LL * qasr_sm_count();
   if (blocks > cap) blocks = cap;
-  dyn_refine_kernel<<<dim3((unsigned)blocks, QASR_DYN_MAX_CAND), kRefThreads, (size_t)(n0 + n1), (cudaStream_t)stream>>>(
-      make_op(op0), make_op(op1), op1 != nullptr, relu, out_lens, B, C_out, T_out, cand, absmax_bits);
+  dyn_refine_kernel<<<(unsigned)blocks, kRefThreads, (size_t)(n0 + n1), (cudaStream_t)stream>>>(
+      stats, make_op(op0), make_op(op1), op1 != nullptr, relu, out_lens, B, C_out, T_out, cand, absmax_bits);
   return qasr_check_launch("dyn_refine_kernel");
 }
 
@@ -484,6 +549,8 @@ extern "C" int qasr_dyn_finalize(const qasr_dyn_finalize_args* a, void* stream) 
   }
   f.peer_slots = reinterpret_cast<unsigned long long* const*>(a->peer_slots);
   f.rank = a->rank; f.world = a->world; f.slot = a->slot; f.seq = a->seq;
+  for (int i = 0; i < 2; ++i) { f.prod_wabs[i] = a->prod_wabs[i]; f.prod_qabs[i] = a->prod_qabs[i]; }
+  f.stats = a->stats; f.stats_C = a->stats_C; f.stats_dual = a->stats_dual;
   dyn_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(f);
   return qasr_check_launch("dyn_finalize_kernel");
 }

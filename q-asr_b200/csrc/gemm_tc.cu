@@ -85,6 +85,9 @@ struct GemmArgs {
 // EPI: bit 0 = all-integer fast epilogue, bits 1..3 (fast path only) = second conv operand,
 // previous-res_act addend, second requantisation stage.  EPI == 0 is the literal (runtime-flag) path.
 constexpr int kEpiFast = 1, kEpiDual = 2, kEpiPrev = 4, kEpiStage2 = 8, kEpiF32 = 16;
+// device-written tables (QASR_F_DEVICE_TABLES, dynamic quantisation): the integer fast path runs where qasr_dyn_finalize
+// proved it (per channel), the literal recipe elsewhere, decided per warp (its 32 rows never change)
+constexpr int kEpiDyn = 32;
 
 constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kAllocWarp = kEpiWarps + 2;
 
@@ -151,46 +154,71 @@ __device__ __forceinline__ void finish32(const GemmArgs& g, const EpiConsts& kc,
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (row_ok && tv + j < g.T_out) orow[tv + j] = epilogue_dequant(g.ep, a0[j], c0);
-    } else if (g.ep.mode == QASR_EPI_STATS) {
-      // statistics pass of dynamic quantisation: this lane's channel, the counted frames of its 32 columns
-      qasr_stats* st = reinterpret_cast<qasr_stats*>(g.out) + cc;
-      if (g.nseg == 1) {
-        long long lo = 0x7fffffffffffffffLL, hi = -0x7fffffffffffffffLL - 1;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (tv + j < len) {
-            const long long z = qasr_acc_bias64(a0[j], c0.bias);
-            lo = z < lo ? z : lo;
-            hi = z > hi ? z : hi;
-          }
-        }
-        if (row_ok && hi >= lo) {
-          atomicMin(reinterpret_cast<long long*>(&st->lo), lo);
-          atomicMax(reinterpret_cast<long long*>(&st->hi), hi);
-        }
-      } else {
-        unsigned lo = 0xffffffffu, hi = 0u;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (tv + j < len) {
-            const float y0 = __fmul_rn((float)qasr_acc_bias64(a0[j], c0.bias), c0.s);
-            const float y1 = __fmul_rn((float)qasr_acc_bias64(a1[j], c1.bias), c1.s);
-            const unsigned key = qasr_f32_key(__fadd_rn(y1, y0));     // identity + x, quant_modules.py:108
-            lo = key < lo ? key : lo;
-            hi = key > hi ? key : hi;
-          }
-        }
-        if (row_ok && hi >= lo) {
-          atomicMin(reinterpret_cast<unsigned*>(&st->lo), lo);
-          atomicMax(reinterpret_cast<unsigned*>(&st->hi), hi);
-        }
-      }
     } else {
       int32_t* orow = reinterpret_cast<int32_t*>(g.out) + row * g.out_ld;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (row_ok && tv + j < g.T_out) orow[tv + j] = a0[j] + c0.bias;
     }
+}
+
+
+// Statistics pass of dynamic quantisation (QASR_EPI_STATS): this lane's channel, the counted frames of its 32 columns,
+// folded into the lane's running extremes (flushed with one pair of atomics when the CTA is done).  One operand: int64
+// extremes of acc + bias; two operands: order-preserving keys of f32(acc1+b1)*s1 + f32(acc0+b0)*s0 (quant_modules.py:108).
+__device__ __forceinline__ void stats32(bool dual, const ChanRegs& c0, const ChanRegs& c1, int tv, int len, const int (&a0)[32],
+                                        const int (&a1)[32], long long& lo, long long& hi) {
+  if (!dual) {
+    if (c0.bias > -(1 << 30) && c0.bias < (1 << 30)) {     // |acc| < 2^30 always: 32-bit arithmetic is exact
+      int l = 2147483647, h = -2147483647 - 1;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (tv + j < len) {
+          const int z = a0[j] + c0.bias;
+          l = min(l, z);
+          h = max(h, z);
+        }
+      }
+      if (h >= l) {
+        lo = (long long)l < lo ? (long long)l : lo;
+        hi = (long long)h > hi ? (long long)h : hi;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (tv + j < len) {
+          const long long z = qasr_acc_bias64(a0[j], c0.bias);
+          lo = z < lo ? z : lo;
+          hi = z > hi ? z : hi;
+        }
+      }
+    }
+  } else {
+    unsigned l = (unsigned)lo, h = (unsigned)hi;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (tv + j < len) {
+        const float y0 = __fmul_rn((float)qasr_acc_bias64(a0[j], c0.bias), c0.s);
+        const float y1 = __fmul_rn((float)qasr_acc_bias64(a1[j], c1.bias), c1.s);
+        const unsigned key = qasr_f32_key(__fadd_rn(y1, y0));     // identity + x
+        l = min(l, key);
+        h = max(h, key);
+      }
+    }
+    lo = (long long)l;
+    hi = (long long)h;
+  }
+}
+__device__ __forceinline__ void stats_flush(bool dual, qasr_stats* st, long long lo, long long hi) {
+  if (!dual) {
+    if (hi >= lo) {
+      atomicMin(reinterpret_cast<long long*>(&st->lo), lo);
+      atomicMax(reinterpret_cast<long long*>(&st->hi), hi);
+    }
+  } else if ((unsigned)hi >= (unsigned)lo) {
+    atomicMin(reinterpret_cast<unsigned*>(&st->lo), (unsigned)lo);
+    atomicMax(reinterpret_cast<unsigned*>(&st->hi), (unsigned)hi);
+  }
 }
 
 template <int EPI>
@@ -385,6 +413,15 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     // float epilogue per warp: all 32 channels of this warp's rows proved (the rows never change)
     const bool warp_f32[2] = {__all_sync(0xffffffffu, c0[0].r != 0.0f) != 0, __all_sync(0xffffffffu, c0[1].r != 0.0f) != 0};
+    const bool warp_lit[2] = {__any_sync(0xffffffffu, c0[0].literal || c1[0].literal) != 0,
+                              __any_sync(0xffffffffu, c0[1].literal || c1[1].literal) != 0};
+    const bool stats_mode = EPI == 0 && g.ep.mode == QASR_EPI_STATS, stats_dual = g.nseg > 1;
+    long long st_lo[2], st_hi[2];
+#pragma unroll
+    for (int ms = 0; ms < 2; ++ms) {
+      st_lo[ms] = stats_dual ? 0xffffffffLL : 0x7fffffffffffffffLL;
+      st_hi[ms] = stats_dual ? 0LL : -0x7fffffffffffffffLL - 1;
+    }
     const uint32_t acc_per_stage = (uint32_t)(g.MT * g.nseg * BN);
     int as = 0;
     uint32_t aphase = 0;
@@ -401,6 +438,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // float or integer epilogue: a per-warp, per-M-tile constant (the warp's 32 rows never change)
     auto finish = [&](int ms, int b, int tv, int len, const int (&a0)[32], const int (&a1)[32]) {
       if (tv >= T_out) return;   // warp-uniform: this column group lies past the end of the utterance
+      if (stats_mode) { stats32(stats_dual, c0[ms], c1[ms], tv, len, a0, a1, st_lo[ms], st_hi[ms]); return; }
+      if ((EPI & kEpiDyn) && warp_lit[ms]) { finish32<0, false>(g, kc, c0[ms], c1[ms], row_ok[ms], cc[ms], b, tv, len, wide_ok, a0, a1); return; }
       if ((EPI & kEpiF32) || (EPI == kEpiFast && warp_f32[ms])) finish_t(std::true_type{}, ms, b, tv, len, a0, a1);
       else finish_t(std::false_type{}, ms, b, tv, len, a0, a1);
     };
@@ -444,6 +483,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+    if (stats_mode) {
+#pragma unroll
+      for (int ms = 0; ms < 2; ++ms)
+        if (row_ok[ms]) stats_flush(stats_dual, reinterpret_cast<qasr_stats*>(g.out) + cc[ms], st_lo[ms], st_hi[ms]);
     }
   }
 
@@ -679,6 +723,9 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const ChanRegs c0 = load_chan0(g.ep, cc);
     const ChanRegs c1 = nseg > 1 ? load_chan(g.ep.ch1, cc) : c0;
     const bool warp_f32 = __all_sync(0xffffffffu, c0.r != 0.0f) != 0;
+    const bool warp_lit = __any_sync(0xffffffffu, c0.literal || c1.literal) != 0;
+    const bool stats_mode = EPI == 0 && g.ep.mode == QASR_EPI_STATS, stats_dual = nseg > 1;
+    long long st_lo = stats_dual ? 0xffffffffLL : 0x7fffffffffffffffLL, st_hi = stats_dual ? 0LL : -0x7fffffffffffffffLL - 1;
     const uint32_t acc_per_stage = (uint32_t)(nseg * bn);
     const uint32_t ltempty0 = leader_addr(tempty_bar(0));   // the barriers are 8 bytes apart in the leader too
     int as = 0;
@@ -690,6 +737,8 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cgroup * chunks * 32);
     auto finish = [&](int b, int tv, int len, const int (&a0)[32], const int (&a1)[32]) {
       if (tv >= T_out) return;   // warp-uniform: past the end of the utterance
+      if (stats_mode) { stats32(stats_dual, c0, c1, tv, len, a0, a1, st_lo, st_hi); return; }
+      if ((EPI & kEpiDyn) && warp_lit) { finish32<0, false>(g, kc, c0, c1, row_ok, cc, b, tv, len, wide_ok, a0, a1); return; }
       if ((EPI & kEpiF32) || (EPI == kEpiFast && warp_f32)) finish32<EPI, true>(g, kc, c0, c1, row_ok, cc, b, tv, len, wide_ok, a0, a1);
       else finish32<EPI, false>(g, kc, c0, c1, row_ok, cc, b, tv, len, wide_ok, a0, a1);
     };
@@ -731,6 +780,7 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       }
       if (++as == nbuf) { as = 0; aphase ^= 1u; }
     }
+    if (stats_mode && row_ok) stats_flush(stats_dual, reinterpret_cast<qasr_stats*>(g.out) + cc, st_lo, st_hi);
   }
 
   tc_fence_before();
@@ -914,6 +964,10 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   if (fast)
     variant = kEpiFast | (op1 ? kEpiDual : 0) | (epi->prev ? kEpiPrev : 0) | ((epi->flags & QASR_F_STAGE2) ? kEpiStage2 : 0);
   if (fast && (epi->flags & QASR_F_FAST_F32)) variant = kEpiFast | kEpiF32;
+  // dynamic quantisation: the tables come from the device, the literal flags stay set for the channels whose fast path
+  // qasr_dyn_finalize could not prove; everything else runs the integer fast path
+  if ((epi->flags & QASR_F_DEVICE_TABLES) && epi->mode == QASR_EPI_REQUANT_I8 && !epi->prev && !(epi->flags & QASR_F_STAGE2))
+    variant = kEpiFast | kEpiDyn | (op1 ? kEpiDual : 0);
   // CTA-pair kernel (tcgen05 cta_group::2): an even number of M tiles keep their weights resident one tile per CTA;
   // halves the shared-memory operand reads per MMA so TMA writes and MMA reads stop time-sharing the port.
   // Bit-exact on every GEMM test.  Its loads + MMAs run faster than the 1-CTA kernel's (11.4 us against 13.2 us,
@@ -958,7 +1012,7 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
     g.n_step = pairs_per_group;
     const int pair_grid = 2 * pairs_per_group * g.m_groups;
     cudaStream_t pst = (cudaStream_t)stream;
-    static bool pair_attr_set[32][64] = {};
+    static bool pair_attr_set[64][64] = {};
     int pdev = 0;
     QASR_CHECK_CUDA(cudaGetDevice(&pdev));
     const bool pneed = pdev >= 0 && pdev < 64 && !pair_attr_set[variant][pdev];
@@ -981,6 +1035,8 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
       QASR_PAIR_CASE(13)
       QASR_PAIR_CASE(15)
       QASR_PAIR_CASE(17)
+      QASR_PAIR_CASE(33)
+      QASR_PAIR_CASE(35)
       default:
         qasr_set_error("conv1d_gemm: internal: no pair kernel variant %d", variant);
         return QASR_ERR_INVALID;
@@ -995,7 +1051,7 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   g.n_step = per_group;
   const int grid = per_group * g.m_groups;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set[32][64] = {};
+  static bool attr_set[64][64] = {};
   int dev = 0;
   QASR_CHECK_CUDA(cudaGetDevice(&dev));
   const bool need_attr = dev >= 0 && dev < 64 && !attr_set[variant][dev];
@@ -1018,6 +1074,8 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
     QASR_GEMM_CASE(13)
     QASR_GEMM_CASE(15)
     QASR_GEMM_CASE(17)
+    QASR_GEMM_CASE(33)
+    QASR_GEMM_CASE(35)
     default:
       qasr_set_error("conv1d_gemm: internal: no kernel variant %d", variant);
       return QASR_ERR_INVALID;

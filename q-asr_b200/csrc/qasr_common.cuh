@@ -147,6 +147,8 @@ struct ChanRegs {
   int sh;               // fast path: e - 32 (host guarantees 32 <= e <= 62)
   long long add;        // fast path: bias * m + 2^(e-1)
   float r;              // float fast path: f32(m * 2^-e), or 0 when only the integer path is proved
+  bool literal;         // device-written tables only (QASR_F_DEVICE_TABLES): the integer fast path is NOT proved for
+                        // this channel (bit 31 of the record's e, set by qasr_dyn_finalize)
 };
 
 __device__ __forceinline__ ChanRegs load_chan(const qasr_chan* p, int c) {
@@ -155,7 +157,8 @@ __device__ __forceinline__ ChanRegs load_chan(const qasr_chan* p, int c) {
   r.s = __int_as_float(v.x);
   r.bias = v.y;
   r.m = v.z;
-  r.e = v.w;
+  r.e = v.w & 0x7fffffff;
+  r.literal = v.w < 0;
   r.mult = dyad_mult(r.m, r.e);
   r.sh = max(r.e - 32, 0);
   r.add = (long long)r.bias * (long long)r.m + ((r.e >= 1 && r.e <= 62) ? (1ll << (r.e - 1)) : 0ll);

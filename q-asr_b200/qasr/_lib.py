@@ -61,6 +61,8 @@ class DynFinalizeArgs(C.Structure):
         ("cons_sw", C.c_void_p * 2), ("cons_bias", C.c_void_p * 2), ("cons_C", C.c_int32 * 2),
         ("peer_slots", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32), ("slot", C.c_int32),
         ("seq", C.c_void_p),
+        ("prod_wabs", C.c_void_p * 2), ("prod_qabs", C.c_int32 * 2),
+        ("stats", C.c_void_p), ("stats_C", C.c_int32), ("stats_dual", C.c_int32),
     ]
 
 
@@ -101,9 +103,8 @@ _SIGS = {
                                    _i32, _i32, _vp]),
     "qasr_normalize_features_f32": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "qasr_ctc_collapse": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
-    "qasr_dyn_select": (C.c_int, [_vp, C.POINTER(DynOperand), C.POINTER(DynOperand), _i32, _i32, _vp, _vp]),
-    "qasr_dyn_refine": (C.c_int, [C.POINTER(DynOperand), C.POINTER(DynOperand), _i32, _vp, _i32, _i32, _i32, _vp, _vp,
-                                  _vp]),
+    "qasr_dyn_refine": (C.c_int, [_vp, C.POINTER(DynOperand), C.POINTER(DynOperand), _i32, _vp, _i32, _i32, _i32, _vp,
+                                  _vp, _vp]),
     "qasr_dyn_finalize": (C.c_int, [C.POINTER(DynFinalizeArgs), _vp]),
     "qasr_minmax_i8": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "qasr_requant_i8_dev": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),

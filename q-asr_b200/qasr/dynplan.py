@@ -6,9 +6,10 @@ host.  This plan keeps the whole forward on the device and int8-resident anyway:
 
   per conv -> consumer QuantAct                                            kernels
     statistics pass     conv with QASR_EPI_STATS (no tensor written)       dwconv / tcgen05 GEMM
-    candidate channels  rigorous bounds on max |y| per channel             qasr_dyn_select
-    exact absmax        candidate channels with the reference's float      qasr_dyn_refine
-                        noise (quant_modules.py:301), position by position
+    exact absmax        rigorous bounds on max |y| per channel pick the    qasr_dyn_refine
+                        candidate channels; those again, position by
+                        position, with the reference's float noise
+                        (quant_modules.py:301)
     range -> scale ->   (m, e) of the producer, s_out / b_int of the       qasr_dyn_finalize
                         consumer convs; under data parallelism the ranks'
                         absmax values meet here through peer memory
@@ -255,7 +256,9 @@ class DynamicPlan:
                                                 C.byref(ep), L.stream_ptr()))
             self._add("gemm_%dx%d_%s" % (conv0.C_in, conv0.C_out, name), run, keep=(ep, g0, g1, out))
 
-    def _finalize(self, kind, src, src_scale, bit, act_scale, prods, prev, cons):
+    def _finalize(self, kind, src, src_scale, bit, act_scale, prods, prev, cons, prod_srcs=(), stats=None):
+        """prods: convs whose (m, e) this range completes (prod_srcs: their input codes, for the fast-path proof);
+        cons: convs that read the new codes; stats: (conv, dual) whose statistics records go back to the reset state."""
         a = L.DynFinalizeArgs()
         a.src_kind, a.src = kind, src.data_ptr()
         a.src_scale = src_scale.data_ptr() if src_scale is not None else None
@@ -264,6 +267,9 @@ class DynamicPlan:
         a.n_prod = len(prods)
         for i, c in enumerate(prods):
             a.prod[i], a.prod_C[i] = c.table.data_ptr(), c.C_out
+            a.prod_wabs[i], a.prod_qabs[i] = c.wabs.data_ptr(), 255 if prod_srcs[i].unsigned else 128
+        if stats is not None:
+            a.stats, a.stats_C, a.stats_dual = stats[0].stats.data_ptr(), stats[0].C_out, int(stats[1])
         if prev is not None:
             a.prev_scale, a.prev_me = prev[0].data_ptr(), prev[1].data_ptr()
         a.n_cons = len(cons)
@@ -302,10 +308,9 @@ class DynamicPlan:
         p1 = C.byref(o1) if o1 is not None else None
         absmax = self._scalar(torch.int32)
         stats, cand, B = conv0.stats, conv0.cand, self.B
-        self._add("select", lambda: L.check(lib.qasr_dyn_select(L.ptr(stats), C.byref(o0), p1, int(relu), conv0.C_out,
-                                                                L.ptr(cand), L.stream_ptr())), keep=(o0, o1))
-        self._add("refine", lambda: L.check(lib.qasr_dyn_refine(C.byref(o0), p1, int(relu), L.ptr(lens), B, conv0.C_out, T_out,
-                                                                L.ptr(cand), L.ptr(absmax), L.stream_ptr())), keep=(o0, o1, lens))
+        self._add("refine", lambda: L.check(lib.qasr_dyn_refine(L.ptr(stats), C.byref(o0), p1, int(relu), L.ptr(lens), B,
+                                                                conv0.C_out, T_out, L.ptr(cand), L.ptr(absmax),
+                                                                L.stream_ptr())), keep=(o0, o1, lens))
         return absmax
 
     def _emit_single(self, conv, src, relu, bit, masked, cons, T_out, stage):
@@ -315,7 +320,7 @@ class DynamicPlan:
             raise NotImplementedError("activation codes wider than 8 bits")
         absmax = self._range_of("conv", conv, src, None, None, relu, masked, T_out, stage)
         scale = self._scalar()
-        self._finalize(0, absmax, None, bit, scale, prods=[conv], prev=None, cons=cons)
+        self._finalize(0, absmax, None, bit, scale, prods=[conv], prev=None, cons=cons, prod_srcs=[src], stats=(conv, False))
         out = ops.alloc_codes(self.B, conv.C_out, T_out, self.device)
         lens = self.lens[stage] if masked else None
         flags = (L.F_DEVICE_TABLES | L.F_EXACT_F32 | L.F_EXACT_DYAD | L.F_BIAS64 | (L.F_RELU0 if relu else 0) |
@@ -331,7 +336,8 @@ class DynamicPlan:
             raise NotImplementedError("res_act wider than 8 bits")
         absmax = self._range_of("res_act", conv, src, rconv, rsrc, False, False, T_out, stage)
         scale = self._scalar()
-        self._finalize(0, absmax, None, ra_bit, scale, prods=[conv, rconv], prev=None, cons=[])
+        self._finalize(0, absmax, None, ra_bit, scale, prods=[conv, rconv], prev=None, cons=[], prod_srcs=[src, rsrc],
+                       stats=(conv, True))
         out = ops.alloc_codes(self.B, conv.C_out, T_out, self.device)
         flags = (L.F_DEVICE_TABLES | L.F_EXACT_F32 | L.F_EXACT_DYAD | L.F_BIAS64 | (0 if src.unsigned else L.F_B_SIGNED) |
                  (0 if rsrc.unsigned else L.F_B1_SIGNED))

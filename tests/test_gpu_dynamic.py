@@ -1,6 +1,6 @@
 """GPU: dynamic quantisation on the device (qasr.dynplan, csrc/dynamic.cu) -- BASELINE config 4's mode.
 
-Kernel level: statistics pass -> qasr_dyn_select -> qasr_dyn_refine -> qasr_dyn_finalize -> requantising pass of one
+Kernel level: statistics pass -> qasr_dyn_refine -> qasr_dyn_finalize -> requantising pass of one
 conv (and of the two-conv res_act tail) against a numpy restatement of the reference's literal arithmetic
 (quant_modules.py:149-156 ranges on floats that carry the un-rounded x / s noise of :301).
 Network level: the fused dynamic plan against the golden vectors of the unmodified reference and against the oracle
@@ -78,13 +78,16 @@ class DevConv:
                                                 ops.round_up(T_out, 16), B, self.C_out, T_out, C.byref(ep), L.stream_ptr()))
 
 
-def finalize(kind, src, bit, act_scale, prods=(), cons=(), src_scale=None, prev=None):
+def finalize(kind, src, bit, act_scale, prods=(), cons=(), src_scale=None, prev=None, qabs=(), stats=None):
     a = L.DynFinalizeArgs()
     a.src_kind, a.src, a.n_levels, a.act_scale = kind, src.data_ptr(), 2 ** (bit - 1) - 1, act_scale.data_ptr()
     a.src_scale = None if src_scale is None else src_scale.data_ptr()
     a.n_prod = len(prods)
     for i, c in enumerate(prods):
         a.prod[i], a.prod_C[i] = c.table.data_ptr(), c.C_out
+        a.prod_wabs[i], a.prod_qabs[i] = c.wabs.data_ptr(), qabs[i]
+    if stats is not None:
+        a.stats, a.stats_C, a.stats_dual = stats[0].stats.data_ptr(), stats[0].C_out, int(stats[1])
     if prev is not None:
         a.prev_scale, a.prev_me = prev[0].data_ptr(), prev[1].data_ptr()
     a.n_cons = len(cons)
@@ -158,21 +161,24 @@ def test_dynamic_range_of_one_conv(case):
     del accv
     op = conv.operand(x, T, not in_signed, sx_dev)
     absmax_dev = torch.zeros(1, dtype=torch.int32, device=DEV)
-    L.check(L.lib().qasr_dyn_select(L.ptr(conv.stats), C.byref(op), None, int(relu), co, L.ptr(conv.cand), L.stream_ptr()))
+    L.check(L.lib().qasr_dyn_refine(L.ptr(conv.stats), C.byref(op), None, int(relu), L.ptr(lens_d) if masked else None, B, co,
+                                    T_out, L.ptr(conv.cand), L.ptr(absmax_dev), L.stream_ptr()))
     cand = conv.cand.cpu().numpy()
     assert 1 <= cand[4] <= 4, cand
     per_ch = np.abs(np.where(valid, y, F32(0))).max(axis=(0, 2))
     assert int(np.argmax(per_ch)) in cand[:4].tolist()
+    assert absmax_dev.cpu().numpy().view(F32)[0] == absmax
+    finalize(0, absmax_dev, bit, sz_dev, prods=[conv], qabs=[128 if in_signed else 255], stats=(conv, False))
     st = conv.stats.cpu().numpy()
     assert (st[:, 0] == 2 ** 63 - 1).all() and (st[:, 1] == -2 ** 63).all()      # reset for the next forward
-    L.check(L.lib().qasr_dyn_refine(C.byref(op), None, int(relu), L.ptr(lens_d) if masked else None, B, co, T_out,
-                                    L.ptr(conv.cand), L.ptr(absmax_dev), L.stream_ptr()))
-    assert absmax_dev.cpu().numpy().view(F32)[0] == absmax
-    finalize(0, absmax_dev, bit, sz_dev, prods=[conv])
     assert sz_dev.cpu().numpy()[0] == s_z
     assert int(absmax_dev.item()) == 0
     tab = conv.table.cpu().numpy()
-    assert np.array_equal(tab[:, 2], m) and np.array_equal(tab[:, 3], e)
+    from qasr import plan as P
+    bound = np.abs(w).reshape(co, -1).sum(1) * (128 if in_signed else 255) + (0 if b_int is None else np.abs(b_int))
+    lit = np.array([not P.fast_ok(int(bound[c]), m[c:c + 1], e[c:c + 1]) for c in range(co)])
+    assert np.array_equal(tab[:, 2], m) and np.array_equal(tab[:, 3] & 0x7fffffff, e)
+    assert np.array_equal(tab[:, 3] < 0, lit), "device-side fast-path proof differs from qasr.plan.fast_ok"
     out = ops.alloc_codes(B, co, T_out, DEV)
     flags = (L.F_DEVICE_TABLES | L.F_EXACT_F32 | L.F_EXACT_DYAD | L.F_BIAS64 | (L.F_RELU0 if relu else 0) |
              (L.F_MASK if masked else 0) | (L.F_B_SIGNED if in_signed else 0))
@@ -221,14 +227,13 @@ def test_dynamic_range_of_res_act(shape):
     c0.launch(x0, T, c0.stats, T, ep, other=c1, x1=x1, T1=T)
     o0, o1 = c0.operand(x0, T, False, sx0_d), c1.operand(x1, T, True, sx1_d)
     absmax_dev = torch.zeros(1, dtype=torch.int32, device=DEV)
-    L.check(L.lib().qasr_dyn_select(L.ptr(c0.stats), C.byref(o0), C.byref(o1), 0, co, L.ptr(c0.cand), L.stream_ptr()))
+    L.check(L.lib().qasr_dyn_refine(L.ptr(c0.stats), C.byref(o0), C.byref(o1), 0, None, B, co, T, L.ptr(c0.cand),
+                                    L.ptr(absmax_dev), L.stream_ptr()))
     cand = c0.cand.cpu().numpy()
     assert 1 <= cand[4] <= 4, cand
     assert int(np.argmax(np.abs((y1 + y0).astype(F32)).max(axis=(0, 2)))) in cand[:4].tolist()
-    L.check(L.lib().qasr_dyn_refine(C.byref(o0), C.byref(o1), 0, None, B, co, T, L.ptr(c0.cand), L.ptr(absmax_dev),
-                                    L.stream_ptr()))
     assert absmax_dev.cpu().numpy().view(F32)[0] == absmax
-    finalize(0, absmax_dev, 8, sra_d, prods=[c0, c1])
+    finalize(0, absmax_dev, 8, sra_d, prods=[c0, c1], qabs=[128, 255], stats=(c0, True))
     assert sra_d.cpu().numpy()[0] == s_ra
     ra = ops.alloc_codes(B, co, T, DEV)
     flags = L.F_DEVICE_TABLES | L.F_EXACT_F32 | L.F_EXACT_DYAD | L.F_BIAS64 | L.F_B_SIGNED
