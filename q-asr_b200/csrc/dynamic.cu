@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int kRefThreads = 128;
+constexpr int kRefThreads = 256;   // 8 warps: pointwise convs split their input channels over the warps
 constexpr int kMaxWRow = 8192;   // weights of one output channel kept in shared memory by dyn_refine
 
 struct DynOp {   // by-value kernel copy of qasr_dyn_operand
@@ -166,13 +166,14 @@ __device__ __forceinline__ int noise_at(const DynOp& op, const int8_t* wrow, con
   }
   return dacc;
 }
-// four consecutive output frames of a 1x1 stride-1 conv: one 32-bit load per input channel
-__device__ __forceinline__ void conv4_pointwise(const DynOp& op, const int8_t* wrow, int b, int t4, int (&acc)[4]) {
+// four consecutive output frames of a 1x1 stride-1 conv over input channels [ci0, ci1): one 32-bit load per channel
+__device__ __forceinline__ void conv4_pointwise(const DynOp& op, const int8_t* wrow, int b, int t4, int ci0, int ci1,
+                                                int (&acc)[4]) {
   acc[0] = acc[1] = acc[2] = acc[3] = 0;
-  const uint8_t* p = op.x + (size_t)b * op.C_in * op.x_ld + t4;
+  const uint8_t* p = op.x + ((size_t)b * op.C_in + ci0) * op.x_ld + t4;
   if (op.in_unsigned) {
-#pragma unroll 4
-    for (int ci = 0; ci < op.C_in; ++ci, p += op.x_ld) {
+#pragma unroll 8
+    for (int ci = ci0; ci < ci1; ++ci, p += op.x_ld) {
       const uint32_t w4 = *reinterpret_cast<const uint32_t*>(p);
       const int w = wrow[ci];
       acc[0] += w * (int)(w4 & 0xff);
@@ -181,8 +182,8 @@ __device__ __forceinline__ void conv4_pointwise(const DynOp& op, const int8_t* w
       acc[3] += w * (int)(w4 >> 24);
     }
   } else {
-#pragma unroll 4
-    for (int ci = 0; ci < op.C_in; ++ci, p += op.x_ld) {
+#pragma unroll 8
+    for (int ci = ci0; ci < ci1; ++ci, p += op.x_ld) {
       const uint32_t w4 = *reinterpret_cast<const uint32_t*>(p);
       const int w = wrow[ci];
       acc[0] += w * (int)(int8_t)(w4 & 0xff);
@@ -206,6 +207,7 @@ __global__ void dyn_refine_kernel(const qasr_stats* stats, const DynOp op0, cons
   __shared__ float sh[kRefThreads / 32];
   __shared__ int s_count;
   __shared__ Cand s_list[QASR_DYN_MAX_CAND];
+  __shared__ int part[2][8][32][4];
   const int tid = threadIdx.x;
   select_candidates(stats, op0, op1, dual, relu, C_out, sh, &s_count, s_list);
   const int ncand = min(s_count, QASR_DYN_MAX_CAND);
@@ -236,41 +238,61 @@ __global__ void dyn_refine_kernel(const qasr_stats* stats, const DynOp op0, cons
     const qasr_chan p1 = dual ? op1.ch[c] : p0;
     const long long b0 = p0.bias == 2147483647 ? 2147483648LL : (long long)p0.bias;
     const long long b1 = p1.bias == 2147483647 ? 2147483648LL : (long long)p1.bias;
-    for (long long gi = blockIdx.x * (long long)kRefThreads + tid; gi < groups; gi += (long long)gridDim.x * kRefThreads) {
-      const int b = (int)(gi / tq), t4 = 4 * (int)(gi - (long long)b * tq);
-      const int len = out_lens ? min(out_lens[b], T_out) : T_out;
-      if (t4 >= len) continue;
-      int a0[4], a1[4] = {0, 0, 0, 0};
-      if (pw0) conv4_pointwise(op0, wsm, b, t4, a0);
-      else {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) a0[u] = t4 + u < len ? conv_at(op0, wsm, c, b, t4 + u) : 0;
+    // the noise term only where the position can win; returns |x_act| of that position or 0
+    auto judge = [&](int b, int t, int acc0, int acc1) -> float {
+      const long long z0 = (long long)acc0 + b0;
+      if (!dual) {
+        const long long key = relu ? z0 : (z0 < 0 ? -z0 : z0);
+        if (key < cd.thr_z) return 0.0f;                      // cannot reach the channel's maximum even with the noise
+        float y = literal_y(z0, noise_at(op0, wsm, lut[0], c, b, t), p0.s_out);
+        if (relu) y = fmaxf(y, 0.0f);                         // jasper.py:661 / :687
+        return fabsf(y);
       }
-      if (dual) {
-        if (pw1) conv4_pointwise(op1, wsm + n0, b, t4, a1);
-        else {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) a1[u] = t4 + u < len ? conv_at(op1, wsm + n0, c, b, t4 + u) : 0;
+      const long long z1 = (long long)acc1 + b1;
+      const float vh = __fadd_rn(__fmul_rn((float)z1, p1.s_out), __fmul_rn((float)z0, p0.s_out));
+      if (fabsf(vh) < cd.thr_f) return 0.0f;
+      const float y0 = literal_y(z0, noise_at(op0, wsm, lut[0], c, b, t), p0.s_out);
+      const float y1 = literal_y(z1, noise_at(op1, wsm + n0, lut[1], c, b, t), p1.s_out);
+      return fabsf(__fadd_rn(y1, y0));                        // identity + x, quant_modules.py:108
+    };
+    if (pw0 && pw1) {
+      // pointwise operands: 32 position groups (4 frames each) per round, the input channels split over the 8 warps,
+      // partial sums meet in shared memory
+      const int lane = tid & 31, warp = tid >> 5;
+      const int cps0 = (op0.C_in + 7) >> 3, cps1 = dual ? (op1.C_in + 7) >> 3 : 0;
+      for (long long gbase = (long long)blockIdx.x * 32; gbase < groups; gbase += (long long)gridDim.x * 32) {
+        const long long gi = gbase + lane;
+        const bool live = gi < groups;
+        const int b = live ? (int)(gi / tq) : 0, t4 = live ? 4 * (int)(gi - (long long)b * tq) : 0;
+        const int len = out_lens ? min(out_lens[b], T_out) : T_out;
+        int a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+        if (live && t4 < len) {
+          conv4_pointwise(op0, wsm, b, t4, min(warp * cps0, op0.C_in), min((warp + 1) * cps0, op0.C_in), a0);
+          if (dual) conv4_pointwise(op1, wsm + n0, b, t4, min(warp * cps1, op1.C_in), min((warp + 1) * cps1, op1.C_in), a1);
         }
-      }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int t = t4 + u;
-        if (t >= len) continue;
-        const long long z0 = (long long)a0[u] + b0;
-        if (!dual) {
-          const long long key = relu ? z0 : (z0 < 0 ? -z0 : z0);
-          if (key < cd.thr_z) continue;                       // cannot reach the channel's maximum even with the noise
-          float y = literal_y(z0, noise_at(op0, wsm, lut[0], c, b, t), p0.s_out);
-          if (relu) y = fmaxf(y, 0.0f);                       // jasper.py:661 / :687
-          best = fmaxf(best, fabsf(y));
-        } else {
-          const long long z1 = (long long)a1[u] + b1;
-          const float vh = __fadd_rn(__fmul_rn((float)z1, p1.s_out), __fmul_rn((float)z0, p0.s_out));
-          if (fabsf(vh) < cd.thr_f) continue;
-          const float y0 = literal_y(z0, noise_at(op0, wsm, lut[0], c, b, t), p0.s_out);
-          const float y1 = literal_y(z1, noise_at(op1, wsm + n0, lut[1], c, b, t), p1.s_out);
-          best = fmaxf(best, fabsf(__fadd_rn(y1, y0)));       // identity + x, quant_modules.py:108
+        for (int u = 0; u < 4; ++u) { part[0][warp][lane][u] = a0[u]; part[1][warp][lane][u] = a1[u]; }
+        __syncthreads();
+        if (warp == 0 && live && t4 < len) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            int s0 = 0, s1 = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { s0 += part[0][w][lane][u]; s1 += part[1][w][lane][u]; }
+            if (t4 + u < len) best = fmaxf(best, judge(b, t4 + u, s0, s1));
+          }
+        }
+        __syncthreads();
+      }
+    } else {
+      for (long long gi = blockIdx.x * (long long)kRefThreads + tid; gi < groups; gi += (long long)gridDim.x * kRefThreads) {
+        const int b = (int)(gi / tq), t4 = 4 * (int)(gi - (long long)b * tq);
+        const int len = out_lens ? min(out_lens[b], T_out) : T_out;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t4 + u;
+          if (t >= len) continue;
+          best = fmaxf(best, judge(b, t, conv_at(op0, wsm, c, b, t), dual ? conv_at(op1, wsm + n0, c, b, t) : 0));
         }
       }
     }
@@ -521,7 +543,10 @@ extern "C" int qasr_dyn_refine(const qasr_stats* stats, const qasr_dyn_operand* 
     qasr_set_error("dyn_refine: %d weights per output channel exceed the %d the kernel keeps in shared memory", n0 + n1, kMaxWRow);
     return QASR_ERR_UNSUPPORTED;
   }
-  long long blocks = ((long long)B * ((T_out + 3) / 4) + kRefThreads - 1) / kRefThreads;
+  const bool pointwise = !op0->depthwise && op0->k == 1 && op0->stride == 1 && op0->pad == 0 &&
+                         (!op1 || (!op1->depthwise && op1->k == 1 && op1->stride == 1 && op1->pad == 0));
+  const long long per_block = pointwise ? 32 : kRefThreads;   // position groups of 4 frames per block and round
+  long long blocks = ((long long)B * ((T_out + 3) / 4) + per_block - 1) / per_block;
   const long long cap = 4LL * qasr_sm_count();
   if (blocks > cap) blocks = cap;
   dyn_refine_kernel<<<(unsigned)blocks, kRefThreads, (size_t)(n0 + n1), (cudaStream_t)stream>>>(

@@ -308,7 +308,8 @@ class DynamicPlan:
         p1 = C.byref(o1) if o1 is not None else None
         absmax = self._scalar(torch.int32)
         stats, cand, B = conv0.stats, conv0.cand, self.B
-        self._add("refine", lambda: L.check(lib.qasr_dyn_refine(L.ptr(stats), C.byref(o0), p1, int(relu), L.ptr(lens), B,
+        kind = "dual" if conv1 is not None else ("dw" if conv0.depthwise else "pw")
+        self._add("refine_" + kind, lambda: L.check(lib.qasr_dyn_refine(L.ptr(stats), C.byref(o0), p1, int(relu), L.ptr(lens), B,
                                                                 conv0.C_out, T_out, L.ptr(cand), L.ptr(absmax),
                                                                 L.stream_ptr())), keep=(o0, o1, lens))
         return absmax
