@@ -19,7 +19,8 @@
 namespace {
 
 constexpr int kRefThreads = 256;   // 8 warps: pointwise convs split their input channels over the warps
-constexpr int kMaxWRow = 8192;   // weights of one output channel kept in shared memory by dyn_refine
+constexpr int kMaxWRow = 8192;
+constexpr int kMaxHits = 64;      // positions per block and candidate channel whose noise term is evaluated by the whole block   // weights of one output channel kept in shared memory by dyn_refine
 
 struct DynOp {   // by-value kernel copy of qasr_dyn_operand
   const uint8_t* x;
@@ -166,6 +167,27 @@ __device__ __forceinline__ int noise_at(const DynOp& op, const int8_t* wrow, con
   }
   return dacc;
 }
+// the same sum spread over the whole block (the taps of one output position are hundreds of different cache lines:
+// one thread walking them alone costs ~100 us); every thread returns the block-wide total
+__device__ int noise_block(const DynOp& op, const int8_t* wrow, const int8_t* lut, int c, int b, int t, int* red) {
+  const int n = op.depthwise ? op.k : op.C_in * op.k;
+  const int tin0 = t * op.stride - op.pad;
+  int part = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ci = op.depthwise ? c : i / op.k, j = op.depthwise ? i : i - (i / op.k) * op.k;
+    const int ti = tin0 + j * op.dil;
+    if (ti >= 0 && ti < op.T_in) part += (int)wrow[i] * (int)lut[op.x[((size_t)b * op.C_in + ci) * op.x_ld + ti]];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  int tot = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+  return tot;
+}
+
 // four consecutive output frames of a 1x1 stride-1 conv over input channels [ci0, ci1): one 32-bit load per channel
 __device__ __forceinline__ void conv4_pointwise(const DynOp& op, const int8_t* wrow, int b, int t4, int ci0, int ci1,
                                                 int (&acc)[4]) {
@@ -208,6 +230,8 @@ __global__ void dyn_refine_kernel(const qasr_stats* stats, const DynOp op0, cons
   __shared__ int s_count;
   __shared__ Cand s_list[QASR_DYN_MAX_CAND];
   __shared__ int part[2][8][32][4];
+  __shared__ int s_nhits, s_red[kRefThreads / 32];
+  __shared__ int4 s_hits[kMaxHits];   // (b, t, acc0, acc1) of the positions that can hold the maximum
   const int tid = threadIdx.x;
   select_candidates(stats, op0, op1, dual, relu, C_out, sh, &s_count, s_list);
   const int ncand = min(s_count, QASR_DYN_MAX_CAND);
@@ -238,22 +262,28 @@ __global__ void dyn_refine_kernel(const qasr_stats* stats, const DynOp op0, cons
     const qasr_chan p1 = dual ? op1.ch[c] : p0;
     const long long b0 = p0.bias == 2147483647 ? 2147483648LL : (long long)p0.bias;
     const long long b1 = p1.bias == 2147483647 ? 2147483648LL : (long long)p1.bias;
-    // the noise term only where the position can win; returns |x_act| of that position or 0
-    auto judge = [&](int b, int t, int acc0, int acc1) -> float {
+    if (tid == 0) s_nhits = 0;
+    __syncthreads();
+    // can this position hold the channel's maximum once the noise is added?  (thresholds from select_candidates)
+    auto qualifies = [&](int acc0, int acc1) -> bool {
       const long long z0 = (long long)acc0 + b0;
-      if (!dual) {
-        const long long key = relu ? z0 : (z0 < 0 ? -z0 : z0);
-        if (key < cd.thr_z) return 0.0f;                      // cannot reach the channel's maximum even with the noise
-        float y = literal_y(z0, noise_at(op0, wsm, lut[0], c, b, t), p0.s_out);
-        if (relu) y = fmaxf(y, 0.0f);                         // jasper.py:661 / :687
-        return fabsf(y);
-      }
+      if (!dual) return (relu ? z0 : (z0 < 0 ? -z0 : z0)) >= cd.thr_z;
       const long long z1 = (long long)acc1 + b1;
-      const float vh = __fadd_rn(__fmul_rn((float)z1, p1.s_out), __fmul_rn((float)z0, p0.s_out));
-      if (fabsf(vh) < cd.thr_f) return 0.0f;
-      const float y0 = literal_y(z0, noise_at(op0, wsm, lut[0], c, b, t), p0.s_out);
-      const float y1 = literal_y(z1, noise_at(op1, wsm + n0, lut[1], c, b, t), p1.s_out);
-      return fabsf(__fadd_rn(y1, y0));                        // identity + x, quant_modules.py:108
+      return fabsf(__fadd_rn(__fmul_rn((float)z1, p1.s_out), __fmul_rn((float)z0, p0.s_out))) >= cd.thr_f;
+    };
+    // |x_act| of one position with the reference's float noise (quant_modules.py:301-309, :108)
+    auto literal = [&](int acc0, int acc1, int d0, int d1) -> float {
+      float y = literal_y((long long)acc0 + b0, d0, p0.s_out);
+      if (dual) y = __fadd_rn(literal_y((long long)acc1 + b1, d1, p1.s_out), y);      // identity + x
+      else if (relu) y = fmaxf(y, 0.0f);                                              // jasper.py:661 / :687
+      return fabsf(y);
+    };
+    // rare: park the position for the block-wide noise pass; a full list falls back to one thread walking the taps
+    auto judge = [&](int b, int t, int acc0, int acc1) -> float {
+      if (!qualifies(acc0, acc1)) return 0.0f;
+      const int slot = atomicAdd(&s_nhits, 1);
+      if (slot < kMaxHits) { s_hits[slot] = make_int4(b, t, acc0, acc1); return 0.0f; }
+      return literal(acc0, acc1, noise_at(op0, wsm, lut[0], c, b, t), dual ? noise_at(op1, wsm + n0, lut[1], c, b, t) : 0);
     };
     if (pw0 && pw1) {
       // pointwise operands: 32 position groups (4 frames each) per round, the input channels split over the 8 warps,
@@ -295,6 +325,14 @@ __global__ void dyn_refine_kernel(const qasr_stats* stats, const DynOp op0, cons
           best = fmaxf(best, judge(b, t, conv_at(op0, wsm, c, b, t), dual ? conv_at(op1, wsm + n0, c, b, t) : 0));
         }
       }
+    }
+    __syncthreads();
+    const int nh = min(s_nhits, kMaxHits);
+    for (int h = 0; h < nh; ++h) {
+      const int4 hit = s_hits[h];
+      const int d0 = noise_block(op0, wsm, lut[0], c, hit.x, hit.y, s_red);
+      const int d1 = dual ? noise_block(op1, wsm + n0, lut[1], c, hit.x, hit.y, s_red) : 0;
+      if (tid == 0) best = fmaxf(best, literal(hit.z, hit.w, d0, d1));
     }
   }
   best = block_max(best, sh);
