@@ -315,15 +315,12 @@ __global__ void dyn_refine_kernel(const qasr_stats* stats, const DynOp op0, cons
         __syncthreads();
       }
     } else {
-      for (long long gi = blockIdx.x * (long long)kRefThreads + tid; gi < groups; gi += (long long)gridDim.x * kRefThreads) {
-        const int b = (int)(gi / tq), t4 = 4 * (int)(gi - (long long)b * tq);
-        const int len = out_lens ? min(out_lens[b], T_out) : T_out;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int t = t4 + u;
-          if (t >= len) continue;
-          best = fmaxf(best, judge(b, t, conv_at(op0, wsm, c, b, t), dual ? conv_at(op1, wsm + n0, c, b, t) : 0));
-        }
+      // any other conv (depthwise k = 33..87, strided, dilated): one output frame per thread
+      const long long total = (long long)B * T_out;
+      for (long long pos = blockIdx.x * (long long)kRefThreads + tid; pos < total; pos += (long long)gridDim.x * kRefThreads) {
+        const int b = (int)(pos / T_out), t = (int)(pos - (long long)b * T_out);
+        if (out_lens && t >= out_lens[b]) continue;
+        best = fmaxf(best, judge(b, t, conv_at(op0, wsm, c, b, t), dual ? conv_at(op1, wsm + n0, c, b, t) : 0));
       }
     }
     __syncthreads();
@@ -583,8 +580,8 @@ extern "C" int qasr_dyn_refine(const qasr_stats* stats, const qasr_dyn_operand* 
   }
   const bool pointwise = !op0->depthwise && op0->k == 1 && op0->stride == 1 && op0->pad == 0 &&
                          (!op1 || (!op1->depthwise && op1->k == 1 && op1->stride == 1 && op1->pad == 0));
-  const long long per_block = pointwise ? 32 : kRefThreads;   // position groups of 4 frames per block and round
-  long long blocks = ((long long)B * ((T_out + 3) / 4) + per_block - 1) / per_block;
+  // per block and round: 32 groups of 4 frames (pointwise), else one frame per thread
+  long long blocks = pointwise ? ((long long)B * ((T_out + 3) / 4) + 31) / 32 : ((long long)B * T_out + kRefThreads - 1) / kRefThreads;
   const long long cap = 4LL * qasr_sm_count();
   if (blocks > cap) blocks = cap;
   dyn_refine_kernel<<<(unsigned)blocks, kRefThreads, (size_t)(n0 + n1), (cudaStream_t)stream>>>(

@@ -75,3 +75,10 @@ def peer_slots(device, n_slots=512):
             return out
         _slots[key] = dict(rank=rank, world=world, slots=dynplan.PeerSlots(rank, world, n_slots, device, gather))
     return _slots[key]
+
+
+def close_peer_slots():
+    """Unmap / free every peer-mapped slot table of this process (call before destroy_process_group)."""
+    for v in _slots.values():
+        v["slots"].close()
+    _slots.clear()
