@@ -420,6 +420,7 @@ def dynamic_dp(device, rank, world, distributed, steps=3):
                            "one NCCL MAX all-reduce of [-min, max] per QuantAct") if distributed else "none (one rank)",
                path=path)
     del model
+    qdist.close_peer_slots()
     torch.cuda.empty_cache()
     return out
 
