@@ -185,21 +185,22 @@ def in_graph_times(plan, flush, iters=5):
     whole span, and the ms covered by any kernel (union of the intervals), or None when the library has no stamps."""
     if not hasattr(plan, "profile_stamps"):
         return None
-    tot = None
+    tot, valid = None, None
     for _ in range(iters):
         flush()
-        st = plan.profile_stamps()          # (n_ops, 2) int64 nanoseconds, or None without library support
+        st = plan.profile_stamps()          # (n_ops, 2) int64 nanoseconds, (0, 0) for launches without a stamp
         if st is None:
             return None
-        st = st.astype(np.float64) - float(st[:, 0].min())
+        valid = st[:, 1] > 0
+        st = np.where(valid[:, None], st.astype(np.float64) - float(st[valid, 0].min()), 0.0)
         tot = st if tot is None else tot + st
     st = tot / iters
     dur = (st[:, 1] - st[:, 0]) / 1e6
     classes = {}
-    for (name, _), d in zip(plan.ops, dur):
-        c = classes.setdefault(op_class(plan, name), 0.0)
-        classes[op_class(plan, name)] = c + float(d)
-    order = np.argsort(st[:, 0])
+    for (name, _), d, ok in zip(plan.ops, dur, valid):
+        if ok:
+            classes[op_class(plan, name)] = classes.get(op_class(plan, name), 0.0) + float(d)
+    order = [i for i in np.argsort(st[:, 0]) if valid[i]]
     covered, cur_s, cur_e = 0.0, None, None
     for i in order:
         s, e = st[i]
@@ -210,7 +211,7 @@ def in_graph_times(plan, flush, iters=5):
         else:
             cur_e = max(cur_e, e)
     covered += cur_e - cur_s
-    return dict(classes=classes, span_ms=float(st[:, 1].max() - st[:, 0].min()) / 1e6, covered_ms=covered / 1e6)
+    return dict(classes=classes, span_ms=float(st[valid, 1].max() - st[valid, 0].min()) / 1e6, covered_ms=covered / 1e6)
 
 
 def oracle_for(model):
@@ -388,6 +389,8 @@ def dynamic_dp(device, rank, world, distributed, steps=3):
     logits_dp, greedy_dp = fwd(x, lens)
     logits_dp = logits_dp[:check_rows].clone()
     qdist.disable_data_parallel()
+    if distributed:
+        fwd(x, lens)                  # the shard-local plan is another plan: build / capture it outside the timing
     ms_local = timed(steps) if distributed else ms_dp   # same shard, ranges from the shard alone: no collective
     t = torch.tensor([ms_dp, ms_local], dtype=torch.float64, device=device)
     if distributed:
@@ -553,7 +556,9 @@ def run_ours(args):
     stamps = in_graph_times(plan, flush)
     step_ms_graph = total_ms / args.steps
     if stamps is not None:
-        kms = stamps["classes"]
+        kms = dict(stamps["classes"])
+        for k, v in classes.items():      # launches without a stamp (the input quantiser): eager figure
+            kms.setdefault(k, v["ms"])
         method = ("measured inside the step: an instrumented copy of the step's CUDA graph (same launches, same "
                   "programmatic-dependent-launch edges) in which every launch stamps %globaltimer at its first CTA's "
                   "start on activation data and at its last CTA's end; class time = sum over its launches of "

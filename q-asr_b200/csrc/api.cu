@@ -28,6 +28,30 @@ namespace { thread_local bool g_plain_launch = false; }
 void qasr_set_plain_launch(bool plain) { g_plain_launch = plain; }
 bool qasr_plain_launch() { return g_plain_launch; }
 
+namespace {
+unsigned long long* g_prof_buf = nullptr;
+int g_prof_cap = 0, g_prof_n = 0;
+}
+unsigned long long* qasr_next_stamp() {
+  if (g_prof_buf == nullptr || g_prof_n >= g_prof_cap) return nullptr;
+  return g_prof_buf + 2 * (g_prof_n++);
+}
+// stamps: device buffer of `capacity` (start, end) uint64 pairs; the caller resets every pair to (UINT64_MAX >> 1, 0)
+// before each run.  Launches issued (or captured into a CUDA graph) between begin and end carry their slot with them.
+extern "C" int qasr_profile_begin(void* stamps, int capacity) {
+  QASR_CHECK_ARG(stamps != nullptr && capacity > 0, "profile_begin: bad arguments");
+  g_prof_buf = static_cast<unsigned long long*>(stamps);
+  g_prof_cap = capacity;
+  g_prof_n = 0;
+  return QASR_OK;
+}
+extern "C" int qasr_profile_end(void) {
+  const int n = g_prof_n;
+  g_prof_buf = nullptr;
+  g_prof_cap = g_prof_n = 0;
+  return n;
+}
+
 void qasr_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

@@ -47,6 +47,7 @@ struct Args {
   int out_ld, out_nct, B, C_out, T_out;
   int nseg, t_tiles, c_tiles, total_tiles;
   Seg seg[2];
+  unsigned long long* stamp;   // in-graph timing slot (qasr_profile_begin) or nullptr
   EpiArgs ep;
 };
 
@@ -128,6 +129,7 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) qasr_stamp_begin(g.stamp);
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks with uniform values, one elected lane issues) =====================
@@ -288,6 +290,7 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) qasr_stamp_end(g.stamp);
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
@@ -423,6 +426,7 @@ extern "C" int qasr_conv1d_ntc_i8(const qasr_gemm_operand* op0, const qasr_gemm_
   g.c_tiles = (C_out + BN - 1) / BN;
   g.total_tiles = g.t_tiles * g.c_tiles * B;
   g.ep = make_epi_args(epi);
+  g.stamp = qasr_next_stamp();
   const bool fast = !(epi->flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64)) &&
                     epi->mode == QASR_EPI_REQUANT_I8;
   int variant = 0;

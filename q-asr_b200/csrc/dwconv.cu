@@ -52,6 +52,7 @@ struct DwArgs {
   int halo;       // zero bytes in front of the row inside a staging buffer (multiple of 16, >= pad + d)
   int copy_bytes; // T_in rounded up to 16: bytes of one bulk copy
   int buf_bytes;  // one staging buffer (multiple of 128)
+  unsigned long long* stamp;   // in-graph timing slot (qasr_profile_begin) or nullptr
   EpiArgs ep;
 };
 
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
   const EpiConsts kc = make_epi_consts(a.ep, false);
   pdl_wait();   // activations (and the output buffer) belong to the stream order; everything above is set-up
   if (lane == 0) {
+    qasr_stamp_begin(a.stamp);
     for (int r = 0; r < min(nrows, kBufs - 1); ++r)
       row_copy_async(smem_addr(bufs + r * a.buf_bytes + a.halo), xbase + r * xstep, a.copy_bytes,
                      smem_addr(bars + r));
@@ -318,6 +320,7 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
     else tiles(std::integral_constant<int, 2>{});
     __syncwarp();  // every lane is done reading this buffer before lane 0 refills it
   }
+  if (lane == 0) qasr_stamp_end(a.stamp);
   if (EK == 2 && a.ep.mode == QASR_EPI_STATS) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -518,6 +521,7 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
   a.bchunk = bchunk;
   a.nbg = (B + bchunk - 1) / bchunk;
   a.ep = make_epi_args(epi);
+  a.stamp = qasr_next_stamp();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
 #define QASR_DW_CASE(KS_)                                      \

@@ -72,6 +72,7 @@ struct DwTcArgs {
   uint32_t rows_bytes; // one piece buffer: bbox * row_pitch (two of them follow the A stages)
   unsigned long long* dbg_trace;   // qasr_debug_set 7: device buffer, role timeline of CTA 0 (3 x 256 slots)
   int dbg_skip;      // qasr_debug_set 6: 1 = epilogue does nothing, 2 = no MMA issue, 4 = no stores, 8 = no Tc rebuild
+  unsigned long long* stamp;   // in-graph timing slot (qasr_profile_begin) or nullptr
   EpiArgs ep;
 };
 
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
     const int tiles_per_ch = a.tiles_per_ch, ntbg = a.ntbg, bbox = a.bbox;
     const int piece_step = a.tb_per_tile * a.N * a.stride, piece_len = a.row_pitch, tshift = a.pad + a.o;
     pdl_wait();                // the activation rows come from the previous kernel
+    if (lane == 0) qasr_stamp_begin(a.stamp);
     int c = u0 / tiles_per_ch, bc, tbg;
     {
       const int r = u0 - c * tiles_per_ch;
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
     // ===================== TMA producer =====================
     const bool leader = elect_one();
     pdl_wait();   // the activation rows come from the previous kernel
+    if (leader) qasr_stamp_begin(a.stamp);
     const int tiles_per_ch = a.tiles_per_ch, ntbg = a.ntbg, tbpt = a.tb_per_tile, n_tblk = a.n_tblk;
     const int slabs = a.slabs, bbox = a.bbox, stages = a.stages;
     const int tstep = a.N * a.stride, tshift = a.pad + a.o;
@@ -445,6 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tc_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) qasr_stamp_end(a.stamp);
   if (warp == kAllocWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
@@ -550,6 +554,7 @@ int qasr_dwconv_tc_launch(const void* x, int x_ld, const int8_t* taps, void* out
   a.idesc = (2u << 4) | (a_signed << 7) | (1u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(a.N >> 3) << 17) |
             ((uint32_t)(128 >> 4) << 24);
   a.ep = make_epi_args(epi);
+  a.stamp = qasr_next_stamp();
   a.dbg_skip = qasr_debug_get(6) > 0 ? (int)qasr_debug_get(6) : 0;
   a.dbg_trace = qasr_debug_get(7) > 0 ? reinterpret_cast<unsigned long long*>(qasr_debug_get(7)) : nullptr;
   CUtensorMap map;

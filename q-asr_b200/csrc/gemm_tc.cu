@@ -76,6 +76,7 @@ struct GemmArgs {
   uint32_t b_kstep;              // bytes between two K steps (32 channels) of the activation operand inside a stage
   int dbg_align, dbg_nonneg;     // bring-up knobs (qasr_debug_set 2 / 3)
   int dbg_skip;                  // qasr_debug_set 6: 1 = epilogue does nothing, 2 = no MMA issue, 4 = no stores
+  unsigned long long* stamp;     // in-graph timing slot (qasr_profile_begin) or nullptr
   EpiArgs ep;
 };
 
@@ -288,6 +289,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     __syncwarp();
     pdl_wait();   // weights above are constants of the plan; activations below come from the previous kernel
+    if (leader) qasr_stamp_begin(g.stamp);
     const int n_total = g.n_total, n_step = g.n_step, n_tiles = g.n_tiles, nseg = g.nseg, stages = g.stages;
     const int a_res = g.a_resident, MT = g.MT;
     const uint32_t stage_bytes = g.stage_bytes;
@@ -493,6 +495,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) qasr_stamp_end(g.stamp);
   if (warp == kAllocWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
@@ -626,6 +629,7 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
     __syncwarp();
     pdl_wait();   // weights above are constants of the plan; activations below come from the previous kernel
+    if (leader) qasr_stamp_begin(g.stamp);
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t stage_bytes = g.stage_bytes;   // 16 KB (128-frame boxes) or 8 KB (64-frame boxes, bn = 128)
@@ -786,6 +790,7 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // the peer's shared memory and TMEM stay alive until the leader's last MMA has retired
+  if (threadIdx.x == 0) qasr_stamp_end(g.stamp);
   if (warp == kAllocWarp) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
@@ -957,6 +962,7 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   g.dbg_align = qasr_debug_get(2) > 0 ? (int)qasr_debug_get(2) : 0;
   g.dbg_nonneg = qasr_debug_get(3) > 0 ? 1 : 0;
   g.dbg_skip = qasr_debug_get(6) > 0 ? (int)qasr_debug_get(6) : 0;
+  g.stamp = qasr_next_stamp();
 
   const bool fast = !(epi->flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64)) &&
                     epi->mode == QASR_EPI_REQUANT_I8;

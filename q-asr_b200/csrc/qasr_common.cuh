@@ -79,6 +79,10 @@ int qasr_validate_epilogue(const qasr_epilogue* e, bool allow_second_operand);
 // dependent launch), set from QASR_F_DEVICE_TABLES for every conv launch.
 void qasr_set_plain_launch(bool plain);
 bool qasr_plain_launch();
+// In-graph kernel timing (qasr_profile_begin / qasr_profile_end): while a session is open every conv launch gets the
+// next slot of the caller's stamp buffer; the kernel leaves there the %globaltimer of its first CTA's start on
+// activation data and of its last CTA's end.  nullptr outside a session (the timed product graph).
+unsigned long long* qasr_next_stamp();
 long long qasr_debug_get(int key);   // bring-up knobs, see api.cu
 extern "C" int qasr_debug_set(int key, long long value);
 
@@ -127,6 +131,18 @@ static inline cudaError_t qasr_launch_pdl_pair(Kern kern, dim3 grid, dim3 block,
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+__device__ __forceinline__ unsigned long long qasr_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void qasr_stamp_begin(unsigned long long* stamp) {
+  if (stamp != nullptr) atomicMin(stamp, qasr_globaltimer());
+}
+__device__ __forceinline__ void qasr_stamp_end(unsigned long long* stamp) {
+  if (stamp != nullptr) atomicMax(stamp + 1, qasr_globaltimer());
 }
 
 // m * 2^-e as a double: exact (m has 31 bits), so z * mult rounds exactly like the

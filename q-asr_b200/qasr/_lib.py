@@ -114,10 +114,13 @@ _SIGS = {
     "qasr_comm_free": (C.c_int, [_vp]),
     "qasr_debug_set": (C.c_int, [C.c_int, C.c_longlong]),
     "qasr_debug_knobs_set": (C.c_int, []),
+    "qasr_profile_begin": (C.c_int, [_vp, C.c_int]),
+    "qasr_profile_end": (C.c_int, []),
 }
 
 # bring-up hooks are not part of include/qasr.h
-EXPORTED_SYMBOLS = [s for s in _SIGS if s not in ("qasr_debug_set", "qasr_debug_knobs_set")]
+EXPORTED_SYMBOLS = [s for s in _SIGS if s not in ("qasr_debug_set", "qasr_debug_knobs_set", "qasr_profile_begin",
+                                                 "qasr_profile_end")]
 
 
 def load_library():

@@ -552,6 +552,40 @@ class FusedPlan:
             T = (T + 2 * p - d * (k - 1) - 1) // s + 1
         return T
 
+    def profile_stamps(self):
+        """One replay of an INSTRUMENTED copy of the plan's graph (same launches, same programmatic-dependent-launch
+        edges; every conv kernel additionally stamps %globaltimer when its first CTA starts on activation data and when
+        its last CTA ends).  Returns an int64 array (len(self.ops), 2) of nanoseconds, rows of launches without a stamp
+        (the input quantiser) are (0, 0).  The timed product graph carries no stamps."""
+        lib = L.lib()
+        if getattr(self, "_prof", None) is None:
+            conv_idx = [i for i, (n, _) in enumerate(self.ops) if n.startswith(("dw_", "gemm_"))]
+            buf = torch.zeros((len(conv_idx), 2), dtype=torch.int64, device=self.device)
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s):
+                self._run_ops()                       # kernel attributes are set outside the capture
+            torch.cuda.current_stream(self.device).wait_stream(s)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            L.check(lib.qasr_profile_begin(L.ptr(buf), len(conv_idx)))
+            try:
+                with torch.cuda.graph(g):
+                    self._run_ops()
+            finally:
+                used = lib.qasr_profile_end()
+            if used != len(conv_idx):
+                raise RuntimeError("profile: %d stamped launches, expected %d" % (used, len(conv_idx)))
+            self._prof = (g, buf, conv_idx)
+        g, buf, conv_idx = self._prof
+        buf[:, 0] = 2 ** 62
+        buf[:, 1] = 0
+        g.replay()
+        torch.cuda.synchronize(self.device)
+        out = np.zeros((len(self.ops), 2), np.int64)
+        out[conv_idx] = buf.cpu().numpy()
+        return out
+
     def load_inputs(self, x, lens):
         """x: (B, C, T) with T <= the plan's frame bucket (see bucket_frames); the tail of the bucket is zero."""
         B, C, T = x.shape
