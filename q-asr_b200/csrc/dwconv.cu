@@ -106,7 +106,9 @@ __device__ __forceinline__ void row_copy_async(uint32_t dst, const void* src, ui
 // EK: 0 = REQUANT all-integer fast path, 1 = REQUANT literal path, 2 = DEQUANT_F32 / RAW_I32 / STATS,
 //     3 = REQUANT float fast path (QASR_F_FAST_F32), 4 = REQUANT with device-written tables (QASR_F_DEVICE_TABLES):
 //     integer fast path for the channels qasr_dyn_finalize proved, literal path for the others
-template <int KS, int S, bool XS, int EK>
+// PROF: in-graph timing stamps (qasr_profile_begin).  A separate instantiation: the two extra 64-bit values cost the
+// product kernel 4-6 registers and with them a resident CTA per SM (measured: +3 % step time).
+template <int KS, int S, bool XS, int EK, bool PROF>
 #ifndef QASR_DW_MIN_BLOCKS
 #define QASR_DW_MIN_BLOCKS 1
 #endif
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
   const EpiConsts kc = make_epi_consts(a.ep, false);
   pdl_wait();   // activations (and the output buffer) belong to the stream order; everything above is set-up
   if (lane == 0) {
-    qasr_stamp_begin(a.stamp);
+    if (PROF) qasr_stamp_begin(a.stamp);
     for (int r = 0; r < min(nrows, kBufs - 1); ++r)
       row_copy_async(smem_addr(bufs + r * a.buf_bytes + a.halo), xbase + r * xstep, a.copy_bytes,
                      smem_addr(bars + r));
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
     else tiles(std::integral_constant<int, 2>{});
     __syncwarp();  // every lane is done reading this buffer before lane 0 refills it
   }
-  if (lane == 0) qasr_stamp_end(a.stamp);
+  if (PROF && lane == 0) qasr_stamp_end(a.stamp);
   if (EK == 2 && a.ep.mode == QASR_EPI_STATS) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -346,13 +348,16 @@ int launch(const DwArgs& a, cudaStream_t stream) {
                     a.ep.prev == nullptr;
   int ek = a.ep.mode != QASR_EPI_REQUANT_I8 ? 2 : ((a.ep.flags & QASR_F_FAST_F32) ? 3 : (fast ? 0 : 1));
   if (ek == 1 && (a.ep.flags & QASR_F_DEVICE_TABLES) && !(a.ep.flags & QASR_F_STAGE2) && a.ep.prev == nullptr) ek = 4;
+  // stamped instantiations exist for the kernels of the static plan (EK 0 and 3); other launches carry no stamp
+  const bool prof = a.stamp != nullptr && (ek == 0 || ek == 3);
 #define QASR_DW_GO(XS_, EK_)                                                                         \
   do {                                                                                               \
-    auto kern = dwconv_mma_kernel<KS, S, XS_, EK_>;                                                  \
-    static size_t attr_smem = 0;                                                                     \
-    if (smem > 48 * 1024 && smem > attr_smem) {                                                      \
+    auto kern = (prof && (EK_ == 0 || EK_ == 3)) ? dwconv_mma_kernel<KS, S, XS_, EK_, (EK_ == 0 || EK_ == 3)>  \
+                                                 : dwconv_mma_kernel<KS, S, XS_, EK_, false>;        \
+    static size_t attr_smem[2] = {0, 0};                                                             \
+    if (smem > 48 * 1024 && smem > attr_smem[prof]) {                                                \
       QASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attr_smem = smem;                                                                              \
+      attr_smem[prof] = smem;                                                                        \
     }                                                                                                \
     QASR_CHECK_CUDA(qasr_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, a));             \
   } while (0)

@@ -92,9 +92,17 @@ class EncDecCTCModel(nn.Module):
         return cls([dict(b) for b in enc["jasper"]], feat_in=int(enc.get("feat_in", 64)), vocabulary=list(vocabulary),
                    preprocessor=preprocessor, **kw)
 
-    def save_to(self, save_path):
-        """Writes a .nemo archive: tar.gz of model_config.yaml + model_weights.ckpt (modelPT.py:254-296)."""
+    def save_to(self, save_path, plan_shape=None):
+        """Writes a .nemo archive: tar.gz of model_config.yaml + model_weights.ckpt (modelPT.py:254-296).
+        plan_shape=(B, C, T): the compiled int8 plan of the calibrated, fixed model for that input shape goes into the
+        same archive (plan_manifest.json + plan.npz: packed weights, integer biases, dyadic tables, epilogue choices per
+        launch); `EncDecCTCModel.load_plan(path)` runs it without building the module tree.  restore_from ignores the
+        two extra members, exactly as the reference ignores unknown files."""
+        import io
         import yaml
+        extra = []
+        if plan_shape is not None:
+            extra = self.plan_for(tuple(plan_shape), next(self.parameters()).device).members()
         with tempfile.TemporaryDirectory() as tmpdir:
             with open(os.path.join(tmpdir, _MODEL_CONFIG_YAML), "w") as f:
                 yaml.safe_dump(self.to_config_dict(), f, sort_keys=False)
@@ -102,6 +110,18 @@ class EncDecCTCModel(nn.Module):
             with tarfile.open(save_path, "w:gz") as tar:
                 tar.add(os.path.join(tmpdir, _MODEL_CONFIG_YAML), arcname="./" + _MODEL_CONFIG_YAML)
                 tar.add(os.path.join(tmpdir, _MODEL_WEIGHTS), arcname="./" + _MODEL_WEIGHTS)
+                for name, data in extra:
+                    info = tarfile.TarInfo("./" + name)
+                    info.size = len(data)
+                    tar.addfile(info, io.BytesIO(data))
+
+    @staticmethod
+    def load_plan(path, device=None):
+        """The compiled plan stored in a .nemo archive (or a stand-alone plan archive): a qasr.plan.FusedPlan whose
+        run(x, lens) / greedy() / log_probs() need no model.  Raises on a libqasr version mismatch."""
+        from qasr import plan as _plan
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        return _plan.FusedPlan.load(path, device)
 
     @classmethod
     def restore_from(cls, restore_path, override_config_path=None, map_location=None, strict=False, **kw):

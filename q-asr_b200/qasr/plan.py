@@ -212,11 +212,22 @@ class ConvParams:
         return np.clip(self.b_int, -2 ** 31, 2 ** 31 - 1)  # 2^31 -> INT32_MAX sentinel (BIAS64 path)
 
 
+PLAN_FORMAT = 1
+
+
 class FusedPlan:
-    def __init__(self, encoder, decoder, in_shape, device, use_graph=True, verbose=False):
+    """Compiled from a calibrated module tree (encoder, decoder), or re-created from a serialised plan
+    (`FusedPlan.load`): every launch is first written down as a pure-data record (shapes, flags, numpy tables,
+    buffer / weight ids) and then materialised into device tensors and a closure over the C ABI, so both paths run
+    the same code and `save()` is a dump of the records."""
+
+    def __init__(self, encoder, decoder, in_shape, device, use_graph=True, verbose=False, _spec=None):
         self.device = torch.device(device)
         self.B, self.C_in, self.T = int(in_shape[0]), int(in_shape[1]), int(in_shape[2])
         self.encoder, self.decoder = encoder, decoder
+        self._bufs, self._buf_ids, self._weights, self._weight_ids = [], {}, [], {}
+        self.spec = dict(format=PLAN_FORMAT, in_shape=[self.B, self.C_in, self.T], buffers=[], launches=[],
+                         len_stages=[], outputs={})
         self.ops = []           # list of (name, callable)
         self.op_bytes = []      # algorithmic HBM bytes per op (int8 in + int8/f32 out, SURVEY.md 8d)
         self.op_macs = []       # multiply-accumulates per op
@@ -225,13 +236,19 @@ class FusedPlan:
         self._keep = []
         self.verbose = verbose
         B = self.B
-        self.ntc = self._needs_channels_last()
+        self.ntc = self._needs_channels_last() if _spec is None else bool(_spec["ntc"])
+        self.spec["ntc"] = self.ntc
         self.x_in = torch.zeros((B, self.C_in, self.T), dtype=torch.float32, device=self.device)
         self.lens = [torch.zeros(B, dtype=torch.int32, device=self.device)]   # per length stage
         self._lens_fns = []
         self._len_stages = []   # (k, stride, dilation, pad) of every conv that changes the frame count
         self.cur_T = self.T
-        self._build()
+        self.logits = self.encoded = None
+        if _spec is None:
+            self._build()
+            self.spec["stats"] = dict(self.stats)
+        else:
+            self._rebuild(_spec)
         self.cur_T_out = self.out_frames(self.T)
         self.graph = None
         self.use_graph = use_graph
@@ -304,6 +321,7 @@ class FusedPlan:
 
     def _new_len_stage(self, stage, k, s, d, p):
         prev = self.lens[stage]
+        self.spec["len_stages"].append([int(stage), int(k), int(s), int(d), int(p)])
         self._len_stages.append((k, s, d, p))
         self.lens.append(torch.zeros_like(prev))
         idx = len(self.lens) - 1
@@ -315,9 +333,26 @@ class FusedPlan:
 
     # -- materialisation -------------------------------------------------------------------
     def _alloc(self, C, T):
-        if self.ntc:
-            return ops.alloc_codes_ntc(self.B, C, T, self.device)
-        return ops.alloc_codes(self.B, C, T, self.device)
+        t = ops.alloc_codes_ntc(self.B, C, T, self.device) if self.ntc else ops.alloc_codes(self.B, C, T, self.device)
+        self._register_buffer(t)
+        return t
+
+    def _register_buffer(self, t):
+        self._buf_ids[t.data_ptr()] = len(self._bufs)
+        self._bufs.append(t)
+        self.spec["buffers"].append(dict(shape=list(t.shape), dtype=str(t.dtype).replace("torch.", "")))
+        return len(self._bufs) - 1
+
+    def _bid(self, t):
+        return None if t is None else self._buf_ids[t.data_ptr()]
+
+    def _wid(self, t):
+        """Id of a packed weight tensor (device); the bytes are dumped by save()."""
+        key = t.data_ptr()
+        if key not in self._weight_ids:
+            self._weight_ids[key] = len(self._weights)
+            self._weights.append(t)
+        return self._weight_ids[key]
 
     def _quantized(self, val, info, first_layer=False):
         key = (id(val), info.key())
@@ -339,20 +374,10 @@ class FusedPlan:
         if info.bit > 8:
             raise NotImplementedError("first-layer activation_bit > 8")
         out = self._alloc(val.C, val.T)
-        scale = torch.tensor([info.scale], dtype=torch.float32, device=self.device)
-        lens = self.lens[0] if info.masked else None
-        x_in, B, C, T, bit = self.x_in, self.B, val.C, val.T, info.bit
-        lib = L.lib()
-
-        if self.ntc:
-            def run():
-                L.check(lib.qasr_quantize_f32_ntc(L.ptr(x_in), T, L.ptr(scale), 0, bit, L.ptr(out), out.shape[-1],
-                                                  B, C, T, L.ptr(lens), L.stream_ptr()))
-        else:
-            def run():
-                L.check(lib.qasr_quantize_f32(L.ptr(x_in), T, L.ptr(scale), bit, L.ptr(out), out.shape[-1], None,
-                                              B, C, T, L.ptr(lens), L.stream_ptr()))
-        self._add("quantize_input", run, nbytes=B * C * T * 5)
+        rec = dict(kind="quantize_input", out=self._bid(out), scale=float(info.scale), bit=int(info.bit),
+                   masked=bool(info.masked), C=int(val.C), T=int(val.T))
+        self.spec["launches"].append(rec)
+        self._materialize(rec)
         return QTensor(val, info, out, True, info.scale, info.n, self.ntc)
 
     def _strip(self, val):
@@ -390,7 +415,7 @@ class FusedPlan:
                     flags |= L.F_FAST_F32
                 elif okc.any():
                     rf = np.where(okc, (m.astype(F64) * np.exp2(-e.astype(F64))).astype(F32), F32(0.0)).astype(F32)
-                    kw["f32_mult"] = torch.from_numpy(rf).to(self.device)
+                    kw["f32_mult"] = rf
             self._emit_conv([(base, cp, m, e)], out, flags, fast, kw, lens, "conv->act")
         elif isinstance(base, ResActVal):
             ra = ActInfo(base.act, False)
@@ -439,16 +464,22 @@ class FusedPlan:
             self._emit_conv([(branch, cpb, mb, eb)], out, flags, fast, dict(prev=prev.tensor, **kw), lens,
                             "res_act_chain")
 
-    def _chan_table(self, cp, m, e):
-        return ops.chan_table(cp.s_out, cp.b_i32(), m, e, self.device)
+    @staticmethod
+    def _chan_table_np(cp, m, e):
+        """qasr_chan records (s_out f32, bias i32, m i32, e i32) as an int32 [C][4] array."""
+        C = cp.s_out.size
+        tab = np.zeros((C, 4), np.int32)
+        tab[:, 0] = np.ascontiguousarray(cp.s_out, dtype=F32).view(np.int32)
+        tab[:, 1] = np.asarray(cp.b_i32(), np.int64).astype(np.int32)
+        tab[:, 2] = np.asarray(m, np.int64).astype(np.int32)
+        tab[:, 3] = np.asarray(e, np.int64).astype(np.int32)
+        return tab
 
     def _emit_conv(self, operands, out, flags, fast, epi_kw, lens, name):
         """One kernel: conv operand 0 (+ operand 1) -> epilogue -> int8 tensor `out`."""
-        tabs = [self._chan_table(cp, m, e) for (_, cp, m, e) in operands]
-        v0, cp0 = operands[0][0], operands[0][1]
-        if not v0.src.signed:
-            pass
-        else:
+        tabs = [self._chan_table_np(cp, m, e) for (_, cp, m, e) in operands]
+        v0 = operands[0][0]
+        if v0.src.signed:
             flags |= L.F_B_SIGNED
         if len(operands) > 1 and operands[1][0].src.signed:
             flags |= L.F_B1_SIGNED
@@ -459,61 +490,171 @@ class FusedPlan:
         self.stats["fast" if fast else "exact"] += 1
         if flags & L.F_FAST_F32:
             self.stats["f32"] += 1
-        ep = ops.make_epilogue(L.EPI_REQUANT_I8, tabs[0], flags=flags, ch1=tabs[1] if len(tabs) > 1 else None,
-                               out_lens=lens, **epi_kw)
+        kw = dict(epi_kw)
+        prev = kw.pop("prev", None)
+        f32_mult = kw.pop("f32_mult", None)
+        ep = dict(mode=L.EPI_REQUANT_I8, flags=int(flags), ch0=tabs[0], ch1=tabs[1] if len(tabs) > 1 else None,
+                  prev=self._bid(prev), lens_stage=None if lens is None else self._stage_of(lens),
+                  f32_mult=None if f32_mult is None else np.asarray(f32_mult, F32),
+                  **{k: int(v) for k, v in kw.items()})
         self._launch_conv(operands, out, ep, name)
+
+    def _stage_of(self, lens):
+        return next(i for i, t in enumerate(self.lens) if t is lens)
 
     def _emit_dequant(self, val, name):
         """float32 output y = f32(acc + b_int) * s_out (decoder logits / encoder API output)."""
         base, relu = self._strip(val)
         cp = ConvParams(base.conv, base.src.scale, base.src.qabs)
         C = base.conv.out_channels
-        one = np.full(C, 2 ** 30, np.int64)
-        tab = ops.chan_table(cp.s_out, cp.b_i32(), one, np.full(C, 30, np.int64), self.device)
+        tab = self._chan_table_np(cp, np.full(C, 2 ** 30, np.int64), np.full(C, 30, np.int64))
         flags = (L.F_RELU0 if relu else 0) | (L.F_BIAS64 if cp.bias64 else 0) | (L.F_B_SIGNED if base.src.signed else 0)
-        ep = ops.make_epilogue(L.EPI_DEQUANT_F32, tab, flags=flags)
+        ep = dict(mode=L.EPI_DEQUANT_F32, flags=int(flags), ch0=tab, ch1=None, prev=None, lens_stage=None, f32_mult=None)
         out = torch.zeros((self.B, C, ops.round_up(base.T, 16)), dtype=torch.float32, device=self.device)
+        self._register_buffer(out)
         self._launch_conv([(base, cp, None, None)], out, ep, name)
-        sf = torch.from_numpy(cp.s_out.copy()).to(self.device).view(1, -1, 1)
-        setattr(self, name, out)
-        setattr(self, name + "_scale", sf)
-        setattr(self, name + "_T", base.T)
+        self.spec["outputs"][name] = dict(buffer=self._bid(out), scale=cp.s_out.copy(), T=int(base.T))
+        self._bind_output(name)
         return out
+
+    def _bind_output(self, name):
+        o = self.spec["outputs"][name]
+        setattr(self, name, self._bufs[o["buffer"]])
+        setattr(self, name + "_scale", torch.from_numpy(np.asarray(o["scale"], F32).copy()).to(self.device).view(1, -1, 1))
+        setattr(self, name + "_T", int(o["T"]))
 
     def _launch_conv(self, operands, out, ep, name):
         v0, cp0 = operands[0][0], operands[0][1]
-        B, lib = self.B, L.lib()
         C_out, T_out = v0.conv.out_channels, v0.T
-        if cp0.depthwise:
-            assert len(operands) == 1 and not self.ntc
-            x, T_in = v0.src.tensor, v0.src.val.T
-            w8, k, s, d, p = cp0.w8, cp0.k, cp0.stride, cp0.dil, cp0.pad
-            import ctypes as C
+        assert not (cp0.depthwise and (len(operands) != 1 or self.ntc))
+        recs = []
+        nbytes = self.B * C_out * T_out * out.element_size() + (self.B * C_out * T_out if ep["prev"] is not None else 0)
+        macs = 0
+        for (v, cp, _, _) in operands:
+            recs.append(dict(src=self._bid(v.src.tensor), T_in=int(v.src.val.T), C_in=int(v.conv.in_channels), k=int(cp.k),
+                             stride=int(cp.stride), dil=int(cp.dil), pad=int(cp.pad),
+                             weights=self._wid(cp.w8 if cp.depthwise else cp.packed)))
+            nbytes += self.B * v.conv.in_channels * v.src.val.T
+            macs += self.B * T_out * C_out * (1 if cp.depthwise else v.conv.in_channels) * cp.k
+        kind = "dw" if cp0.depthwise else ("ntc" if self.ntc else "gemm")
+        rec = dict(kind=kind, name=("dw_k%d_%s" % (cp0.k, name)) if cp0.depthwise else
+                   "gemm_%dx%d_%s" % (v0.conv.in_channels, C_out, name),
+                   out=self._bid(out), C_out=int(C_out), T_out=int(T_out), operands=recs, ep=ep, nbytes=int(nbytes),
+                   macs=int(macs))
+        self.spec["launches"].append(rec)
+        self._materialize(rec)
+
+    # -- records -> device tensors + closures over the C ABI (compile path and load path alike) -------------
+    def _materialize(self, rec):
+        import ctypes as C
+        lib, B = L.lib(), self.B
+        if rec["kind"] == "quantize_input":
+            out = self._bufs[rec["out"]]
+            scale = torch.tensor([rec["scale"]], dtype=torch.float32, device=self.device)
+            lens = self.lens[0] if rec["masked"] else None
+            x_in, Cn, T, bit = self.x_in, rec["C"], rec["T"], rec["bit"]
+            if self.ntc:
+                def run():
+                    L.check(lib.qasr_quantize_f32_ntc(L.ptr(x_in), T, L.ptr(scale), 0, bit, L.ptr(out), out.shape[-1],
+                                                      B, Cn, T, L.ptr(lens), L.stream_ptr()))
+            else:
+                def run():
+                    L.check(lib.qasr_quantize_f32(L.ptr(x_in), T, L.ptr(scale), bit, L.ptr(out), out.shape[-1], None,
+                                                  B, Cn, T, L.ptr(lens), L.stream_ptr()))
+            self._add("quantize_input", run, keep=(scale,), nbytes=B * Cn * T * 5)
+            return
+        e = rec["ep"]
+        dev = lambda a, dt=None: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(self.device)  # noqa: E731
+        stage2 = {k: e[k] for k in ("m2", "e2", "qmin2", "qmax2") if k in e}
+        ep = ops.make_epilogue(e["mode"], dev(e["ch0"]), flags=e["flags"], ch1=dev(e["ch1"]),
+                               prev=None if e["prev"] is None else self._bufs[e["prev"]],
+                               qmin=e.get("qmin", -128), qmax=e.get("qmax", 127),
+                               out_lens=None if e["lens_stage"] is None else self.lens[e["lens_stage"]],
+                               f32_mult=dev(e["f32_mult"]), **stage2)
+        out = self._bufs[rec["out"]]
+        C_out, T_out = rec["C_out"], rec["T_out"]
+        o0 = rec["operands"][0]
+        if rec["kind"] == "dw":
+            x, w8 = self._bufs[o0["src"]], self._weights[o0["weights"]]
+            T_in, k, s, d, p = o0["T_in"], o0["k"], o0["stride"], o0["dil"], o0["pad"]
 
             def run():
                 L.check(lib.qasr_dwconv1d_i8(L.ptr(x), x.shape[-1], L.ptr(w8), L.ptr(out), out.shape[-1], B,
                                              C_out, T_in, T_out, k, s, d, p, C.byref(ep), L.stream_ptr()))
-            self._add("dw_k%d_%s" % (k, name), run, keep=(ep, w8),
-                      nbytes=B * C_out * (T_in + T_out * out.element_size()), macs=B * C_out * T_out * k)
-        else:
-            gops = []
-            for (v, cp, _, _) in operands:
-                gops.append(ops.gemm_operand(v.src.tensor, v.src.val.T, cp.packed, v.conv.in_channels, cp.k,
-                                             cp.stride, cp.dil, cp.pad))
-            import ctypes as C
-            op1 = C.byref(gops[1]) if len(gops) > 1 else None
-            entry = lib.qasr_conv1d_ntc_i8 if self.ntc else lib.qasr_conv1d_gemm_i8
+            self._add(rec["name"], run, keep=(ep, w8), nbytes=rec["nbytes"], macs=rec["macs"])
+            return
+        gops = [ops.gemm_operand(self._bufs[o["src"]], o["T_in"], self._weights[o["weights"]], o["C_in"], o["k"],
+                                 o["stride"], o["dil"], o["pad"]) for o in rec["operands"]]
+        op1 = C.byref(gops[1]) if len(gops) > 1 else None
+        entry = lib.qasr_conv1d_ntc_i8 if rec["kind"] == "ntc" else lib.qasr_conv1d_gemm_i8
 
-            def run():
-                L.check(entry(C.byref(gops[0]), op1, L.ptr(out), out.shape[-1], B, C_out, T_out, C.byref(ep),
-                              L.stream_ptr()))
-            nbytes = B * C_out * T_out * out.element_size() + (B * C_out * T_out if ep.prev else 0)
-            macs = 0
-            for (v, cp, _, _) in operands:
-                nbytes += B * v.conv.in_channels * v.src.val.T
-                macs += B * T_out * C_out * v.conv.in_channels * cp.k
-            self._add("gemm_%dx%d_%s" % (v0.conv.in_channels, C_out, name), run, keep=(ep, gops), nbytes=nbytes,
-                      macs=macs)
+        def run():
+            L.check(entry(C.byref(gops[0]), op1, L.ptr(out), out.shape[-1], B, C_out, T_out, C.byref(ep), L.stream_ptr()))
+        self._add(rec["name"], run, keep=(ep, gops), nbytes=rec["nbytes"], macs=rec["macs"])
+
+    # -- serialisation (SURVEY 8(f)3: a compiled int8 plan for deployment) ------------------------------------
+    def members(self):
+        """The compiled plan as archive members for a .nemo-style tar.gz (the reference's container,
+        nemo/core/classes/modelPT.py:254-296): `plan_manifest.json` (format / library version / shapes) + `plan.npz`
+        (every launch record: packed int8 weights, b_int / (m, e) / s_out tables, f32 multipliers, epilogue flags).
+        No module tree is needed to run it again (FusedPlan.load)."""
+        import io
+        import json
+        from . import planio
+        spec = dict(self.spec)
+        spec["weights"] = [w.detach().cpu().numpy().view(np.uint8).reshape(-1) for w in self._weights]
+        spec["enc_stage"] = int(self.enc_stage)
+        manifest = dict(format=PLAN_FORMAT, qasr_version=int(L.load_library().qasr_version()), in_shape=spec["in_shape"],
+                        ntc=self.ntc, launches=len(spec["launches"]), stats=spec.get("stats"))
+        buf = io.BytesIO()
+        planio.dump(buf, spec)
+        return [("plan_manifest.json", json.dumps(manifest, indent=1).encode()), ("plan.npz", buf.getvalue())]
+
+    def save(self, path):
+        """A stand-alone plan archive (tar.gz of the two members); EncDecCTCModel.save_to(..., plan_shapes=) puts the
+        same members into the .nemo file next to model_weights.ckpt."""
+        import io
+        import tarfile
+        with tarfile.open(path, "w:gz") as tar:
+            for name, data in self.members():
+                info = tarfile.TarInfo("./" + name)
+                info.size = len(data)
+                tar.addfile(info, io.BytesIO(data))
+
+    @classmethod
+    def load(cls, path, device, use_graph=True):
+        """Re-creates a plan saved by save().  Refuses a plan written by another library version: the packed weight
+        layouts and epilogue flags are private to one libqasr build."""
+        import io
+        import json
+        import tarfile
+        from . import planio
+        with tarfile.open(path, "r:*") as tar:
+            files = {os.path.basename(m.name): tar.extractfile(m).read() for m in tar.getmembers() if m.isfile()}
+        manifest = json.loads(files["plan_manifest.json"].decode())
+        have = int(L.load_library().qasr_version())
+        if manifest.get("format") != PLAN_FORMAT or manifest.get("qasr_version") != have:
+            raise RuntimeError("plan %s was compiled for libqasr version %s / plan format %s; this build is version %d / "
+                               "format %d: recompile the plan from the model" % (path, manifest.get("qasr_version"),
+                                                                                manifest.get("format"), have, PLAN_FORMAT))
+        spec = planio.load(io.BytesIO(files["plan.npz"]))
+        return cls(None, None, spec["in_shape"], device, use_graph=use_graph, _spec=spec)
+
+    def _rebuild(self, spec):
+        for (stage, k, s, d, p) in spec["len_stages"]:
+            self._new_len_stage(int(stage), int(k), int(s), int(d), int(p))
+        for b in spec["buffers"]:
+            self._register_buffer(torch.zeros(tuple(int(v) for v in b["shape"]), dtype=getattr(torch, b["dtype"]),
+                                              device=self.device))
+        self._weights = [torch.from_numpy(np.ascontiguousarray(w)).to(self.device).view(torch.int8) for w in spec["weights"]]
+        for rec in spec["launches"]:
+            self.spec["launches"].append(rec)
+            self._materialize(rec)
+        self.spec["outputs"] = spec["outputs"]
+        for name in spec["outputs"]:
+            self._bind_output(name)
+        self.enc_stage = int(spec["enc_stage"])
+        self.stats.update(spec.get("stats") or {})
 
     def _add(self, name, fn, keep=None, nbytes=0, macs=0):
         self.ops.append((name, fn))

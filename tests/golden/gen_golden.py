@@ -10,6 +10,7 @@ Integer codes are recovered from the reference's float tensors as rne(x / scale)
 """
 import os
 import sys
+import zlib
 
 import numpy as np
 import torch
@@ -43,7 +44,9 @@ def npf(t):
 # --------------------------------------------------------------------------------------
 def net_case(name, topo_name, topo_kwargs, B, T, wbit, abit, mode, percentile=None, n_calib=2,
              momentum=None):
-    torch.manual_seed(hash(name) % 10000)
+    # fixed seed table: crc32 of the case name (Python's hash() of a str is salted per process).  The committed fixtures
+    # of round 1 were drawn with the salted hash; they carry their own state_dict, so tests never depend on the seed.
+    torch.manual_seed(zlib.crc32(name.encode()) % 10000)
     blocks = topology.TOPOLOGIES[topo_name](**topo_kwargs)
     m = RefModel(ref, blocks)
     m.eval()

@@ -296,3 +296,52 @@ def test_jasper10x5dr_t800_vs_oracle():
     logits = plan.run(x.to(DEV), lens.to(DEV))
     assert np.array_equal(_logit_codes(logits, plan.logits_scale.reshape(-1)), want["logit_codes"])
     assert np.array_equal(plan.greedy().cpu().numpy(), want["greedy"])
+
+
+# ------------------------------------------------------------------------------------------
+# the compiled int8 plan, serialised and run without the module tree
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["net_tinyqn_w6a6_pct_static", "net_tinyjasper_w8a8_static"])
+def test_compiled_plan_round_trip(name, tmp_path):
+    import json
+    import tarfile
+    from nemo.collections.asr.models.ctc_models import EncDecCTCModel
+    from qasr import plan as P
+    from test_gpu_model import build_from_case, set_ranges_from_spec
+    case = specio.load(os.path.join(GOLDEN, name + ".npz"))
+    model, qm = build_from_case(case)
+    set_ranges_from_spec(model, case["spec"])            # the reference's calibrated ranges
+    qm.evaluate(model)
+    x, lens = torch.from_numpy(case["x"]).to(DEV), torch.from_numpy(case["lens"]).to(DEV)
+    plan = model.plan_for(x.shape, torch.device(DEV))
+    want = plan.run(x, lens).clone()
+    want_greedy = plan.greedy().clone()
+    path = str(tmp_path / "model_with_plan.nemo")
+    model.save_to(path, plan_shape=tuple(x.shape))
+    with tarfile.open(path) as tar:
+        assert {os.path.basename(m.name) for m in tar.getmembers()} >= {"model_config.yaml", "model_weights.ckpt",
+                                                                         "plan_manifest.json", "plan.npz"}
+    del plan, model
+    loaded = EncDecCTCModel.load_plan(path, DEV)         # no module tree, no calibration: records -> kernels
+    assert loaded.encoder is None and len(loaded.ops) > 5
+    got = loaded.run(x, lens)
+    assert torch.equal(got, want) and torch.equal(loaded.greedy(), want_greedy)
+    codes = torch.round(got.double() / loaded.logits_scale.double()).to(torch.int64).cpu().numpy()
+    assert np.array_equal(codes, case["out"]["logit_codes"])          # == the unmodified reference's logit codes
+    # the archive still restores as a model (unknown members are ignored, modelPT.py:373-405)
+    again = EncDecCTCModel.restore_from(path)
+    assert sum(p.numel() for p in again.parameters()) > 0
+    # a plan written by another library build is refused
+    bad = str(tmp_path / "stale_plan.tar.gz")
+    with tarfile.open(path) as tar:
+        files = {os.path.basename(m.name): tar.extractfile(m).read() for m in tar.getmembers() if m.isfile()}
+    man = json.loads(files["plan_manifest.json"].decode())
+    man["qasr_version"] += 1
+    import io
+    with tarfile.open(bad, "w:gz") as tar:
+        for n, data in (("plan_manifest.json", json.dumps(man).encode()), ("plan.npz", files["plan.npz"])):
+            info = tarfile.TarInfo("./" + n)
+            info.size = len(data)
+            tar.addfile(info, io.BytesIO(data))
+    with pytest.raises(RuntimeError, match="libqasr version"):
+        P.FusedPlan.load(bad, DEV)
