@@ -347,6 +347,8 @@ class EncDecCTCModel(nn.Module):
             p.run(processed_signal, processed_signal_length)
             if not p.overflowed():
                 self.decoder.last_logits = p.logits[:, :, :p.cur_T_out]
+                self.decoder.act.act_scaling_factor = p.decoder_act_scale.clone()   # as QuantAct.forward leaves it (:177)
+                self.decoder.decoder_layers[0]._prepare()                           # conv_scaling_factor / weight_integer
                 return p.log_probs(), p.out_lens().to(torch.long), p.greedy().to(torch.long)
         encoded, encoded_len, encoded_sf = self.encoder(audio_signal=processed_signal,
                                                         length=processed_signal_length)

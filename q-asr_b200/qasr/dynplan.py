@@ -215,6 +215,7 @@ class DynamicPlan:
         # ---- decoder: 1x1 conv with bias on the decoder QuantAct's codes -> float logits (conv_asr.py:270-275)
         dconv = conv_of(self.decoder.decoder_layers[0])
         self.enc_stage = cur.stage
+        self.decoder_act_scale = cur.scale      # device scalar: the decoder QuantAct's scale of the last run
         self.logits = torch.zeros((self.B, dconv.C_out, ops.round_up(cur.T, 16)), dtype=torch.float32, device=self.device)
         flags = L.F_DEVICE_TABLES | L.F_BIAS64 | (0 if cur.unsigned else L.F_B_SIGNED)
         ep = ops.make_epilogue(L.EPI_DEQUANT_F32, dconv.table, flags=flags)

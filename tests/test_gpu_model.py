@@ -299,10 +299,14 @@ def test_quartznet15x5_dynamic_vs_oracle(quartznet):
         want = O.model_forward(spec, x.numpy(), lens.numpy())
     finally:
         O.LITERAL_NOISE = False
-    log_probs, enc_len, greedy = model(processed_signal=x.to(DEV), processed_signal_length=lens.to(DEV))
-    sf = model.decoder.decoder_layers[0].conv_scaling_factor * model.decoder.act.act_scaling_factor
-    assert np.array_equal(logit_codes(model.decoder.last_logits, sf), want["logit_codes"])
-    assert np.array_equal(greedy.cpu().numpy(), want["greedy"])
+    for fused in (False, True):     # module-level path (statistics kernels per QuantAct), then the fused dynamic plan
+        model.use_fused_plan = fused
+        log_probs, enc_len, greedy = model(processed_signal=x.to(DEV), processed_signal_length=lens.to(DEV))
+        # forward() leaves the decoder QuantAct's scale of THIS batch in the module, like the reference does
+        sf = model.decoder.decoder_layers[0].conv_scaling_factor * model.decoder.act.act_scaling_factor
+        assert np.array_equal(logit_codes(model.decoder.last_logits, sf), want["logit_codes"]), fused
+        assert np.array_equal(greedy.cpu().numpy(), want["greedy"])
+    assert model._dynamic_plan_or_none(x.to(DEV)) is not None
     qm.set_dynamic(model, False)
 
 

@@ -345,3 +345,27 @@ def test_compiled_plan_round_trip(name, tmp_path):
             tar.addfile(info, io.BytesIO(data))
     with pytest.raises(RuntimeError, match="libqasr version"):
         P.FusedPlan.load(bad, DEV)
+
+
+def test_synthesize_then_inference_chain(nemo_and_calib, tmp_path, monkeypatch, capsys):
+    """SURVEY 8(f)4 -> a14: synthesize.py (FP32 teacher on the GPU, BatchNorm-statistics distillation) writes the pickle,
+    inference.py calibrates on it (--load) and decodes; hypotheses again equal the oracle's."""
+    nemo, _ = nemo_and_calib
+    path = os.path.join(ROOT, "q-asr_b200", "examples", "asr", "quantization", "synthesize.py")
+    spec = importlib.util.spec_from_file_location("qasr_synthesize_entry_r2", path)
+    syn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(syn)
+    monkeypatch.setattr(sys, "argv", ["synthesize.py", "--asr_model", nemo, "--num_batch", "2", "--batch_size", "4", "--seqlen",
+                                      "96", "--train_iter", "8", "--dump_path", str(tmp_path), "--seed", "5"])
+    pkl = syn.main()
+    monkeypatch.setattr(sys, "argv", ["inference.py", "--asr_model", nemo, "--dataset", "synthetic:2:96", "--batch_size", "4",
+                                      "--load", pkl])
+    res = _load_entry_point().main()
+    capsys.readouterr()
+    model, vocab = res["model"], res["model"].decoder.vocabulary
+    spec_o = spec_from_model(model.encoder, model.decoder)
+    want = []
+    for feats, lens, _ in res["test_data"]:
+        out = O.model_forward(spec_o, feats.numpy(), lens.numpy())
+        want += ["".join(vocab[c] for c in O.ctc_greedy_collapse(row, len(vocab))) for row in out["greedy"]]
+    assert res["hypotheses"] == want and len(want) == 8
