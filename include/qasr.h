@@ -333,6 +333,11 @@ typedef struct {
   int32_t prod_qabs[2];
   qasr_stats* stats;             /* optional: statistics records to put back into their reset state       */
   int32_t stats_C, stats_dual;
+  int32_t phase;                 /* world > 1 only.  0: post this rank's absmax to every rank's slots, wait for all
+                                    ranks, finish (one rank per GPU: the production form).  1: post only.  2: wait and
+                                    finish only.  1 and 2 let ONE stream run several ranks' plans in turn (all ranks'
+                                    posts are complete before any rank waits), which is how the exchange is tested on a
+                                    single GPU: launches that spin on each other must never share a GPU.             */
 } qasr_dyn_finalize_args;
 int qasr_dyn_finalize(const qasr_dyn_finalize_args* a, void* stream);
 

@@ -373,7 +373,7 @@ struct DynFin {
   const int32_t* prod_wabs[2];
   int prod_qabs[2];
   qasr_stats* stats;
-  int stats_C, stats_dual;
+  int stats_C, stats_dual, phase;
 };
 
 // May the all-integer epilogue ((z*m + 2^(e-1)) >> e) replace the literal float recipe for |z| <= bound?  Same proof as
@@ -391,44 +391,54 @@ __device__ __forceinline__ bool fast_ok_dev(long long bound, int m, int e) {
 
 __global__ void dyn_finalize_kernel(const DynFin a) {
   __shared__ float s_scale;
+  const bool post = a.world <= 1 || a.phase != 2, finish = a.world <= 1 || a.phase != 1;
   if (threadIdx.x == 0) {
-    float absmax;
-    if (a.src_kind == 0) {
-      uint32_t* p = static_cast<uint32_t*>(a.src);
-      absmax = __uint_as_float(*p);
-      *p = 0u;
-    } else if (a.src_kind == 1) {
-      const float* p = static_cast<const float*>(a.src);
-      absmax = fmaxf(fabsf(p[0]), fabsf(p[1]));
-    } else {
-      int32_t* p = static_cast<int32_t*>(a.src);
-      const int lo = p[0], hi = p[1];
-      absmax = hi >= lo ? fmaxf(fabsf(__fmul_rn((float)lo, a.src_scale[0])), fabsf(__fmul_rn((float)hi, a.src_scale[0]))) : 0.0f;
-      p[0] = 2147483647;
-      p[1] = -2147483647 - 1;
+    float absmax = 0.0f;
+    if (post) {
+      if (a.src_kind == 0) {
+        uint32_t* p = static_cast<uint32_t*>(a.src);
+        absmax = __uint_as_float(*p);
+        *p = 0u;
+      } else if (a.src_kind == 1) {
+        const float* p = static_cast<const float*>(a.src);
+        absmax = fmaxf(fabsf(p[0]), fabsf(p[1]));
+      } else {
+        int32_t* p = static_cast<int32_t*>(a.src);
+        const int lo = p[0], hi = p[1];
+        absmax = hi >= lo ? fmaxf(fabsf(__fmul_rn((float)lo, a.src_scale[0])), fabsf(__fmul_rn((float)hi, a.src_scale[0]))) : 0.0f;
+        p[0] = 2147483647;
+        p[1] = -2147483647 - 1;
+      }
     }
     if (a.world > 1) {
       // one-shot all-reduce(MAX) over peer memory: write (sequence, value) into this rank's slot of EVERY rank's
       // table, then wait until all ranks' entries of this sequence number have arrived here.  A rank can run ahead
       // of a peer by less than one forward (every exchange waits for all ranks), so the sequence number in the
       // entry tells this forward's value from the previous one.
-      const uint32_t seq = ++(*a.seq);
-      const unsigned long long word = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(absmax);
-      for (int r = 0; r < a.world; ++r) {
-        unsigned long long* dst = a.peer_slots[r] + (size_t)a.slot * a.world + a.rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+      if (post) {
+        const uint32_t seq = ++(*a.seq);
+        const unsigned long long word = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(absmax);
+        for (int r = 0; r < a.world; ++r) {
+          unsigned long long* dst = a.peer_slots[r] + (size_t)a.slot * a.world + a.rank;
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+        }
       }
-      const unsigned long long* mine = a.peer_slots[a.rank] + (size_t)a.slot * a.world;
-      for (int r = 0; r < a.world; ++r) {
-        unsigned long long v;
-        unsigned spin = 0;
-        do {
-          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + r) : "memory");
-          if (++spin > (1u << 28)) __trap();   // a lost peer must not hang the GPU
-        } while ((uint32_t)(v >> 32) != seq);
-        absmax = fmaxf(absmax, __uint_as_float((uint32_t)v));
+      if (finish) {
+        const uint32_t seq = *a.seq;
+        const unsigned long long* mine = a.peer_slots[a.rank] + (size_t)a.slot * a.world;
+        absmax = 0.0f;
+        for (int r = 0; r < a.world; ++r) {
+          unsigned long long v;
+          unsigned spin = 0;
+          do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + r) : "memory");
+            if (++spin > (1u << 28)) __trap();   // a lost peer must not hang the GPU
+          } while ((uint32_t)(v >> 32) != seq);
+          absmax = fmaxf(absmax, __uint_as_float((uint32_t)v));
+        }
       }
     }
+    if (!finish) return;
     // symmetric_linear_quantization_params, quant_utils.py:51-52: clamp(max(|min|, |max|), 1e-8) / n
     const float s = __fdiv_rn(fmaxf(absmax, 1e-8f), (float)a.n_levels);
     a.act_scale[0] = s;
@@ -440,6 +450,7 @@ __global__ void dyn_finalize_kernel(const DynFin a) {
       a.prev_me[1] = e;
     }
   }
+  if (!finish) return;
   __syncthreads();
   const float s = s_scale;
   for (int i = 0; i < a.n_prod; ++i) {
@@ -611,6 +622,8 @@ extern "C" int qasr_dyn_finalize(const qasr_dyn_finalize_args* a, void* stream) 
   f.rank = a->rank; f.world = a->world; f.slot = a->slot; f.seq = a->seq;
   for (int i = 0; i < 2; ++i) { f.prod_wabs[i] = a->prod_wabs[i]; f.prod_qabs[i] = a->prod_qabs[i]; }
   f.stats = a->stats; f.stats_C = a->stats_C; f.stats_dual = a->stats_dual;
+  f.phase = a->phase;
+  QASR_CHECK_ARG(a->phase >= 0 && a->phase <= 2, "dyn_finalize: phase");
   dyn_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(f);
   return qasr_check_launch("dyn_finalize_kernel");
 }

@@ -62,7 +62,7 @@ class DynFinalizeArgs(C.Structure):
         ("peer_slots", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32), ("slot", C.c_int32),
         ("seq", C.c_void_p),
         ("prod_wabs", C.c_void_p * 2), ("prod_qabs", C.c_int32 * 2),
-        ("stats", C.c_void_p), ("stats_C", C.c_int32), ("stats_dual", C.c_int32),
+        ("stats", C.c_void_p), ("stats_C", C.c_int32), ("stats_dual", C.c_int32), ("phase", C.c_int32),
     ]
 
 

@@ -75,6 +75,7 @@ class DynamicPlan:
         self._lens_fns, self._len_stages = [], []
         self._convs = []
         self._n_slots = 0
+        self.finalize_args = {}      # op index -> qasr_dyn_finalize_args (its `phase` is read at launch time)
         self.cur_T = self.T
         self._build()
         self.cur_T_out = self.out_frames(self.T)
@@ -286,6 +287,7 @@ class DynamicPlan:
             if self._n_slots > slots.n_slots:
                 raise RuntimeError("range exchange: more QuantAct ranges than slots (%d)" % slots.n_slots)
         lib = L.lib()
+        self.finalize_args[len(self.ops)] = a
         self._add("finalize", lambda: L.check(lib.qasr_dyn_finalize(C.byref(a), L.stream_ptr())),
                   keep=(a, src, src_scale, act_scale, prods, prev, cons))
         self.stats["finalize"] += 1
@@ -432,8 +434,16 @@ class PeerSlots:
     the other ranks of the node map through CUDA IPC (qasr_comm_*); `gather` is how the 64-byte handles travel
     (torch.distributed.all_gather_object in production, a list in the single-process tests)."""
 
-    def __init__(self, rank, world, n_slots, device, gather):
+    def __init__(self, rank, world, n_slots, device, gather=None, local_tables=None):
+        """local_tables: every rank's table as a tensor of THIS process (all ranks' plans live in one process and run
+        in turn on one stream with the post / wait phases of qasr_dyn_finalize: the single-GPU test form)."""
         self.rank, self.world, self.n_slots = rank, world, n_slots
+        self._opened, self._own = [], None
+        if local_tables is not None:
+            self._local = local_tables
+            self._table = torch.tensor([t.data_ptr() for t in local_tables], dtype=torch.int64, device=device)
+            self._seq = torch.zeros(n_slots, dtype=torch.int32, device=device)
+            return
         lib = L.lib()
         own = C.c_void_p()
         handle = (C.c_ubyte * 64)()
