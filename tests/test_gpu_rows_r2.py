@@ -143,7 +143,8 @@ def test_quant_conv_unfixed_bn(case):
     qc = _make_conv(Q, Q.QuantConv1d, case["weight"], case["groups"], case["pad"], case["bn"], fix_bn=False)
     for call in case["calls"]:
         s_x = _d(call["s_x"])
-        out, sf = qc(_d(call["in_codes"]).float() * s_x, s_x)
+        with torch.no_grad():
+            out, sf = qc(_d(call["in_codes"]).float() * s_x, s_x)
         assert np.allclose(qc.bn.running_mean.cpu().numpy(), call["mean"], rtol=1e-5, atol=1e-6)
         assert np.allclose(qc.bn.running_var.cpu().numpy(), call["var"], rtol=1e-5, atol=1e-6)
         assert np.allclose(sf.reshape(-1).cpu().numpy(), call["out_scale"], rtol=1e-5, atol=0)
