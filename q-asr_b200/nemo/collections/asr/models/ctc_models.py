@@ -56,6 +56,11 @@ class EncDecCTCModel(nn.Module):
         if c["preprocessor"] is not None:
             cfg["preprocessor"] = dict(_target_="nemo.collections.asr.modules.AudioToMelSpectrogramPreprocessor",
                                        **c["preprocessor"])
+        # bn_folding() removes the BatchNorm entries from every block's module list (jasper.py:451-474), which renumbers
+        # the state_dict keys behind them: a checkpoint of a folded model only loads into a folded module tree
+        from nemo.quantization.utils.quant_modules import QuantConv1d
+        if any(isinstance(m, QuantConv1d) and m.bn is not None for m in self.encoder.modules()):
+            cfg["quantization"] = dict(bn_folded=True)
         return cfg
 
     @classmethod
@@ -145,6 +150,9 @@ class EncDecCTCModel(nn.Module):
             with open(config_yaml) as f:
                 conf = yaml.safe_load(f)
             instance = cls.from_config_dict(conf, **kw)
+            model_cfg = conf["model"] if "model" in conf and "encoder" not in conf else conf
+            if (model_cfg.get("quantization") or {}).get("bn_folded"):
+                instance.encoder.bn_folding()      # same module numbering as the checkpoint (see to_config_dict)
             state = torch.load(os.path.join(tmpdir, _MODEL_WEIGHTS), map_location="cpu")
             instance.load_state_dict(state, strict=False)
         return instance.to(map_location)
