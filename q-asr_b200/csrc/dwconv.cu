@@ -33,6 +33,10 @@
 
 #include "qasr_common.cuh"
 
+#ifndef QASR_TAPE_DEFAULT
+#define QASR_TAPE_DEFAULT 0   // engine choice without knob 8: 1 = tape engine wherever it applies
+#endif
+
 namespace {
 
 constexpr int kWarps = 4;
@@ -408,8 +412,15 @@ bool qasr_dwconv_tc_supported(int B, int C, int T_in, int T_out, int k, int stri
 int qasr_dwconv_tc_launch(const void* x, int x_ld, const int8_t* taps, void* out, int out_ld, int B, int C, int T_in,
                           int T_out, int k, int stride, int dilation, int pad, const qasr_epilogue* epi, void* stream);
 
+// tape engine (dwconv_tape.cu): tcgen05 on the utterance rows themselves through overlapping no-swizzle descriptors
+bool qasr_dwconv_tape_supported(int k, int stride, int dilation, int pad);
+int64_t qasr_dwconv_tape_packed_bytes(int C, int k, int stride, int dilation, int pad);
+int qasr_dwconv_tape_pack(const int8_t* w, uint8_t* bm, int C, int k, int dilation, int pad, cudaStream_t st);
+int qasr_dwconv_tape_launch(const void* x, int x_ld, const uint8_t* bmat, void* out, int out_ld, int B, int C, int T_in,
+                            int T_out, int k, int dilation, int pad, const qasr_epilogue* epi, void* stream);
+
 // packed layout: [IMMA A-fragment table (absent when the tap window exceeds 6 x 32)] [raw taps [C][k], for the
-// tcgen05 kernel which builds its banded matrices on the fly]
+// tcgen05 kernel which builds its banded matrices on the fly] [16 x K weight matrices of the tape engine]
 static int64_t dw_table_bytes(int C, int k, int stride, int dilation, int pad) {
   const int ks = dw_ksteps(k, stride, dilation, pad);
   return ks > 6 ? 0 : (int64_t)C * ks * 128 * 4;
@@ -419,7 +430,7 @@ extern "C" int64_t qasr_dw_packed_bytes(int32_t C, int32_t k, int32_t stride, in
   if (C <= 0 || k <= 0 || (stride != 1 && stride != 2) || dilation < 1 || pad < 0) return -1;
   const int64_t table = dw_table_bytes(C, k, stride, dilation, pad);
   if (table == 0 && !qasr_dwconv_tc_supported(1, C, 1, 1, k, stride, dilation, pad)) return -1;
-  return table + (((int64_t)C * k + 15) / 16) * 16;
+  return table + (((int64_t)C * k + 15) / 16) * 16 + qasr_dwconv_tape_packed_bytes(C, k, stride, dilation, pad);
 }
 
 extern "C" int qasr_pack_dw_weights(const int8_t* w, void* wp, int32_t C, int32_t k, int32_t stride,
@@ -431,6 +442,11 @@ extern "C" int qasr_pack_dw_weights(const int8_t* w, void* wp, int32_t C, int32_
   const int64_t table = dw_table_bytes(C, k, stride, dilation, pad);
   QASR_CHECK_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(wp) + table, w, (size_t)C * k, cudaMemcpyDeviceToDevice,
                                   (cudaStream_t)stream));
+  if (qasr_dwconv_tape_supported(k, stride, dilation, pad)) {
+    int rc = qasr_dwconv_tape_pack(w, static_cast<uint8_t*>(wp) + table + (((int64_t)C * k + 15) / 16) * 16, C, k, dilation, pad,
+                                   (cudaStream_t)stream);
+    if (rc) return rc;
+  }
   if (table == 0) return QASR_OK;
   const int total = C * ks * 128;
   pack_dw_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
@@ -472,6 +488,14 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
   // 6 K steps (k = 87 dilated): the lanes' 8-byte fragment loads are 12 words apart and collide on banks
   // (30.9 us against 27.5 us on tcgen05, 512 channels, batch 64 x 800 frames)
   if (knob < 0 && tc_ok && dw_ksteps(k, stride, dilation, pad) >= 6) use_tc = true;
+  // tape engine (tcgen05 on the rows themselves): requantising launches with stride 1.  Bring-up knob 8 = 2 forces it,
+  // 0 / 1 force the other engines.
+  const bool tape_ok = epi->mode == QASR_EPI_REQUANT_I8 && qasr_dwconv_tape_supported(k, stride, dilation, pad) &&
+                       !(epi->flags & QASR_F_STAGE2) && epi->prev == nullptr && out_ld % 16 == 0;
+  const bool use_tape = tape_ok && (knob == 2 || (knob < 0 && QASR_TAPE_DEFAULT));
+  if (use_tape)
+    return qasr_dwconv_tape_launch(x, x_ld, reinterpret_cast<const uint8_t*>(w) + table_bytes + (((int64_t)C * k + 15) / 16) * 16,
+                                   out, out_ld, B, C, T_in, T_out, k, dilation, pad, epi, stream);
   if (epi->mode == QASR_EPI_STATS) {   // the statistics epilogue lives in the IMMA engine
     if (table_bytes == 0) {
       qasr_set_error("dwconv: STATS pass needs the IMMA engine (tap window of k=%d dilation=%d exceeds 6 x 32)", k, dilation);

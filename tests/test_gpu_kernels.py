@@ -440,11 +440,13 @@ DW_CASES = [
 ]
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["imma", "tcgen05", "tcgen05_rows"])
+@pytest.fixture(params=[0, 1, 2, 3], ids=["imma", "tcgen05", "tcgen05_rows", "tape"])
 def dw_engine(request):
     """Forces one of the depthwise engines (bring-up knobs 8 / 11) so all are checked on every case: IMMA,
-    tcgen05 with TMA-fetched windows, tcgen05 with bulk-copied rows cut into windows in shared memory."""
-    L.lib().qasr_debug_set(8, min(request.param, 1))
+    tcgen05 with TMA-fetched windows, tcgen05 with bulk-copied rows cut into windows in shared memory, and the tape
+    engine (tcgen05 on the utterance rows themselves through overlapping descriptors; strided cases fall through to
+    the default engine)."""
+    L.lib().qasr_debug_set(8, 2 if request.param == 3 else min(request.param, 1))
     L.lib().qasr_debug_set(11, 1 if request.param == 2 else -1)
     yield request.param
     L.lib().qasr_debug_set(8, -1)
