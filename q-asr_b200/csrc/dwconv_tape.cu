@@ -16,8 +16,16 @@
 //
 // Work item = (channel, chunk of `nb` utterances); a CTA walks a contiguous range of items, double-buffering tapes.
 // Warp roles (608 threads, 1 CTA / SM): warps 0..15 epilogue (quarter = warp & 3 is the TMEM lane quarter, warp >> 2
-// the unit of the round), warp 16 producer (bulk copies), warp 17 MMA issuer, warp 18 TMEM allocator.
+// the unit of the round), warp 16 producer, warp 17 MMA issuer, warp 18 TMEM allocator.
+// Input delivery, measured per item of 22 rows x 800 bytes: one bulk copy per row 1.0-1.3 us (~47 clk per copy on the
+// SM's copy engine), LDG / STS pairs 3.3 us (a full L2 latency per batch of 8), 16-byte cp.async 1.8-2.2 us; hence ONE
+// TMA tensor copy per item through a 4-D view of the tensor.
 // A "round" = 4 units (one per epilogue group) = 64 TMEM columns; 8 rounds of accumulators are in flight.
+// TMEM reads deliver 64 bytes per clock per SM, i.e. 16 outputs per clock: 5.6 us for a 512-channel layer at batch
+// 64 x 800 frames, the floor of any tcgen05 depthwise kernel.  The epilogue's arithmetic (~115 warp instructions per
+// 512 outputs, issue-bound at about the same 5-6 us) therefore has to OVERLAP the reads: every epilogue warp keeps the
+// tcgen05.ld of its next unit in flight while it requantises and stores the current one (two register buffers), across
+// item boundaries.
 #include <cuda.h>
 
 #include "qasr_common.cuh"
@@ -28,10 +36,12 @@ namespace {
 using namespace qasr_tc;
 
 constexpr int kEpiWarps = 16;
-constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kAllocWarp = kEpiWarps + 2;
-constexpr int kThreads = 32 * (kEpiWarps + 3);
+constexpr int kProdWarps = 1;
+constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + kProdWarps, kAllocWarp = kMmaWarp + 1;
+constexpr int kThreads = 32 * (kEpiWarps + kProdWarps + 2);
 constexpr int kMaxBufs = 4;
 constexpr int kSlots = 8;                 // accumulator rounds in flight: 8 x 64 columns = the 512 TMEM columns
+constexpr int kRound = 4;                 // units per round: one per epilogue group
 constexpr int kMaxKS = 8;
 constexpr uint32_t kBmatBytes = 512;      // one K step of the 16 x K weight matrix: 2 n-groups x 2 k-chunks x 128 B
 constexpr uint32_t kSmemBudget = 227 * 1024;
@@ -49,13 +59,51 @@ struct TapeArgs {
   int copy_bytes;    // T_in rounded up to 16
   int nb, nbc, items;
   int nbuf;
+  int inner;         // TMA view of a row: [T / inner][inner] (inner divides G and copy_bytes)
   uint32_t tape_bytes;   // one tape buffer
   float inv_rpu;
   uint32_t idesc;
+  int dbg_skip;      // qasr_debug_set 6: 1 = epilogue drains TMEM only, 2 = no MMA issue, 4 = no input copies
+  unsigned long long* dbg_trace;   // qasr_debug_set 7: device buffer, role timeline of CTA 0 (4 x 256 slots)
   unsigned long long* stamp;
   EpiArgs ep;
 };
 
+// The producer runs at most kMaxBufs items ahead of the MMA issuer, which runs at most kSlots rounds (>= 1 round per item)
+// ahead of the epilogue: 16 slots never wrap onto a record that is still to be read.
+constexpr int kChanRing = 16;
+struct alignas(16) ChanSlot {
+  int4 rec;
+  float r;
+  int pad[3];
+};
+
+#define TAPE_TRACE(role, n) do { if (a.dbg_trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (n) < 256) { a.dbg_trace[(role) * 256 + (n)] = qasr_globaltimer(); } } while (0)
+
+__device__ __forceinline__ void mbar_poll(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spin > (1u << 26)) __trap();   // a wedged pipeline traps instead of hanging the GPU
+  }
+}
+// suspending wait without a time hint: the warp sleeps in hardware (no issue slots taken from the computing warps of its
+// scheduler, which a polling loop of 16 waiting warps does) and is woken by the phase change or a short system time-out
+__device__ __forceinline__ void mbar_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spin > (1u << 24)) __trap();
+  }
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t p;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
@@ -67,7 +115,28 @@ __device__ __forceinline__ uint64_t desc_noswizzle(uint32_t addr, uint32_t lbo, 
          ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) dwconv_tape_kernel(const TapeArgs a) {
+// 16 accumulators of one lane (16 consecutive frames of one channel) -> 16 codes.  MODE: 0 = float fast path,
+// 1 = integer fast path, 2 = literal recipe (one channel per work item: the choice is warp-uniform)
+template <int MODE>
+__device__ __forceinline__ void tape_codes(const EpiArgs& ep, const EpiConsts& kc, const ChanRegs& c0, const int (&acc)[16],
+                                           uint32_t (&w)[4]) {
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    int q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int v = acc[4 * q4 + j];
+      q[j] = MODE == 0 ? (int)epilogue_f32_bits(kc, v, c0)
+                       : (MODE == 1 ? epilogue_fast<false, false, false>(ep, kc, v, c0, 0, c0, 0)
+                                    : epilogue_exact(ep, kc, v, c0, false, 0, c0, 0));
+    }
+    w[q4] = pack4(q[0], q[1], q[2], q[3]);
+  }
+}
+
+// LIT: the epilogue carries the literal (double-precision) recipe as well -- only layers with a channel that needs it
+template <bool LIT>
+__global__ void __launch_bounds__(kThreads, 1) dwconv_tape_kernel(const __grid_constant__ CUtensorMap tmX, const TapeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -78,12 +147,15 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tape_kernel(const TapeArgs
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * kMaxBufs + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * kMaxBufs + kSlots + s); };
   const uint32_t tmem_slot = bars + 8u * (2 * kMaxBufs + 2 * kSlots);
+  // channel records of the items in flight (written by the producer, read by the epilogue warps): {int4 record, float r}
+  ChanSlot* const chan_ring = reinterpret_cast<ChanSlot*>(smem_gen + (bars + 8u * (2 * kMaxBufs + 2 * kSlots + 2) - smem_base));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int i0 = (int)((long long)blockIdx.x * a.items / gridDim.x);
   const int i1 = (int)((long long)(blockIdx.x + 1) * a.items / gridDim.x);
+  if (threadIdx.x == 0) TAPE_TRACE(3, 0);
 
   if (warp == kMmaWarp && lane == 0) {
     for (int s = 0; s < kMaxBufs; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -107,30 +179,42 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tape_kernel(const TapeArgs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int nbc = a.nbc, nb = a.nb, rpu = a.rpu;
+  if (threadIdx.x == 0) TAPE_TRACE(3, 1);
 
   if (warp == kProducerWarp) {
-    // ===================== producer: one bulk copy per utterance row + the channel's weight matrix =====================
+    // ===================== producer: ONE tensor copy per item =====================
+    // The (B, C, T) tensor is described to TMA as [B][C][T / inner][inner]; a box [nb][1][rpu * 16 / inner][inner] that starts
+    // G / inner rows BEFORE the utterance lands in shared memory as nb x P contiguous bytes = the tape, with the gap in
+    // front of every utterance (and whatever lies past the end of a row or of the batch) zero-filled by TMA.
     pdl_wait();   // the activation rows come from the previous kernel
-    if (lane == 0) qasr_stamp_begin(a.stamp);
+    if (lane == 0) {
+      qasr_stamp_begin(a.stamp);
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    }
     int buf = 0;
     uint32_t phase = 0;
     int c = i0 / nbc, bc = i0 - c * nbc;
     for (int it = i0; it < i1; ++it) {
-      const int b0 = bc * nb, nrows = min(nb, a.B - b0);
       mbar_wait(empty_bar(buf), phase ^ 1u);
+      TAPE_TRACE(0, 2 * (it - i0));
       if (lane == 0) {
-        mbar_expect_tx(full_bar(buf), (uint32_t)(nrows * a.copy_bytes) + (uint32_t)a.KS * kBmatBytes);
+        // the item's channel record, with the float multiplier of the fast path derived here (off the epilogue's path)
+        const int4 rec = __ldg(reinterpret_cast<const int4*>(a.ep.ch0) + c);
+        ChanSlot& cs = chan_ring[(it - i0) & (kChanRing - 1)];
+        cs.rec = rec;
+        cs.r = (a.ep.flags & QASR_F_FAST_F32) ? __double2float_rn(dyad_mult(rec.z, rec.w & 0x7fffffff))
+                                              : (a.ep.rf != nullptr ? __ldg(a.ep.rf + c) : 0.0f);
+        mbar_expect_tx(full_bar(buf), (uint32_t)(nb * a.P) + (uint32_t)a.KS * kBmatBytes);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(bmat_base + (uint32_t)buf * kMaxKS * kBmatBytes), "l"(a.bmat + (size_t)c * a.KS * kBmatBytes),
                        "r"((uint32_t)a.KS * kBmatBytes), "r"(full_bar(buf)) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(smem_base + (uint32_t)buf * a.tape_bytes), "l"(&tmX), "r"(full_bar(buf)), "r"(0), "r"(-(a.G / a.inner)), "r"(c),
+              "r"(bc * nb) : "memory");
       }
       __syncwarp();
-      const uint32_t dst0 = smem_base + (uint32_t)buf * a.tape_bytes + (uint32_t)a.G;
-      const uint8_t* src0 = a.x + ((size_t)b0 * a.C + c) * a.x_ld;
-      for (int r = lane; r < nrows; r += 32)
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(dst0 + (uint32_t)(r * a.P)), "l"(src0 + (size_t)r * a.C * a.x_ld), "r"((uint32_t)a.copy_bytes),
-                       "r"(full_bar(buf)) : "memory");
+      TAPE_TRACE(0, 2 * (it - i0) + 1);
       if (++buf == a.nbuf) { buf = 0; phase ^= 1u; }
       if (++bc == nbc) { bc = 0; ++c; }
     }
@@ -139,108 +223,172 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tape_kernel(const TapeArgs
     const bool leader = elect_one();
     const uint32_t idesc = a.idesc;
     const int KS = a.KS;
+    const uint64_t a_hi = desc_noswizzle(0, 16u, 128u), b_hi = desc_noswizzle(0, 128u, 256u);
     int buf = 0, slot = 0;
     uint32_t phase = 0, sphase = 0;
     int bc = i0 % nbc;
     for (int it = i0; it < i1; ++it) {
       const int nrows = min(nb, a.B - bc * nb);
       const int units = (nrows * rpu + 127) >> 7;
+      TAPE_TRACE(1, 3 * (it - i0));
       mbar_wait(full_bar(buf), phase);
+      TAPE_TRACE(1, 3 * (it - i0) + 1);
       tc_fence_after();
       const uint32_t tape = smem_base + (uint32_t)buf * a.tape_bytes;
       const uint32_t bm = bmat_base + (uint32_t)buf * kMaxKS * kBmatBytes;
-      for (int u = 0; u < units; u += 4) {
-        mbar_wait(tempty_bar(slot), sphase ^ 1u);
+      for (int u = 0; u < units; u += kRound) {
+        mbar_poll(tempty_bar(slot), sphase ^ 1u);
         tc_fence_after();
-        if (leader) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (u + g < units) {
-              const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 64 + g * 16);
-              const uint32_t a_addr = tape + (uint32_t)(u + g) * 2048u;
-              for (int ks = 0; ks < KS; ++ks)
-                tc_mma_i8(d_tmem, desc_noswizzle(a_addr + 32u * ks, 16u, 128u),
-                          desc_noswizzle(bm + (uint32_t)ks * kBmatBytes, 128u, 256u), idesc, ks != 0 ? 1u : 0u);
-            }
+        // descriptors as warp-uniform values (low word = address >> 4, advanced by plain adds): they live in uniform
+        // registers and the elected lane issues back to back (see gemm_tc.cu)
+        const uint32_t a_lo0 = ((tape & 0x3FFFFu) >> 4) + (uint32_t)u * 128u, b_lo0 = (bm & 0x3FFFFu) >> 4;
+        const uint32_t d0 = tmem_base + (uint32_t)(slot * kRound * 16);
+        const int ng = min(kRound, units - u);
+        if (leader && !(a.dbg_skip & 2)) {
+          // K step outermost: consecutive MMAs write different accumulators (a dependent accumulate waits for the
+          // whole pipeline latency of its predecessor, which at N = 16 is several times the MMA's own slot)
+          for (int ks = 0; ks < KS; ++ks) {
+            for (int g = 0; g < ng; ++g)
+              tc_mma_i8(d0 + (uint32_t)(g * 16), a_hi | (uint64_t)(a_lo0 + (uint32_t)(g * 128 + ks * 2)),
+                        b_hi | (uint64_t)(b_lo0 + (uint32_t)(ks * 32)), idesc, ks != 0 ? 1u : 0u);
           }
-          tc_commit(tfull_bar(slot));
         }
+        if (leader) tc_commit(tfull_bar(slot));
         __syncwarp();
         if (++slot == kSlots) { slot = 0; sphase ^= 1u; }
       }
       if (leader) tc_commit(empty_bar(buf));   // the tape is free once every MMA that reads it has retired
       __syncwarp();
+      TAPE_TRACE(1, 3 * (it - i0) + 2);
       if (++buf == a.nbuf) { buf = 0; phase ^= 1u; }
       if (++bc == nbc) bc = 0;
     }
   } else if (warp < kEpiWarps) {
     // ===================== epilogue: TMEM -> codes -> one 16-byte store per lane =====================
+    // Every warp keeps the TMEM load of its NEXT unit in flight while it requantises and stores the current one (two
+    // register buffers, alternating), also across item boundaries.  What a unit needs later is reduced to a 4-register
+    // job at issue time (where its lane stores, how many of its 16 frames are valid, which channel record it uses).
     const int quarter = warp & 3, grp = warp >> 2;
     const EpiConsts kc = make_epi_consts(a.ep, false);
     const bool masked = a.ep.flags & QASR_F_MASK;
     const bool literal_all = a.ep.flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64);
     const bool dyn = a.ep.flags & QASR_F_DEVICE_TABLES;
     pdl_wait();   // out / out_lens (and device-written tables) belong to the stream order
-    int slot = 0, rot = 0;   // rot: which position of a round this group takes; advances so units go round-robin over groups
-    uint32_t sphase = 0;
-    int c = i0 / nbc, bc = i0 - c * nbc;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    for (int it = i0; it < i1; ++it) {
-      const int b0 = bc * nb, nrows = min(nb, a.B - b0);
-      const int rows_total = nrows * rpu, units = (rows_total + 127) >> 7;
-      const ChanRegs c0 = load_chan0(a.ep, c);
-      // 0 = float fast path, 1 = integer fast path, 2 = literal recipe: one channel per item, so warp-uniform
-      const int mode = c0.r != 0.0f ? 0 : ((literal_all && !(dyn && !c0.literal)) ? 2 : 1);
-      uint8_t* const out_c = reinterpret_cast<uint8_t*>(a.out) + (size_t)c * a.out_ld;
-      for (int u = 0; u < units; u += 4) {
-        mbar_wait(tfull_bar(slot), sphase);
-        tc_fence_after();
-        int acc[16];
-        const int pos = (grp + rot) & 3;
-        const bool have = u + pos < units;
-        if (have) {
-          tmem_ld16(lane_addr + (uint32_t)(slot * 64 + pos * 16), acc);
-          tmem_ld_wait();
+    const int lane_row = quarter * 32 + lane;
+    uint8_t* const out = reinterpret_cast<uint8_t*>(a.out);
+    constexpr int kNoStore = INT_MIN;
+
+    struct Job {
+      uint8_t* ptr;   // this lane's 16 output bytes
+      int nvalid;     // frames of them below the utterance's length (<= 0: all zero); kNoStore: a row of the gap
+      int ring;       // slot of the channel record
+    };
+    // walk over the rounds of the CTA's items: group g takes position (g + rot) & 3 of every round; rot carries the deal
+    // over the item boundary so that the groups stay evenly loaded
+    int it = i0, c = i0 / nbc, bc = i0 - c * nbc;
+    int u = 0, units = 0, rows_total = 0, rot = 0;
+    uint32_t slot = 0, sphase = 0;
+    auto open_item = [&]() {
+      rows_total = min(nb, a.B - bc * nb) * rpu;
+      units = (rows_total + 127) >> 7;
+      u = 0;
+    };
+    // waits for the next round's accumulators; starts the TMEM load of this group's unit and fills in its job
+    auto issue = [&](int (&acc)[16], Job& j) -> bool {
+      mbar_sleep(tfull_bar(slot), sphase);
+      tc_fence_after();
+      const int pos = (grp + rot) & 3;
+      const int unit = u + pos;
+      if (unit >= units) return false;
+      tmem_ld16(lane_addr + (uint32_t)(slot * (kRound * 16) + pos * 16), acc);
+      const int R = unit * 128 + lane_row;                        // tape row of this lane
+      const int bl = __float2int_rz(((float)R + 0.5f) * a.inv_rpu);
+      const int i = R - bl * rpu;
+      const int b = bc * nb + bl;
+      const bool valid = R < rows_total && i < a.rows_valid;       // else: a row of the gap, no output frames
+      int len = a.T_out;
+      if (masked && valid) len = min(__ldg(a.ep.out_lens + b), len);
+      j.ptr = out + ((size_t)b * a.C + c) * a.out_ld + 16 * i;
+      j.nvalid = valid ? len - 16 * i : kNoStore;
+      j.ring = (it - i0) & (kChanRing - 1);
+      return true;
+    };
+    // after the load has landed: hand the TMEM slot back and step the walk
+    auto retire = [&]() {
+      tc_fence_before();
+      mbar_arrive_warp(tempty_bar(slot));
+      if (++slot == kSlots) { slot = 0; sphase ^= 1u; }
+      u += kRound;
+      if (u >= units) {
+        rot = (rot - units) & 3;
+        ++it;
+        if (++bc == nbc) { bc = 0; ++c; }
+        if (it < i1) open_item();
+      }
+    };
+    // 16 accumulators -> 16 codes, length mask, one 16-byte store
+    auto finish = [&](const int (&acc)[16], const Job& j) {
+      if (j.nvalid == kNoStore || (a.dbg_skip & 1)) return;
+      // the producer wrote the record before the tape became full, the MMA issuer saw the tape full before it committed
+      // the round this unit came from
+      const ChanSlot& cs = chan_ring[j.ring];
+      ChanRegs c0;
+      c0.r = cs.r;
+      c0.bias = cs.rec.y;
+      uint32_t w[4];
+      if (c0.r != 0.0f) {                                  // float fast path (one channel per unit: warp-uniform)
+        tape_codes<0>(a.ep, kc, c0, acc, w);
+      } else {
+        const int4 rec = cs.rec;
+        c0.s = __int_as_float(rec.x);
+        c0.m = rec.z;
+        c0.e = rec.w & 0x7fffffff;
+        c0.literal = rec.w < 0;
+        if (LIT && literal_all && !(dyn && !c0.literal)) {  // literal recipe
+          c0.mult = dyad_mult(c0.m, c0.e);
+          tape_codes<2>(a.ep, kc, c0, acc, w);
+        } else {                                           // integer fast path
+          c0.sh = max(c0.e - 32, 0);
+          c0.add = (long long)c0.bias * (long long)c0.m + ((c0.e >= 1 && c0.e <= 62) ? (1ll << (c0.e - 1)) : 0ll);
+          tape_codes<1>(a.ep, kc, c0, acc, w);
         }
-        tc_fence_before();
-        mbar_arrive_warp(tempty_bar(slot));
-        if (++slot == kSlots) { slot = 0; sphase ^= 1u; }
-        if (!have) continue;
-        const int R = (u + pos) * 128 + quarter * 32 + lane;      // tape row of this lane
-        const int bl = __float2int_rz(((float)R + 0.5f) * a.inv_rpu);
-        const int i = R - bl * rpu;
-        if (R >= rows_total || i >= a.rows_valid) continue;       // a row of the gap: no output frames
-        const int b = b0 + bl, t0 = 16 * i;
-        const int len = masked ? min(a.ep.out_lens[b], a.T_out) : a.T_out;
-        uint32_t w[4];
+      }
+      if (j.nvalid < 16) {   // length mask / row tail: zero the bytes at t >= len
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          int q[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int v = acc[4 * q4 + j];
-            q[j] = mode == 0 ? (int)epilogue_f32_bits(kc, v, c0)
-                             : (mode == 1 ? epilogue_fast<false, false, false>(a.ep, kc, v, c0, 0, c0, 0)
-                                          : epilogue_exact(a.ep, kc, v, c0, false, 0, c0, 0));
-          }
-          w[q4] = pack4(q[0], q[1], q[2], q[3]);
+          const int nv = j.nvalid - 4 * q4;
+          w[q4] &= nv >= 4 ? 0xffffffffu : (nv <= 0 ? 0u : (0xffffffffu >> (8 * (4 - nv))));
         }
-        if (t0 + 16 > len) {   // length mask / row tail: zero the bytes at t >= len
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const int nvalid = len - (t0 + 4 * q4);
-            w[q4] &= nvalid >= 4 ? 0xffffffffu : (nvalid <= 0 ? 0u : (0xffffffffu >> (8 * (4 - nvalid))));
-          }
-        }
-        *reinterpret_cast<uint4*>(out_c + (size_t)b * a.C * a.out_ld + t0) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      rot = (rot - units) & 3;   // the next item's first unit goes to the group after the one that took this item's last
-      if (++bc == nbc) { bc = 0; ++c; }
+      *reinterpret_cast<uint4*>(j.ptr) = make_uint4(w[0], w[1], w[2], w[3]);
+    };
+
+    if (it < i1) {
+      int accA[16], accB[16];
+      Job jA, jB;
+      open_item();
+      bool hA = issue(accA, jA), hB = false;
+      for (;;) {
+        if (hA) tmem_ld_wait();
+        retire();
+        const bool moreB = it < i1;
+        if (moreB) hB = issue(accB, jB);
+        if (hA) finish(accA, jA);
+        if (!moreB) break;
+        if (hB) tmem_ld_wait();
+        retire();
+        const bool moreA = it < i1;
+        if (moreA) hA = issue(accA, jA);
+        if (hB) finish(accB, jB);
+        if (!moreA) break;
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TAPE_TRACE(3, 2);
   if (threadIdx.x == 0) qasr_stamp_end(a.stamp);
   if (warp == kAllocWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -269,7 +417,7 @@ struct TapeGeom {
 };
 inline TapeGeom tape_geom(int k, int dil, int pad) {
   TapeGeom g;
-  g.G = round_up_i(pad > 0 ? pad : 1, 16);
+  g.G = round_up_i(pad > 0 ? pad : 1, 32);   // multiple of 32: rows whose length is one too can travel as 32-byte TMA rows
   g.d = g.G - pad;
   g.KS = (16 + (k - 1) * dil + g.d + 31) / 32;
   return g;
@@ -324,7 +472,7 @@ int qasr_dwconv_tape_launch(const void* x, int x_ld, const uint8_t* bmat, void* 
   a.items = C * a.nbc;
   const int units_max = (nb * a.rpu + 127) / 128;
   a.tape_bytes = (uint32_t)round_up_i(units_max * 2048 + 32 * a.KS + 16, 128);
-  const uint32_t fixed = 128 /*align*/ + 8u * (2 * kMaxBufs + 2 * kSlots + 2);
+  const uint32_t fixed = 128 /*align*/ + 8u * (2 * kMaxBufs + 2 * kSlots + 2) + kChanRing * (uint32_t)sizeof(ChanSlot);
   int nbuf = (int)((kSmemBudget - fixed) / (a.tape_bytes + kMaxKS * kBmatBytes));
   if (nbuf > kMaxBufs) nbuf = kMaxBufs;
   if (nbuf < 2) {
@@ -336,7 +484,29 @@ int qasr_dwconv_tape_launch(const void* x, int x_ld, const uint8_t* bmat, void* 
   // instruction descriptor: D = S32, A = activations (un)signed 8-bit K-major, B = weights signed 8-bit K-major, N = 16, M = 128
   a.idesc = (2u << 4) | (a_signed << 7) | (1u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(16 >> 3) << 17) |
             ((uint32_t)(128 >> 4) << 24);
+  // row view for TMA: the largest inner length that divides both the gap and the row (16 always does)
+  int inner = 16;
+  for (int cand = 256; cand > 16; cand -= 16)
+    if (a.G % cand == 0 && a.copy_bytes % cand == 0) { inner = cand; break; }
+  if (qasr_debug_get(14) >= 16 && a.G % (int)qasr_debug_get(14) == 0 && a.copy_bytes % (int)qasr_debug_get(14) == 0)
+    inner = (int)qasr_debug_get(14);   // bring-up: force the inner length
+  a.inner = inner;
+  CUtensorMap map;
+  {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { qasr_set_error("cuTensorMapEncodeTiled entry point not available"); return QASR_ERR_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)(a.copy_bytes / inner), (cuuint64_t)C, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)inner, (cuuint64_t)x_ld, (cuuint64_t)x_ld * (cuuint64_t)C};
+    cuuint32_t box[4] = {(cuuint32_t)inner, (cuuint32_t)(a.P / inner), 1, (cuuint32_t)a.nb};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { qasr_set_error("cuTensorMapEncodeTiled(tape) failed: %d", (int)r); return QASR_ERR_CUDA; }
+  }
   a.ep = make_epi_args(epi);
+  a.dbg_skip = qasr_debug_get(6) > 0 ? (int)qasr_debug_get(6) : 0;
+  a.dbg_trace = qasr_debug_get(7) > 0 ? reinterpret_cast<unsigned long long*>(qasr_debug_get(7)) : nullptr;
   a.stamp = qasr_next_stamp();
   const size_t smem = fixed + (size_t)nbuf * (a.tape_bytes + kMaxKS * kBmatBytes);
   int grid = sms < a.items ? sms : a.items;
@@ -344,9 +514,15 @@ int qasr_dwconv_tape_launch(const void* x, int x_ld, const uint8_t* bmat, void* 
   int dev = 0;
   QASR_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    QASR_CHECK_CUDA(cudaFuncSetAttribute(dwconv_tape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    QASR_CHECK_CUDA(cudaFuncSetAttribute(dwconv_tape_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    QASR_CHECK_CUDA(cudaFuncSetAttribute(dwconv_tape_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
     attr_set[dev] = true;
   }
-  QASR_CHECK_CUDA(qasr_launch_pdl(dwconv_tape_kernel, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream, a));
+  const bool lit = a.ep.flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64);
+  if (lit) {
+    QASR_CHECK_CUDA(qasr_launch_pdl(dwconv_tape_kernel<true>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream, map, a));
+  } else {
+    QASR_CHECK_CUDA(qasr_launch_pdl(dwconv_tape_kernel<false>, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream, map, a));
+  }
   return qasr_check_launch("dwconv_tape_kernel");
 }

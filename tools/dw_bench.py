@@ -36,8 +36,22 @@ def run(C, k, dil, knobs, iters=20):
     return np.median(ts)
 
 
-for (C, k, dil) in ((512, 33, 1), (512, 75, 1), (256, 33, 1), (512, 87, 2)):
-    print("C=%d k=%d dil=%d: imma %6.1f us   tcgen05 %6.1f us" % (C, k, dil, run(C, k, dil, {8: 0}), run(C, k, dil, {8: 1})), flush=True)
+for (C, k, dil) in ((512, 33, 1), (512, 51, 1), (512, 63, 1), (512, 75, 1), (256, 33, 1), (256, 39, 1), (512, 87, 2)):
+    print("C=%d k=%d dil=%d: imma %6.1f us   tcgen05 %6.1f us   tape %6.1f us" % (
+        C, k, dil, run(C, k, dil, {8: 0}), run(C, k, dil, {8: 1}), run(C, k, dil, {8: 2})), flush=True)
+if len(sys.argv) > 1 and sys.argv[1] == "tapeinner":
+    for inner in (16, 32):
+        print("tape, TMA rows of %3d bytes: C=512 k=33 %6.1f us   C=512 k=75 %6.1f us   loads only k=33 %6.1f us" % (
+            inner, run(512, 33, 1, {8: 2, 14: inner}), run(512, 75, 1, {8: 2, 14: inner}), run(512, 33, 1, {8: 2, 14: inner, 6: 3})), flush=True)
+if len(sys.argv) > 1 and sys.argv[1] == "tapeknobs":
+    for name, kn in (("full", {}), ("no epilogue math", {6: 1}), ("no mma", {6: 2}), ("no copies", {6: 4}), ("no mma, no epilogue", {6: 3}),
+                     ("skeleton", {6: 7})):
+        kn = dict(kn); kn[8] = 2
+        print("tape C=512 %-20s k=33 %6.1f us   k=75 %6.1f us" % (name, run(512, 33, 1, kn), run(512, 75, 1, kn)), flush=True)
+if len(sys.argv) > 1 and sys.argv[1] == "tape":
+    for nb in (4, 8, 11, 16, 22, 32, 64):
+        print("tape, %2d utterances per item: C=512 k=33 %6.1f us   C=512 k=75 %6.1f us   C=256 k=33 %6.1f us" % (
+            nb, run(512, 33, 1, {8: 2, 15: nb}), run(512, 75, 1, {8: 2, 15: nb}), run(256, 33, 1, {8: 2, 15: nb})), flush=True)
 if len(sys.argv) > 1 and sys.argv[1] == "occupancy":
     for per_sm in (28, 32, 36, 40, 44, 48, 56, 64, 80):
         print("warps/SM wanted %3d: C=512 k=33 %6.1f us   C=512 k=75 %6.1f us   C=256 k=33 %6.1f us" % (
