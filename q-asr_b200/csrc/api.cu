@@ -8,19 +8,21 @@ thread_local char g_err[512] = "";
 // bring-up / benchmarking knobs (qasr_debug_set; not part of the public header): -1 = unset
 //   0,1: B-operand descriptor strides   2,3: TMA coordinate experiments   4: force streaming weights
 //   5: M tiles per CTA   6: skip epilogue (1) / MMA (2) / stores (4)   8: depthwise path (0 = IMMA, 1 = tcgen05)
-long long g_dbg[16] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+//   16: IMMA depthwise rows end with the masked tail path (1) instead of the shifted full tile
+constexpr int kKnobs = 24;
+long long g_dbg[kKnobs] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
 }
 
 extern "C" int qasr_debug_set(int key, long long value) {
-  if (key < 0 || key >= 16) return QASR_ERR_INVALID;
+  if (key < 0 || key >= kKnobs) return QASR_ERR_INVALID;
   g_dbg[key] = value;
   return QASR_OK;
 }
-long long qasr_debug_get(int key) { return key >= 0 && key < 16 ? g_dbg[key] : -1; }
+long long qasr_debug_get(int key) { return key >= 0 && key < kKnobs ? g_dbg[key] : -1; }
 // how many bring-up knobs are set: bench.py refuses to time the kernels unless this is 0
 extern "C" int qasr_debug_knobs_set(void) {
   int n = 0;
-  for (int i = 0; i < 16; ++i) n += g_dbg[i] != -1;
+  for (int i = 0; i < kKnobs; ++i) n += g_dbg[i] != -1;
   return n;
 }
 

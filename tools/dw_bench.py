@@ -39,6 +39,35 @@ def run(C, k, dil, knobs, iters=20):
 for (C, k, dil) in ((512, 33, 1), (512, 51, 1), (512, 63, 1), (512, 75, 1), (256, 33, 1), (256, 39, 1), (512, 87, 2)):
     print("C=%d k=%d dil=%d: imma %6.1f us   tcgen05 %6.1f us   tape %6.1f us" % (
         C, k, dil, run(C, k, dil, {8: 0}), run(C, k, dil, {8: 1}), run(C, k, dil, {8: 2})), flush=True)
+if len(sys.argv) > 1 and sys.argv[1] == "cold":
+    # the same launch on rotating buffer sets (together larger than the 126 MB L2): every launch reads cold rows
+    def run_rot(C, k, nsets, engine):
+        pad = k // 2
+        xs = [torch.randint(0, 64, (B, C, T), dtype=torch.int8, device=dev) for _ in range(nsets)]
+        outs = [torch.zeros((B, C, T), dtype=torch.int8, device=dev) for _ in range(nsets)]
+        w = torch.randint(-31, 32, (C, k), dtype=torch.int8, device=dev)
+        wd = ops.pack_dw_weights(w, 1, 1, pad)
+        ch = ops.chan_table(np.full(C, 1e-4, np.float32), np.zeros(C), np.full(C, (1 << 30) + 12345), np.full(C, 40), dev)
+        ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=L.F_FAST_F32, qmin=-32, qmax=31)
+        lib.qasr_debug_set(8, engine)
+        for i in range(nsets): ops.dwconv(xs[i], T, wd, outs[i], T, k, 1, 1, pad, ep)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        iters = 4 * nsets
+        with torch.cuda.graph(g):
+            for i in range(iters): ops.dwconv(xs[i % nsets], T, wd, outs[i % nsets], T, k, 1, 1, pad, ep)
+        g.replay(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); g.replay(); b.record(); b.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3 / iters)
+        lib.qasr_debug_set(8, -1)
+        return np.median(ts)
+    for (C, k) in ((512, 33), (512, 63), (256, 33)):
+        n = 8 if C == 512 else 16
+        print("C=%d k=%d: imma warm %6.1f us   cold (%d buffer sets) %6.1f us   tape warm %6.1f   tape cold %6.1f" % (
+            C, k, run_rot(C, k, 1, 0), n, run_rot(C, k, n, 0), run_rot(C, k, 1, 2), run_rot(C, k, n, 2)), flush=True)
 if len(sys.argv) > 1 and sys.argv[1] == "tapeinner":
     for inner in (16, 32):
         print("tape, TMA rows of %3d bytes: C=512 k=33 %6.1f us   C=512 k=75 %6.1f us   loads only k=33 %6.1f us" % (
