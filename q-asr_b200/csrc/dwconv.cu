@@ -32,80 +32,13 @@
 #include <type_traits>
 
 #include "qasr_common.cuh"
+#include "dw_common.cuh"
 
 #ifndef QASR_TAPE_DEFAULT
 #define QASR_TAPE_DEFAULT 0   // engine choice without knob 8: 1 = tape engine wherever it applies
 #endif
 
 namespace {
-
-constexpr int kWarps = 4;
-constexpr int kThreads = 32 * kWarps;
-constexpr int kTile = 128;   // outputs per warp tile
-constexpr int kBufs = 3;     // input rows in flight per warp (bulk async copies, 2 ahead)
-constexpr uint32_t kSpinLimit = 1u << 24;
-
-struct DwArgs {
-  const uint8_t* x;
-  const int8_t* w;
-  void* out;
-  int x_ld, out_ld, B, C, T_in, T_out, k, stride, dil, pad;
-  int d;          // (-pad) mod 8
-  int bchunk;     // utterances per warp work item
-  int nbg;        // ceil(B / bchunk)
-  int halo;       // zero bytes in front of the row inside a staging buffer (multiple of 16, >= pad + d)
-  int copy_bytes; // T_in rounded up to 16: bytes of one bulk copy
-  int buf_bytes;  // one staging buffer (multiple of 128)
-  unsigned long long* stamp;   // in-graph timing slot (qasr_profile_begin) or nullptr
-  EpiArgs ep;
-};
-
-template <bool XS>
-__device__ __forceinline__ void imma_16832(int (&acc)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  if (XS)
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-  else
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// first MMA of a chain: D = A x B + C with every C register = c (the initial accumulator value), D written to
-// fresh registers, so the loop needs no moves to re-initialise its accumulators
-template <bool XS>
-__device__ __forceinline__ void imma_16832_init(int (&acc)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, int c) {
-  if (XS)
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
-                 : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(c));
-  else
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
-                 : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(c));
-}
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (spin > kSpinLimit) __trap();
-  }
-}
-// one input row global -> shared through the bulk-copy engine, completion on an mbarrier
-__device__ __forceinline__ void row_copy_async(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
 
 // EK: 0 = REQUANT all-integer fast path, 1 = REQUANT literal path, 2 = DEQUANT_F32 / RAW_I32 / STATS,
 //     3 = REQUANT float fast path (QASR_F_FAST_F32), 4 = REQUANT with device-written tables (QASR_F_DEVICE_TABLES):
@@ -398,13 +331,6 @@ __global__ void pack_dw_kernel(const int8_t* __restrict__ w, uint32_t* __restric
   }
 }
 
-inline int dw_misalign(int pad) { return ((-pad) % 8 + 8) % 8; }
-
-int dw_ksteps(int k, int stride, int dilation, int pad) {
-  const int d = dw_misalign(pad);
-  return (15 * stride + d + (k - 1) * dilation + 1 + 31) / 32;
-}
-
 }  // namespace
 
 // tensor-core variant (dwconv_tc.cu)
@@ -418,6 +344,11 @@ int64_t qasr_dwconv_tape_packed_bytes(int C, int k, int stride, int dilation, in
 int qasr_dwconv_tape_pack(const int8_t* w, uint8_t* bm, int C, int k, int dilation, int pad, cudaStream_t st);
 int qasr_dwconv_tape_launch(const void* x, int x_ld, const uint8_t* bmat, void* out, int out_ld, int B, int C, int T_in,
                             int T_out, int k, int dilation, int pad, const qasr_epilogue* epi, void* stream);
+
+// row-tape walk of the IMMA engine (dwconv_rt.cu): stride 1, requantising fast epilogues
+bool qasr_dwconv_rt_supported(int T_in, int k, int dilation, int pad);
+int qasr_dwconv_rt_launch(const void* x, int x_ld, const int8_t* w, void* out, int out_ld, int B, int C, int T_in, int T_out,
+                          int k, int dilation, int pad, int ek, const qasr_epilogue* epi, void* stream);
 
 // packed layout: [IMMA A-fragment table (absent when the tap window exceeds 6 x 32)] [raw taps [C][k], for the
 // tcgen05 kernel which builds its banded matrices on the fly] [16 x K weight matrices of the tape engine]
@@ -512,7 +443,19 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
                                  epi, stream);
   }
 
+  // stride-1 launches on the integer / float fast epilogues walk row tapes (dwconv_rt.cu: -25 % warp instructions per
+  // row of 800 frames); bring-up knob 16 = 0 keeps them on the row-at-a-time kernel below
+  if (stride == 1 && epi->mode == QASR_EPI_REQUANT_I8 && qasr_debug_get(16) != 0 &&
+      qasr_dwconv_rt_supported(T_in, k, dilation, pad)) {
+    const bool fast = !(epi->flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64 | QASR_F_STAGE2)) &&
+                      epi->prev == nullptr;
+    const int ek = (epi->flags & QASR_F_FAST_F32) ? 3 : (fast ? 0 : 1);
+    if (ek != 1)
+      return qasr_dwconv_rt_launch(x, x_ld, w, out, out_ld, B, C, T_in, T_out, k, dilation, pad, ek, epi, stream);
+  }
+
   DwArgs a;
+  memset(&a, 0, sizeof(a));
   a.x = static_cast<const uint8_t*>(x);
   a.w = w;
   a.out = out;

@@ -440,17 +440,20 @@ DW_CASES = [
 ]
 
 
-@pytest.fixture(params=[0, 1, 2, 3], ids=["imma", "tcgen05", "tcgen05_rows", "tape"])
+@pytest.fixture(params=[0, 1, 2, 3, 4], ids=["imma", "tcgen05", "tcgen05_rows", "tape", "imma_rows"])
 def dw_engine(request):
     """Forces one of the depthwise engines (bring-up knobs 8 / 11) so all are checked on every case: IMMA,
     tcgen05 with TMA-fetched windows, tcgen05 with bulk-copied rows cut into windows in shared memory, and the tape
     engine (tcgen05 on the utterance rows themselves through overlapping descriptors; strided cases fall through to
-    the default engine)."""
-    L.lib().qasr_debug_set(8, 2 if request.param == 3 else min(request.param, 1))
+    the default engine).  "imma" walks row tapes on the fast epilogues (dwconv_rt.cu), "imma_rows" keeps every launch on
+    the row-at-a-time kernel (bring-up knob 16 = 0)."""
+    L.lib().qasr_debug_set(8, 2 if request.param == 3 else (0 if request.param == 4 else min(request.param, 1)))
     L.lib().qasr_debug_set(11, 1 if request.param == 2 else -1)
+    L.lib().qasr_debug_set(16, 0 if request.param == 4 else -1)
     yield request.param
     L.lib().qasr_debug_set(8, -1)
     L.lib().qasr_debug_set(11, -1)
+    L.lib().qasr_debug_set(16, -1)
 
 
 @pytest.mark.parametrize("fast", [False, True, "f32"], ids=["exact", "fast", "f32"])
@@ -510,6 +513,33 @@ def test_dwconv_merged_row_tails(case, fast):
     finally:
         lib.qasr_debug_set(8, -1)
         lib.qasr_debug_set(10, -1)
+
+
+ROW_TAPE_CASES = [
+    # the row-tape walk of the IMMA engine (dwconv_rt.cu) with R rows per tape forced (bring-up knob 17): ragged lengths,
+    # batches that are not a multiple of R, rows of 6.25 / 2.6 / 1.2 tiles, gaps of 16 .. 64 bytes, 2 .. 5 K steps
+    ("k33_T800_b10", 10, 24, 800, 33, 1, 1, False),
+    ("k63_T333_b7", 7, 16, 333, 63, 1, 1, True),
+    ("k75_T150_b9", 9, 16, 150, 75, 1, 1, False),
+    ("k87_dil2_T420_b5", 5, 16, 420, 87, 1, 2, False),
+    ("k121_T300_b6", 6, 8, 300, 121, 1, 1, True),
+    ("k9_T113_b13", 13, 8, 113, 9, 1, 1, False),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows", [2, 3, 4, 8])
+@pytest.mark.parametrize("fast", [True, "f32"], ids=["fast", "f32"])
+@pytest.mark.parametrize("case", ROW_TAPE_CASES, ids=lambda c: c[0])
+def test_dwconv_row_tapes(case, fast, rows):
+    lib = L.lib()
+    lib.qasr_debug_set(8, 0)
+    lib.qasr_debug_set(17, rows)
+    try:
+        test_dwconv_requant(case, fast, 0)
+    finally:
+        lib.qasr_debug_set(8, -1)
+        lib.qasr_debug_set(17, -1)
 
 
 def test_dwconv_raw_and_dequant(dw_engine):

@@ -36,9 +36,17 @@ def run(C, k, dil, knobs, iters=20):
     return np.median(ts)
 
 
+MODE = sys.argv[1] if len(sys.argv) > 1 else ""
+if MODE == "rt":
+    # row-tape walk of the IMMA engine (dwconv_rt.cu) against the row-at-a-time kernel (knob 16 = 0); knob 17 = rows per tape
+    for (C, k, dil) in ((512, 33, 1), (512, 51, 1), (512, 63, 1), (512, 75, 1), (256, 33, 1), (256, 39, 1)):
+        print("C=%d k=%d: rows %6.1f us   tapes %6.1f us   R=2 %6.1f   R=4 %6.1f   R=8 %6.1f" % (
+            C, k, run(C, k, dil, {8: 0, 16: 0}), run(C, k, dil, {8: 0}), run(C, k, dil, {8: 0, 17: 2}),
+            run(C, k, dil, {8: 0, 17: 4}), run(C, k, dil, {8: 0, 17: 8})), flush=True)
+    sys.exit(0)
 for (C, k, dil) in ((512, 33, 1), (512, 51, 1), (512, 63, 1), (512, 75, 1), (256, 33, 1), (256, 39, 1), (512, 87, 2)):
-    print("C=%d k=%d dil=%d: imma %6.1f us   tcgen05 %6.1f us   tape %6.1f us" % (
-        C, k, dil, run(C, k, dil, {8: 0}), run(C, k, dil, {8: 1}), run(C, k, dil, {8: 2})), flush=True)
+    print("C=%d k=%d dil=%d: imma rows %6.1f us   imma tapes %6.1f us   tcgen05 %6.1f us   tape %6.1f us" % (
+        C, k, dil, run(C, k, dil, {8: 0, 16: 0}), run(C, k, dil, {8: 0}), run(C, k, dil, {8: 1}), run(C, k, dil, {8: 2})), flush=True)
 if len(sys.argv) > 1 and sys.argv[1] == "cold":
     # the same launch on rotating buffer sets (together larger than the 126 MB L2): every launch reads cold rows
     def run_rot(C, k, nsets, engine):
