@@ -90,7 +90,9 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
   const EpiConsts kc = make_epi_consts(a.ep, false);
   pdl_wait();   // activations (and the output buffer) belong to the stream order; everything above is set-up
   if (lane == 0) {
-    if (PROF) qasr_stamp_begin(a.stamp);
+    // thousands of warps on ONE address at the same moment cost a stamped launch microseconds: the first CTA on data is
+    // one of the first the grid dispatched (see dwconv_rt.cu)
+    if (PROF && warp == 0 && blockIdx.x < 296) qasr_stamp_begin(a.stamp);
     for (int r = 0; r < min(nrows, kBufs - 1); ++r)
       row_copy_async(smem_addr(bufs + r * a.buf_bytes + a.halo), xbase + r * xstep, a.copy_bytes,
                      smem_addr(bars + r));

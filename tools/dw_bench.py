@@ -18,7 +18,13 @@ def run(C, k, dil, knobs, iters=20):
     m = np.full(C, (1 << 30) + 12345); e = np.full(C, 40)
     ch = ops.chan_table(np.full(C, 1e-4, np.float32), np.zeros(C), m, e, dev)
     # timing only: the float epilogue is what 99.7 % of the bench workload's channels run (no proof needed to time it)
-    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=0 if os.environ.get("DW_INT_EPILOGUE") else L.F_FAST_F32, qmin=-32, qmax=31)
+    if os.environ.get("DW_PLAN_LIKE"):
+        # what the plan launches on most layers: length mask + the per-channel float-multiplier table (all channels proved)
+        rf = torch.full((C,), float(np.float32(((1 << 30) + 12345) * 2.0 ** -40)), dtype=torch.float32, device=dev)
+        ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=L.F_MASK | (L.F_RELU0 if os.environ.get("DW_PLAN_LIKE") == "relu" else 0), qmin=-32, qmax=31,
+                               out_lens=torch.full((B,), T, dtype=torch.int32, device=dev), f32_mult=rf)
+    else:
+        ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=0 if os.environ.get("DW_INT_EPILOGUE") else L.F_FAST_F32, qmin=-32, qmax=31)
     out = torch.zeros((B, C, T), dtype=torch.int8, device=dev)
     for kk, v in knobs.items(): lib.qasr_debug_set(kk, v)
     for _ in range(3): ops.dwconv(x, T, wd, out, T, k, 1, dil, pad, ep)
@@ -37,6 +43,10 @@ def run(C, k, dil, knobs, iters=20):
 
 
 MODE = sys.argv[1] if len(sys.argv) > 1 else ""
+if MODE == "plan":
+    for (C, k, dil) in ((512, 33, 1), (512, 63, 1), (256, 33, 1), (256, 39, 1)):
+        print("C=%d k=%d: rows %6.1f us   tapes %6.1f us   (DW_PLAN_LIKE=%s)" % (C, k, run(C, k, dil, {8: 0, 16: 0}), run(C, k, dil, {8: 0}), os.environ.get("DW_PLAN_LIKE")), flush=True)
+    sys.exit(0)
 if MODE == "rt":
     # row-tape walk of the IMMA engine (dwconv_rt.cu) against the row-at-a-time kernel (knob 16 = 0); knob 17 = rows per tape
     for (C, k, dil) in ((512, 33, 1), (512, 51, 1), (512, 63, 1), (512, 75, 1), (256, 33, 1), (256, 39, 1)):

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """In-graph timeline of the bench workload's step: per launch, start / end (first CTA on data, last CTA out) in us from
-the step's first stamp, the launch's duration and the gap to the previous launch's end.  usage: tools/stamps_dump.py [B]"""
+the step's first stamp, the launch's duration and the gap to the previous launch's end.
+usage: tools/stamps_dump.py [B] [knob=value ...] [brief]     (bring-up knobs of qasr_debug_set, e.g. 17=4)"""
 import os
 import sys
 
@@ -14,8 +15,14 @@ from qasr.params import synthetic_features  # noqa: E402
 
 dev = torch.device("cuda:0")
 wl = dict(bench.WORKLOAD)
-if len(sys.argv) > 1:
-    wl["batch"] = int(sys.argv[1])
+brief = "brief" in sys.argv
+from qasr import _lib as L  # noqa: E402
+for arg in sys.argv[1:]:
+    if "=" in arg:
+        kk, v = arg.split("=")
+        L.lib().qasr_debug_set(int(kk), int(v))
+    elif arg.isdigit():
+        wl["batch"] = int(arg)
 model = bench.build_model(dev, wl)
 x, lens = synthetic_features(wl["batch"], wl["frames"], seed=1000)
 plan = model.plan_for(x.shape, dev)
@@ -34,14 +41,20 @@ for _ in range(N):
 st = acc / N / 1e3
 prev_end = 0.0
 tot = {}
+per_shape = {}
 for (name, _), (s, e), v, nbytes in zip(plan.ops, st, ok, plan.op_bytes):
     if not v:
         continue
-    print("%-34s start %9.2f  end %9.2f  dur %7.2f  gap %6.2f  %6.0f GB/s" % (name, s, e, e - s, s - prev_end,
-                                                                               nbytes / (e - s) / 1e3))
+    if not brief:
+        print("%-34s start %9.2f  end %9.2f  dur %7.2f  gap %6.2f  %6.0f GB/s" % (name, s, e, e - s, s - prev_end,
+                                                                                   nbytes / (e - s) / 1e3))
     prev_end = e
     k = name.split("_")[0]
     tot[k] = tot.get(k, 0.0) + e - s
+    kk = "_".join(name.split("_")[:2])
+    per_shape.setdefault(kk, []).append(e - s)
+print("knobs %s: median us per launch: %s" % ([a for a in sys.argv[1:] if "=" in a],
+                                               {k: round(float(np.median(v)), 1) for k, v in per_shape.items()}))
 print("span %.2f us; per class %s" % (st[ok, 1].max(), {k: round(v, 1) for k, v in tot.items()}))
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ms = 0.0
