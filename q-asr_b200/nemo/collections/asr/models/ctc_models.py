@@ -183,12 +183,22 @@ class EncDecCTCModel(nn.Module):
         if not (self.use_fused_plan and x.is_cuda and not self.training and self.decoder.quant_mode == "symmetric"
                 and self.encoder.quant_mode == "symmetric"):
             return False
+        # stamped attributes only (quant_modules._bump): the verdict holds until the state epoch moves
+        from nemo.quantization.utils import quant_modules as _qm
+        epoch = _qm._STATE_COUNTER[0]
+        hit = getattr(self, "_dynamic_verdict", None)
+        if hit is not None and hit[0] == epoch:
+            return hit[1]
+        ok = True
         for m in self.modules():
             if type(m) is QuantAct and (m.running_stat or not m.dynamic or m.percentile or m.per_channel):
-                return False
+                ok = False
+                break
             if isinstance(m, QuantConv1d) and (m.quant_mode != "symmetric" or (m.bn is not None and not m.fix_bn)):
-                return False
-        return True
+                ok = False
+                break
+        object.__setattr__(self, "_dynamic_verdict", (epoch, ok))
+        return ok
 
     def _dynamic_plan_or_none(self, x):
         """The device-side dynamic plan for this exact input shape (a dynamic range depends on every frame of the batch,

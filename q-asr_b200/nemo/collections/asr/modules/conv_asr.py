@@ -72,12 +72,22 @@ class ConvASREncoder(nn.Module):
     def _fusable(self, audio_signal):
         if not (self.use_fused_plan and self.quant_mode == "symmetric" and audio_signal.is_cuda and not self.training):
             return False
+        # every flag below is a stamped attribute (quant_modules._bump): the verdict holds until the state epoch moves
+        from nemo.quantization.utils import quant_modules as _qm
+        epoch = _qm._STATE_COUNTER[0]
+        hit = getattr(self, "_fusable_verdict", None)
+        if hit is not None and hit[0] == epoch:
+            return hit[1]
+        ok = True
         for m in self.modules():
             if type(m) is QuantAct and (m.running_stat or m.dynamic or m.per_channel):
-                return False
+                ok = False
+                break
             if isinstance(m, QuantConv1d) and (m.quant_mode != "symmetric" or (m.bn is not None and not m.fix_bn)):
-                return False
-        return True
+                ok = False
+                break
+        object.__setattr__(self, "_fusable_verdict", (epoch, ok))
+        return ok
 
     def invalidate_plan(self):
         self._plan_cache = {}

@@ -768,16 +768,37 @@ class FusedPlan:
         return self._q[val_key]
 
 
+_QUANT_MODULES = {}   # id(encoder) -> (weakref to encoder, id(decoder), state epoch, flat list of quant modules)
+
+
+def _quant_modules(encoder, decoder):
+    """The QuantAct / QuantConv1d modules of the model as a flat list.  The recursive module walk costs ~1 ms per call
+    on QuartzNet15x5 (1 900 modules) and sat between the caller's copy and the graph launch of every forward; the
+    tree can only change through stamped attribute assignments (quant_modules._bump moves the global epoch), so the
+    list is rebuilt when the epoch moves and reused otherwise."""
+    import weakref
+    from nemo.quantization.utils import quant_modules as qmods
+    epoch = qmods._STATE_COUNTER[0]
+    hit = _QUANT_MODULES.get(id(encoder))
+    if hit is not None and hit[0]() is encoder and hit[1] == id(decoder) and hit[2] == epoch:
+        return hit[3]
+    mods = list(encoder.modules()) + (list(decoder.modules()) if decoder is not None else [])
+    mods = [m for m in mods if type(m) is qmods.QuantAct or isinstance(m, qmods.QuantConv1d)]
+    for k in [k for k, v in _QUANT_MODULES.items() if v[0]() is None]:
+        del _QUANT_MODULES[k]
+    _QUANT_MODULES[id(encoder)] = (weakref.ref(encoder), id(decoder), epoch, mods)
+    return mods
+
+
 def _signature(encoder, decoder):
     """Everything the compiled plan bakes in.  Quant modules stamp every attribute assignment (ranges, bit widths,
     flags, weights, folded BN: quant_modules._bump), in-place edits show in the tensors' version counters."""
-    from nemo.quantization.utils.quant_modules import QuantAct, QuantConv1d
+    from nemo.quantization.utils.quant_modules import QuantAct
     sig = []
-    mods = list(encoder.modules()) + (list(decoder.modules()) if decoder is not None else [])
-    for m in mods:
+    for m in _quant_modules(encoder, decoder):
         if type(m) is QuantAct:
             sig.append((m._state_version, m.x_min.data_ptr(), m.x_min._version, m.x_max.data_ptr(), m.x_max._version))
-        elif isinstance(m, QuantConv1d):
+        else:
             sig.append(m.state_signature())
     return tuple(sig)
 
