@@ -14,18 +14,19 @@
 // per-window TMA rows (the input arrives as one bulk copy per utterance row), K = 16 + (k-1) dil + d bytes of window
 // per row (k = 33: two MMAs of K = 32).  The 16 x K weight matrices are packed once per layer (qasr_pack_dw_weights).
 //
-// Work item = (channel, chunk of `nb` utterances); a CTA walks a contiguous range of items, double-buffering tapes.
+// Work item = (channel, chunk of `nb` utterances, at most 16 units of 128 tape rows); a CTA walks a contiguous range of
+// items, up to four tapes in flight.
 // Warp roles (608 threads, 1 CTA / SM): warps 0..15 epilogue (quarter = warp & 3 is the TMEM lane quarter, warp >> 2
-// the unit of the round), warp 16 producer, warp 17 MMA issuer, warp 18 TMEM allocator.
+// the group that takes every fourth unit), warp 16 producer, warp 17 MMA issuer, warp 18 TMEM allocator.
 // Input delivery, measured per item of 22 rows x 800 bytes: one bulk copy per row 1.0-1.3 us (~47 clk per copy on the
 // SM's copy engine), LDG / STS pairs 3.3 us (a full L2 latency per batch of 8), 16-byte cp.async 1.8-2.2 us; hence ONE
 // TMA tensor copy per item through a 4-D view of the tensor.
-// A "round" = 4 units (one per epilogue group) = 64 TMEM columns; 8 rounds of accumulators are in flight.
-// TMEM reads deliver 64 bytes per clock per SM, i.e. 16 outputs per clock: 5.6 us for a 512-channel layer at batch
-// 64 x 800 frames, the floor of any tcgen05 depthwise kernel.  The epilogue's arithmetic (~115 warp instructions per
-// 512 outputs, issue-bound at about the same 5-6 us) therefore has to OVERLAP the reads: every epilogue warp keeps the
-// tcgen05.ld of its next unit in flight while it requantises and stores the current one (two register buffers), across
-// item boundaries.
+// An item is ONE accumulator round (256 TMEM columns, two rounds in flight): every warp waits once per item for the
+// accumulators and hands the slot back once.  With a round per 4 units (the first version) every one of the 16 epilogue
+// warps walked the chain wait -> tcgen05.ld -> arrive ~31 times per CTA at ~400 clk each whatever the number of slots:
+// 19.8 us on 512 channels x B64 x T800 (k = 33), 16.9 us with a round per item.  tcgen05.ld.32x32b.x16 itself drains
+// 426 B / clk / SM (tools/ubench/ldtm_rate.cu), far from binding.  Every epilogue warp keeps the tcgen05.ld of its next unit
+// in flight while it requantises and stores the current one (two register buffers), across item boundaries.
 #include <cuda.h>
 
 #include "qasr_common.cuh"
@@ -40,8 +41,9 @@ constexpr int kProdWarps = 1;
 constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + kProdWarps, kAllocWarp = kMmaWarp + 1;
 constexpr int kThreads = 32 * (kEpiWarps + kProdWarps + 2);
 constexpr int kMaxBufs = 4;
-constexpr int kSlots = 8;                 // accumulator rounds in flight: 8 x 64 columns = the 512 TMEM columns
-constexpr int kRound = 4;                 // units per round: one per epilogue group
+constexpr int kSlots = 2;                 // accumulator rounds in flight: 2 x 256 columns = the 512 TMEM columns
+constexpr int kRound = 16;                // units per round = per work item (the host sizes items to <= 16 units): ONE
+                                          // full / empty handshake per item and warp instead of one per 4 units
 constexpr int kMaxKS = 8;
 constexpr uint32_t kBmatBytes = 512;      // one K step of the 16 x K weight matrix: 2 n-groups x 2 k-chunks x 128 B
 constexpr uint32_t kSmemBudget = 227 * 1024;
@@ -284,24 +286,38 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tape_kernel(const __grid_c
       int nvalid;     // frames of them below the utterance's length (<= 0: all zero); kNoStore: a row of the gap
       int ring;       // slot of the channel record
     };
-    // walk over the rounds of the CTA's items: group g takes position (g + rot) & 3 of every round; rot carries the deal
-    // over the item boundary so that the groups stay evenly loaded
+    // Walk over the CTA's items.  An item is ONE round: the MMA issuer commits all its units (<= 16, 16 TMEM columns each)
+    // at once; group g drains units pos, pos + 4, pos + 8, pos + 12 with pos = (g + rot) & 3, rot carrying the deal over the
+    // item boundary so that the groups stay evenly loaded.  Every warp waits once per item for the accumulators and hands
+    // the slot back once, after the last of its loads has landed.
     int it = i0, c = i0 / nbc, bc = i0 - c * nbc;
-    int u = 0, units = 0, rows_total = 0, rot = 0;
+    int unit = 0, units = 0, rows_total = 0, rot = 0;
     uint32_t slot = 0, sphase = 0;
-    auto open_item = [&]() {
-      rows_total = min(nb, a.B - bc * nb) * rpu;
-      units = (rows_total + 127) >> 7;
-      u = 0;
-    };
-    // waits for the next round's accumulators; starts the TMEM load of this group's unit and fills in its job
-    auto issue = [&](int (&acc)[16], Job& j) -> bool {
-      mbar_sleep(tfull_bar(slot), sphase);
-      tc_fence_after();
-      const int pos = (grp + rot) & 3;
-      const int unit = u + pos;
-      if (unit >= units) return false;
-      tmem_ld16(lane_addr + (uint32_t)(slot * (kRound * 16) + pos * 16), acc);
+    bool open = false;   // the current item's accumulators have been waited for
+    // after the previous load has landed: moves to this warp's next unit (retiring items on the way), starts its TMEM load
+    // and fills in its job; false when the CTA's items are exhausted
+    auto next = [&](int (&acc)[16], Job& j) -> bool {
+      for (;;) {
+        if (it >= i1) return false;
+        if (!open) {
+          rows_total = min(nb, a.B - bc * nb) * rpu;
+          units = (rows_total + 127) >> 7;
+          unit = (grp + rot) & 3;
+          mbar_sleep(tfull_bar(slot), sphase);
+          tc_fence_after();
+          open = true;
+        }
+        if (unit < units) break;
+        // this warp is through with the item: hand the slot back, step to the next item
+        tc_fence_before();
+        mbar_arrive_warp(tempty_bar(slot));
+        if (++slot == kSlots) { slot = 0; sphase ^= 1u; }
+        rot = (rot - units) & 3;
+        ++it;
+        if (++bc == nbc) { bc = 0; ++c; }
+        open = false;
+      }
+      tmem_ld16(lane_addr + (uint32_t)(slot * (kRound * 16) + unit * 16), acc);
       const int R = unit * 128 + lane_row;                        // tape row of this lane
       const int bl = __float2int_rz(((float)R + 0.5f) * a.inv_rpu);
       const int i = R - bl * rpu;
@@ -312,20 +328,8 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tape_kernel(const __grid_c
       j.ptr = out + ((size_t)b * a.C + c) * a.out_ld + 16 * i;
       j.nvalid = valid ? len - 16 * i : kNoStore;
       j.ring = (it - i0) & (kChanRing - 1);
+      unit += 4;
       return true;
-    };
-    // after the load has landed: hand the TMEM slot back and step the walk
-    auto retire = [&]() {
-      tc_fence_before();
-      mbar_arrive_warp(tempty_bar(slot));
-      if (++slot == kSlots) { slot = 0; sphase ^= 1u; }
-      u += kRound;
-      if (u >= units) {
-        rot = (rot - units) & 3;
-        ++it;
-        if (++bc == nbc) { bc = 0; ++c; }
-        if (it < i1) open_item();
-      }
     };
     // 16 accumulators -> 16 codes, length mask, one 16-byte store
     auto finish = [&](const int (&acc)[16], const Job& j) {
@@ -364,24 +368,19 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_tape_kernel(const __grid_c
       *reinterpret_cast<uint4*>(j.ptr) = make_uint4(w[0], w[1], w[2], w[3]);
     };
 
-    if (it < i1) {
+    // two register buffers: the TMEM load of the next unit is in flight while the current one is requantised and stored
+    {
       int accA[16], accB[16];
       Job jA, jB;
-      open_item();
-      bool hA = issue(accA, jA), hB = false;
-      for (;;) {
-        if (hA) tmem_ld_wait();
-        retire();
-        const bool moreB = it < i1;
-        if (moreB) hB = issue(accB, jB);
-        if (hA) finish(accA, jA);
-        if (!moreB) break;
-        if (hB) tmem_ld_wait();
-        retire();
-        const bool moreA = it < i1;
-        if (moreA) hA = issue(accA, jA);
-        if (hB) finish(accB, jB);
-        if (!moreA) break;
+      bool hA = next(accA, jA);
+      while (hA) {
+        tmem_ld_wait();
+        const bool hB = next(accB, jB);
+        finish(accA, jA);
+        if (!hB) break;
+        tmem_ld_wait();
+        hA = next(accA, jA);
+        finish(accB, jB);
       }
     }
   }
@@ -459,14 +458,19 @@ int qasr_dwconv_tape_launch(const void* x, int x_ld, const uint8_t* bmat, void* 
   a.rpu = a.P / 16;
   a.rows_valid = (T_out + 15) / 16;
   a.inv_rpu = 1.0f / (float)a.rpu;
-  // utterances per work item: tapes of <= ~24 KB (a few units each), and enough items to balance 148 CTAs
+  // utterances per work item: at most 16 units (one accumulator round of 256 TMEM columns), and enough items to balance
+  // 148 CTAs
   const int sms = qasr_sm_count();
-  int nb = 24 * 1024 / a.P;
-  if (nb < 1) nb = 1;
-  if (nb > B) nb = B;
+  const int nb_cap = (kRound * 128) / a.rpu;
+  if (nb_cap < 1) {
+    qasr_set_error("dwconv(tape): rows of %d frames exceed one accumulator round", T_in);
+    return QASR_ERR_UNSUPPORTED;
+  }
+  int nb = nb_cap < B ? nb_cap : B;
   while (nb > 4 && (long long)C * ((B + nb - 1) / nb) < 8LL * sms) nb = (nb + 1) / 2;
   nb = (B + (B + nb - 1) / nb - 1) / ((B + nb - 1) / nb);   // same number of chunks, evenly sized
   if (qasr_debug_get(15) > 0) nb = (int)qasr_debug_get(15) < B ? (int)qasr_debug_get(15) : B;   // bring-up knob 15: utterances per item
+  if (nb > nb_cap) nb = nb_cap;
   a.nb = nb;
   a.nbc = (B + nb - 1) / nb;
   a.items = C * a.nbc;
