@@ -14,7 +14,7 @@ import bench  # noqa: E402
 from qasr.params import synthetic_features  # noqa: E402
 
 dev = torch.device("cuda:0")
-wl = dict(bench.WORKLOAD)
+wl = dict(bench.WORKLOAD_CFG1 if "cfg1" in sys.argv else bench.WORKLOAD)
 brief = "brief" in sys.argv
 from qasr import _lib as L  # noqa: E402
 for arg in sys.argv[1:]:
@@ -26,6 +26,7 @@ for arg in sys.argv[1:]:
 model = bench.build_model(dev, wl)
 x, lens = synthetic_features(wl["batch"], wl["frames"], seed=1000)
 plan = model.plan_for(x.shape, dev)
+print("plan", plan.stats)
 plan.load_inputs(x.to(dev), lens.to(dev))
 for _ in range(3):
     plan.run()
