@@ -106,6 +106,26 @@ def f32_ok_channels(bound, m, e, lo, hi):
     return sane & (np.clip(exact, lo, hi) == np.clip(fl, lo, hi).astype(np.int64)).all(axis=1)
 
 
+def window_bound(m, e, lo, hi):
+    """Smallest Z such that the requantised value of every accumulator |z| >= Z lies outside the clamp window [lo, hi]
+    for EVERY channel: (Z * m) >> e >= max(|lo|, |hi|) + 2.  All epilogue recipes (the reference's float one, the integer
+    and the float fast paths) are non-decreasing in z, so recipes that agree on |z| <= Z and are saturated at +-Z agree
+    for every larger accumulator as well: the proofs only have to cover min(bound, Z).  That matters for 8-bit weights
+    and activations: the worst-case accumulator of a 512-channel pointwise conv (512 x 127 x 255 = 2^24) exceeds the 2^22
+    up to which the reference's float32 round trip (quant_modules.py:305-307, quant_utils.py:187) is the identity, while
+    its clamp window ends at |z| ~ 128 / r ~ 2^17."""
+    m = np.atleast_1d(m).astype(np.int64)
+    e = np.atleast_1d(e).astype(np.int64)
+    live = m > 0
+    if not live.any():
+        return 0
+    if ((e[live] < 1) | (e[live] > 62)).any():
+        return 2 ** 62
+    want = max(abs(int(lo)), abs(int(hi))) + 2
+    z = (want * (np.int64(1) << e[live]) + m[live] - 1) // m[live] + 2      # ceil(want * 2^e / m) + 2
+    return int(z.max())
+
+
 def stage2_fast_ok(bound, m, e):
     """Same proof for the scalar second requantisation (generic 64-bit shift: 1 <= e <= 62)."""
     mi, ei = int(np.atleast_1d(m)[0]), int(np.atleast_1d(e)[0])
@@ -405,10 +425,15 @@ class FusedPlan:
             m, e = dyadic_np(cp.s_out, info.scale)
             if relu:
                 flags |= L.F_RELU0
-            fast = fast_ok(cp.bound, m, e)
+            lo_eff = max(qmin, 0) if relu else qmin
+            # the proofs cover the accumulators up to the end of the clamp window; beyond it every recipe is saturated
+            # (window_bound).  The fast kernels stay monotone up to |z| < 2^29: int64 products, and the float path's
+            # 0x4B400000 + z stays a positive, finite bit pattern.
+            eff = cp.bound if cp.bound >= 2 ** 29 else min(cp.bound, window_bound(m, e, lo_eff, qmax))
+            fast = fast_ok(eff, m, e)
             kw = dict(qmin=qmin, qmax=qmax)
             if fast and os.environ.get("QASR_NO_F32") != "1":   # float epilogue where the host can prove it, channel by channel
-                okc = f32_ok_channels(cp.bound, m, e, max(qmin, 0) if relu else qmin, qmax)
+                okc = f32_ok_channels(eff, m, e, lo_eff, qmax)
                 self.stats["f32_channels"] += int(okc.sum())
                 self.stats["channels"] += int(okc.size)
                 if okc.all():

@@ -413,6 +413,111 @@ def test_gemm_dequant_f32_bigacc():
     assert np.array_equal(from_codes_tensor(outq, T, False), want_q)
 
 
+def _literal_requant(acc_plus_bias, s_out, m, e, lo, hi, relu):
+    """The reference's recipe on accumulators of any size: float32 round trip (quant_modules.py:305-307,
+    quant_utils.py:187), then the dyadic in float64 (quant_utils.py:195-196), then the clamp."""
+    a32 = acc_plus_bias.astype(np.float32)
+    y = (a32 * s_out.reshape(1, -1, 1)).astype(np.float32)
+    if relu:
+        y = np.maximum(y, np.float32(0))
+    z = np.round((y / s_out.reshape(1, -1, 1)).astype(np.float32)).astype(np.float64)
+    return np.clip(O.dyadic_mul(z, m.reshape(1, -1, 1), e.reshape(1, -1, 1)), lo, hi).astype(np.int64)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["literal", "fast", "f32"])
+@pytest.mark.parametrize("relu", [False, True], ids=["signed", "relu"])
+def test_fast_paths_beyond_the_clamp_window(path, relu, gemm_engine):
+    """8-bit weights x 8-bit activations over 512 channels reach |acc| ~ 2^24, beyond the 2^22 up to which the
+    reference's float32 round trip is the identity, while the clamp window ends near |z| ~ 130 / r ~ 2^16.  The plan
+    proves the fast epilogues on min(bound, plan.window_bound) and relies on every recipe being saturated beyond:
+    here half of the channels run far outside the window on all three epilogues, against the literal recipe."""
+    from qasr import plan as P
+    B, ci, co, T = 2, 512, 256, 170
+    r = rng(21)
+    q = r.integers(150, 256, (B, ci, T))
+    w = r.integers(-12, 13, (co, ci, 1))
+    big = np.arange(co) % 2 == 1
+    sign = np.where(np.arange(co) % 4 == 1, 1, -1)
+    w[big] = (r.integers(80, 128, (int(big.sum()), ci, 1)) * sign[big].reshape(-1, 1, 1))
+    bias = r.integers(-50000, 50000, co)
+    acc = O.conv1d_int(q, w, bias, 1, 0, 1, 1)                 # includes the bias
+    assert np.abs(acc).max() > 2 ** 23 and np.abs(acc[:, ~big]).max() < 2 ** 21
+    lo, hi = (0, 255) if relu else (-128, 127)
+    qmin = -256 if relu else -128
+    bound = int(np.abs(acc).max())
+    m, e = norm_me(*rand_dyadic(r, co, 1.5e-3, 6e-3))
+    for _ in range(200):   # dyadics the host can prove inside the window (what the plan would require)
+        bad = [i for i in range(co) if not (P.fast_ok(min(bound, P.window_bound(m[i:i + 1], e[i:i + 1], lo, hi)), m[i:i + 1], e[i:i + 1])
+                                            and P.f32_ok(min(bound, P.window_bound(m[i:i + 1], e[i:i + 1], lo, hi)), m[i:i + 1], e[i:i + 1], lo, hi))]
+        if not bad:
+            break
+        mm, ee = norm_me(*rand_dyadic(r, len(bad), 1.5e-3, 6e-3))
+        m[bad], e[bad] = mm, ee
+    assert not bad
+    assert P.window_bound(m, e, lo, hi) < 2 ** 18
+    s_out = r.uniform(1e-5, 1e-3, co).astype(np.float32)
+    want = _literal_requant(acc, s_out, m, e, lo, hi, relu)
+    assert (want[:, big] == hi).any() and (want[:, big] == lo).any()     # both ends saturate
+    x = to_codes_tensor(q, False)
+    wp = ops.pack_weights(torch.from_numpy(w.astype(np.int8)).to(DEV))
+    ch = ops.chan_table(s_out, bias, m, e, DEV)
+    flags = L.F_RELU0 if relu else 0
+    if path == "literal":
+        flags |= L.F_EXACT_F32 | L.F_EXACT_DYAD
+    elif path == "f32":
+        flags |= L.F_FAST_F32
+    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=flags, qmin=qmin, qmax=hi)
+    out = ops.alloc_codes(B, co, T, DEV)
+    ops.conv_gemm(ops.gemm_operand(x, T, wp, ci, 1, 1, 1, 0), None, out, B, co, T, ep)
+    torch.cuda.synchronize()
+    got = from_codes_tensor(out, T, signed=not relu)
+    assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["literal", "fast", "f32"])
+def test_dwconv_fast_paths_beyond_the_clamp_window(path, dw_engine):
+    """Same argument on the depthwise engines: integer biases push acc + bias to ~2^24 on half of the channels."""
+    from qasr import plan as P
+    B, Cn, T, k = 3, 64, 300, 33
+    r = rng(22)
+    q = r.integers(0, 256, (B, Cn, T))
+    w = r.integers(-20, 21, (Cn, 1, k))
+    big = np.arange(Cn) % 2 == 1
+    bias = r.integers(-40000, 40000, Cn)
+    bias[big] = r.integers(2 ** 23, 2 ** 24, int(big.sum())) * np.where(np.arange(Cn)[big] % 4 == 1, 1, -1)
+    acc = O.conv1d_int(q, w, bias, 1, k // 2, 1, Cn)
+    lo, hi = -128, 127
+    bound = int(np.abs(acc).max())
+    assert bound > 2 ** 23
+    m, e = norm_me(*rand_dyadic(r, Cn, 1.5e-3, 6e-3))
+    for _ in range(200):
+        bad = [i for i in range(Cn) if not (P.fast_ok(min(bound, P.window_bound(m[i:i + 1], e[i:i + 1], lo, hi)), m[i:i + 1], e[i:i + 1])
+                                            and P.f32_ok(min(bound, P.window_bound(m[i:i + 1], e[i:i + 1], lo, hi)), m[i:i + 1], e[i:i + 1], lo, hi))]
+        if not bad:
+            break
+        mm, ee = norm_me(*rand_dyadic(r, len(bad), 1.5e-3, 6e-3))
+        m[bad], e[bad] = mm, ee
+    assert not bad
+    s_out = r.uniform(1e-5, 1e-3, Cn).astype(np.float32)
+    want = _literal_requant(acc, s_out, m, e, lo, hi, False)
+    x = to_codes_tensor(q, False)
+    wd = ops.pack_dw_weights(torch.from_numpy(w[:, 0, :].astype(np.int8)).to(DEV).contiguous(), 1, 1, k // 2)
+    ch = ops.chan_table(s_out, bias, m, e, DEV)
+    flags = 0
+    if path == "literal":
+        flags |= L.F_EXACT_F32 | L.F_EXACT_DYAD
+    elif path == "f32":
+        flags |= L.F_FAST_F32
+    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=flags, qmin=lo, qmax=hi)
+    out = ops.alloc_codes(B, Cn, T, DEV)
+    ops.dwconv(x, T, wd, out, T, k, 1, 1, k // 2, ep)
+    torch.cuda.synchronize()
+    got = from_codes_tensor(out, T, signed=True)
+    assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
+
+
 # ------------------------------------------------------------------------------------------
 # K1 depthwise
 # ------------------------------------------------------------------------------------------
