@@ -103,6 +103,12 @@ typedef struct {
                                  quantisation: scales exist on the device only): the kernel is launched
                                  WITHOUT programmatic dependent launch, so it starts after its predecessor
                                  has completed and its pre-wait prologue may read the tables            */
+#define QASR_F_RANGE_CHECK 2048 /* integer fast path only: the host proved it for |acc + bias| < 2^22 (where the reference's
+                                  float32 round trip, quant_modules.py:305-307 / quant_utils.py:187, is the identity); the
+                                  kernel compares every accumulator with that limit and evaluates the literal recipe
+                                  (EXACT_F32 + EXACT_DYAD) for the elements beyond it.  For launches whose worst-case
+                                  bound exceeds 2^22 (8-bit weights x activations over >= 256 channels) while real
+                                  accumulators practically never do */
 #define QASR_F_FAST_F32   512 /* single-operand REQUANT only: the host proved that
                                  clamp(rint(f32(acc+bias) * f32(m*2^-e))), one float FMA
                                  with a single rounding, equals the dyadic result for every

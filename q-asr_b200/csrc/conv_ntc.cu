@@ -83,6 +83,7 @@ __device__ __forceinline__ ChanRegs load_chan_smem(const uint4* fast, const uint
 
 // EPI as in gemm_tc.cu: bit0 fast, bit1 dual, bit2 prev, bit3 stage2; 0 = literal path
 constexpr int kEpiFast = 1, kEpiDual = 2, kEpiPrev = 4, kEpiStage2 = 8;
+constexpr int kEpiRange = 64;   // QASR_F_RANGE_CHECK (see gemm_tc.cu)
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t p;
@@ -254,7 +255,7 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
                 c1 = load_chan_smem(tab + 2 * BN + col0 + j, tab + 3 * BN + col0 + j, need_exact);
               const int prev = (int)(int8_t)((pw[w4] >> (8 * i)) & 0xff);
               if (EPI & kEpiFast)
-                q[i] = epilogue_fast<(EPI & kEpiDual) != 0, (EPI & kEpiPrev) != 0, (EPI & kEpiStage2) != 0>(
+                q[i] = epilogue_fast<(EPI & kEpiDual) != 0, (EPI & kEpiPrev) != 0, (EPI & kEpiStage2) != 0, (EPI & kEpiRange) != 0>(
                     g.ep, kc, acc0[j], c0, (EPI & kEpiDual) ? acc1[j] : 0, c1, prev);
               else
                 q[i] = epilogue_exact(g.ep, kc, acc0[j], c0, g.nseg > 1, g.nseg > 1 ? acc1[j] : 0, c1, prev);
@@ -432,10 +433,11 @@ extern "C" int qasr_conv1d_ntc_i8(const qasr_gemm_operand* op0, const qasr_gemm_
   int variant = 0;
   if (fast)
     variant = kEpiFast | (op1 ? kEpiDual : 0) | (epi->prev ? kEpiPrev : 0) | ((epi->flags & QASR_F_STAGE2) ? kEpiStage2 : 0);
+  if (fast && (epi->flags & QASR_F_RANGE_CHECK)) variant |= kEpiRange;
   int grid = qasr_sm_count();
   if (grid > g.total_tiles) grid = g.total_tiles;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set[16][64] = {};
+  static bool attr_set[128][64] = {};
   int dev = 0;
   QASR_CHECK_CUDA(cudaGetDevice(&dev));
   const bool need_attr = dev >= 0 && dev < 64 && !attr_set[variant][dev];
@@ -456,6 +458,14 @@ extern "C" int qasr_conv1d_ntc_i8(const qasr_gemm_operand* op0, const qasr_gemm_
     QASR_NTC_CASE(11)
     QASR_NTC_CASE(13)
     QASR_NTC_CASE(15)
+    QASR_NTC_CASE(65)
+    QASR_NTC_CASE(67)
+    QASR_NTC_CASE(69)
+    QASR_NTC_CASE(71)
+    QASR_NTC_CASE(73)
+    QASR_NTC_CASE(75)
+    QASR_NTC_CASE(77)
+    QASR_NTC_CASE(79)
     default:
       qasr_set_error("conv1d_ntc: internal: no kernel variant %d", variant);
       return QASR_ERR_INVALID;

@@ -89,6 +89,8 @@ constexpr int kEpiFast = 1, kEpiDual = 2, kEpiPrev = 4, kEpiStage2 = 8, kEpiF32 
 // device-written tables (QASR_F_DEVICE_TABLES, dynamic quantisation): the integer fast path runs where qasr_dyn_finalize
 // proved it (per channel), the literal recipe elsewhere, decided per warp (its 32 rows never change)
 constexpr int kEpiDyn = 32;
+// QASR_F_RANGE_CHECK: integer fast path with the per-element |acc + bias| < 2^22 test (literal recipe beyond)
+constexpr int kEpiRange = 64;
 
 constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kAllocWarp = kEpiWarps + 2;
 
@@ -124,7 +126,7 @@ __device__ __forceinline__ void finish32(const GemmArgs& g, const EpiConsts& kc,
             q[i] = (int)epilogue_f32_bits(kc, a0[j], c0);
           } else if (EPI & kEpiFast) {
             const int prev = (EPI & kEpiPrev) ? (int)(int8_t)(pw[w4] >> (8 * i)) : 0;
-            q[i] = epilogue_fast<(EPI & kEpiDual) != 0, (EPI & kEpiPrev) != 0, (EPI & kEpiStage2) != 0>(
+            q[i] = epilogue_fast<(EPI & kEpiDual) != 0, (EPI & kEpiPrev) != 0, (EPI & kEpiStage2) != 0, (EPI & kEpiRange) != 0>(
                 g.ep, kc, a0[j], c0, (EPI & kEpiDual) ? a1[j] : 0, c1, prev);
           } else {
             const int prev = (int)(int8_t)((pw[w4] >> (8 * i)) & 0xff);
@@ -969,6 +971,7 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   int variant = 0;
   if (fast)
     variant = kEpiFast | (op1 ? kEpiDual : 0) | (epi->prev ? kEpiPrev : 0) | ((epi->flags & QASR_F_STAGE2) ? kEpiStage2 : 0);
+  if (fast && (epi->flags & QASR_F_RANGE_CHECK)) variant |= kEpiRange;
   if (fast && (epi->flags & QASR_F_FAST_F32)) variant = kEpiFast | kEpiF32;
   // dynamic quantisation: the tables come from the device, the literal flags stay set for the channels whose fast path
   // qasr_dyn_finalize could not prove; everything else runs the integer fast path
@@ -1018,7 +1021,7 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
     g.n_step = pairs_per_group;
     const int pair_grid = 2 * pairs_per_group * g.m_groups;
     cudaStream_t pst = (cudaStream_t)stream;
-    static bool pair_attr_set[64][64] = {};
+    static bool pair_attr_set[128][64] = {};
     int pdev = 0;
     QASR_CHECK_CUDA(cudaGetDevice(&pdev));
     const bool pneed = pdev >= 0 && pdev < 64 && !pair_attr_set[variant][pdev];
@@ -1043,6 +1046,14 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
       QASR_PAIR_CASE(17)
       QASR_PAIR_CASE(33)
       QASR_PAIR_CASE(35)
+      QASR_PAIR_CASE(65)
+      QASR_PAIR_CASE(67)
+      QASR_PAIR_CASE(69)
+      QASR_PAIR_CASE(71)
+      QASR_PAIR_CASE(73)
+      QASR_PAIR_CASE(75)
+      QASR_PAIR_CASE(77)
+      QASR_PAIR_CASE(79)
       default:
         qasr_set_error("conv1d_gemm: internal: no pair kernel variant %d", variant);
         return QASR_ERR_INVALID;
@@ -1057,7 +1068,7 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   g.n_step = per_group;
   const int grid = per_group * g.m_groups;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set[64][64] = {};
+  static bool attr_set[128][64] = {};
   int dev = 0;
   QASR_CHECK_CUDA(cudaGetDevice(&dev));
   const bool need_attr = dev >= 0 && dev < 64 && !attr_set[variant][dev];
@@ -1082,6 +1093,14 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
     QASR_GEMM_CASE(17)
     QASR_GEMM_CASE(33)
     QASR_GEMM_CASE(35)
+    QASR_GEMM_CASE(65)
+    QASR_GEMM_CASE(67)
+    QASR_GEMM_CASE(69)
+    QASR_GEMM_CASE(71)
+    QASR_GEMM_CASE(73)
+    QASR_GEMM_CASE(75)
+    QASR_GEMM_CASE(77)
+    QASR_GEMM_CASE(79)
     default:
       qasr_set_error("conv1d_gemm: internal: no kernel variant %d", variant);
       return QASR_ERR_INVALID;

@@ -248,11 +248,20 @@ __device__ __forceinline__ EpiConsts make_epi_consts(const EpiArgs& ep, bool has
 
 // Full per-element REQUANT pipeline -> final 8-bit code (as int), all-integer fast path.  The
 // operand / stage structure is a compile-time property of the kernel instantiation.
-template <bool DUAL, bool PREV, bool STAGE2>
+template <bool DUAL, bool PREV, bool STAGE2, bool RC = false>
 __device__ __forceinline__ int epilogue_fast(const EpiArgs& ep, const EpiConsts& k, int acc0, const ChanRegs& c0,
                                              int acc1, const ChanRegs& c1, int prev) {
   int o = contrib_fast(acc0, c0);
   if (DUAL) o += contrib_fast(acc1, c1);
+  if (RC) {   // QASR_F_RANGE_CHECK: a separate instantiation (its doubles cost the plain fast path registers)
+    // proved for |acc + bias| < 2^22 only: the (practically never seen) elements beyond go through the literal recipe
+    const bool big0 = (unsigned)(acc0 + c0.bias + (1 << 22)) >= (1u << 23);
+    const bool big1 = DUAL && (unsigned)(acc1 + c1.bias + (1 << 22)) >= (1u << 23);
+    if (big0 || big1) {
+      o = (int)contrib_exact(acc0, c0, (ep.flags & QASR_F_RELU0) != 0, true, false);
+      if (DUAL) o += (int)contrib_exact(acc1, c1, false, true, false);
+    }
+  }
   if (PREV) o += prev;
   int q = min(max(o, k.lo1), k.hi1);
   if (STAGE2) {

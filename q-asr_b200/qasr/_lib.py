@@ -17,6 +17,7 @@ F_RELU0, F_RELU1, F_STAGE2, F_MASK = 1, 2, 4, 8
 F_EXACT_F32, F_EXACT_DYAD, F_B_SIGNED, F_B1_SIGNED, F_BIAS64 = 16, 32, 64, 128, 256
 F_FAST_F32 = 512
 F_DEVICE_TABLES = 1024
+F_RANGE_CHECK = 2048
 DYN_MAX_CAND = 4
 
 

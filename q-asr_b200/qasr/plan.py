@@ -75,6 +75,19 @@ def fast_ok(bound, m, e):
     return True
 
 
+F32_IDENTITY = 2 ** 22 - 1   # largest |acc + bias| for which the reference's float32 round trip is proved to be the identity
+
+
+def fast_ok_checked(bound, m, e):
+    """(ok, range_check): the integer fast path for |z| <= bound, if need be with the kernel's per-element range check
+    (QASR_F_RANGE_CHECK): proved up to 2^22 - 1, elements beyond take the literal recipe inside the same launch."""
+    if fast_ok(bound, m, e):
+        return True, False
+    if bound < 2 ** 31 - 1 and fast_ok(min(bound, F32_IDENTITY), m, e):
+        return True, True
+    return False, False
+
+
 def f32_ok(bound, m, e, lo, hi):
     """f32_ok_channels() for every channel at once (QASR_F_FAST_F32)."""
     return bool(f32_ok_channels(bound, m, e, lo, hi).all())
@@ -431,8 +444,13 @@ class FusedPlan:
             # 0x4B400000 + z stays a positive, finite bit pattern.
             eff = cp.bound if cp.bound >= 2 ** 29 else min(cp.bound, window_bound(m, e, lo_eff, qmax))
             fast = fast_ok(eff, m, e)
+            if not fast:
+                fast, rc = fast_ok_checked(cp.bound, m, e)
+                if rc:
+                    flags |= L.F_RANGE_CHECK
+                    eff = 0          # no float path on top of a range-checked launch
             kw = dict(qmin=qmin, qmax=qmax)
-            if fast and os.environ.get("QASR_NO_F32") != "1":   # float epilogue where the host can prove it, channel by channel
+            if fast and not (flags & L.F_RANGE_CHECK) and os.environ.get("QASR_NO_F32") != "1":   # float epilogue where the host can prove it, channel by channel
                 okc = f32_ok_channels(eff, m, e, lo_eff, qmax)
                 self.stats["f32_channels"] += int(okc.sum())
                 self.stats["channels"] += int(okc.size)
@@ -480,12 +498,18 @@ class FusedPlan:
         if isinstance(main, ConvVal):
             cpm = ConvParams(main.conv, main.src.scale, main.src.qabs)
             mm, em = dyadic_np(cpm.s_out, ra.scale)
-            fast = fast_extra and fast_ok(cpm.bound, mm, em) and fast_ok(cpb.bound, mb, eb)
+            (okm, rcm), (okb, rcb) = fast_ok_checked(cpm.bound, mm, em), fast_ok_checked(cpb.bound, mb, eb)
+            fast = fast_extra and okm and okb
+            if fast and (rcm or rcb):
+                flags |= L.F_RANGE_CHECK
             self._emit_conv([(main, cpm, mm, em), (branch, cpb, mb, eb)], out, flags, fast, kw, lens, "res_act")
         else:  # chain: previous res_act result (same scale, ratio exactly 1) + this branch
             assert isinstance(main, ResActVal) and main.act is val.act
             prev = self._plain_resact(main)
-            fast = fast_extra and fast_ok(cpb.bound, mb, eb)
+            okb, rcb = fast_ok_checked(cpb.bound, mb, eb)
+            fast = fast_extra and okb
+            if fast and rcb:
+                flags |= L.F_RANGE_CHECK
             self._emit_conv([(branch, cpb, mb, eb)], out, flags, fast, dict(prev=prev.tensor, **kw), lens,
                             "res_act_chain")
 
@@ -513,6 +537,8 @@ class FusedPlan:
             if any(cp.bias64 for (_, cp, _, _) in operands):
                 flags |= L.F_BIAS64
         self.stats["fast" if fast else "exact"] += 1
+        if flags & L.F_RANGE_CHECK:
+            self.stats["range_checked"] = self.stats.get("range_checked", 0) + 1
         if flags & L.F_FAST_F32:
             self.stats["f32"] += 1
         kw = dict(epi_kw)

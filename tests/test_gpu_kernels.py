@@ -476,6 +476,61 @@ def test_fast_paths_beyond_the_clamp_window(path, relu, gemm_engine):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("path", ["literal", "range_check"])
+def test_dual_residual_beyond_the_float32_identity(path, gemm_engine):
+    """res_act of two 512-channel 8-bit convs (jasper.py:681): the contributions are summed BEFORE the clamp, so no clamp
+    window bounds the accumulators that matter, and their worst case (2^24) exceeds the 2^22 of the float32 round trip.
+    QASR_F_RANGE_CHECK keeps the launch on the integer fast path (proved for |acc + bias| < 2^22) and sends the elements
+    beyond through the literal recipe: half of the channels here are beyond on one or both operands."""
+    from qasr import plan as P
+    B, ci, co, T = 2, 512, 256, 150
+    r = rng(31)
+    q0, q1 = r.integers(120, 256, (B, ci, T)), r.integers(-128, 128, (B, ci, T))
+    w0, w1 = r.integers(-10, 11, (co, ci, 1)), r.integers(-10, 11, (co, ci, 1))
+    big0, big1 = np.arange(co) % 2 == 1, np.arange(co) % 3 == 1
+    w0[big0] = r.integers(90, 128, (int(big0.sum()), ci, 1)) * np.where(np.arange(co)[big0] % 4 == 1, 1, -1).reshape(-1, 1, 1)
+    w1[big1] = r.integers(-127, 128, (int(big1.sum()), ci, 1))
+    q1[:, :, ::3] = np.where(w1[big1][0, :, 0] > 0, 127, -128).reshape(1, -1, 1)   # signs aligned with one channel: |acc1| > 2^22 there
+    b0, b1 = r.integers(-50000, 50000, co), r.integers(-50000, 50000, co)
+    acc0, acc1 = O.conv1d_int(q0, w0, b0, 1, 0, 1, 1), O.conv1d_int(q1, w1, b1, 1, 0, 1, 1)
+    assert np.abs(acc0).max() > 2 ** 23 and np.abs(acc1).max() > 2 ** 22
+    m0, e0 = norm_me(*rand_dyadic(r, co, 2e-6, 2e-5))
+    m1, e1 = norm_me(*rand_dyadic(r, co, 2e-6, 2e-5))
+    for mm, ee in ((m0, e0), (m1, e1)):
+        for _ in range(200):
+            bad = [i for i in range(co) if not P.fast_ok(P.F32_IDENTITY, mm[i:i + 1], ee[i:i + 1])]
+            if not bad:
+                break
+            a, b = norm_me(*rand_dyadic(r, len(bad), 2e-6, 2e-5))
+            mm[bad], ee[bad] = a, b
+        assert not bad
+    s0, s1 = r.uniform(1e-5, 1e-3, co).astype(np.float32), r.uniform(1e-5, 1e-3, co).astype(np.float32)
+
+    def contribution(acc, s, m, e):
+        y = (acc.astype(np.float32) * s.reshape(1, -1, 1)).astype(np.float32)
+        z = np.round((y / s.reshape(1, -1, 1)).astype(np.float32)).astype(np.float64)
+        return O.dyadic_mul(z, m.reshape(1, -1, 1), e.reshape(1, -1, 1))
+    m2, e2 = norm_me(*O.batch_frexp(np.array([1.7])))
+    o = np.clip(contribution(acc0, s0, m0, e0) + contribution(acc1, s1, m1, e1), -128, 127)
+    o = np.maximum(o, 0)
+    want = np.clip(O.dyadic_mul(o, m2[0], e2[0]), -256, 255).astype(np.int64)
+    assert len(np.unique(want)) > 50
+    x0, x1 = to_codes_tensor(q0, False), to_codes_tensor(q1, True)
+    wp0 = ops.pack_weights(torch.from_numpy(w0.astype(np.int8)).to(DEV))
+    wp1 = ops.pack_weights(torch.from_numpy(w1.astype(np.int8)).to(DEV))
+    ch0, ch1 = ops.chan_table(s0, b0, m0, e0, DEV), ops.chan_table(s1, b1, m1, e1, DEV)
+    flags = L.F_RELU1 | L.F_STAGE2 | L.F_B1_SIGNED
+    flags |= (L.F_EXACT_F32 | L.F_EXACT_DYAD) if path == "literal" else L.F_RANGE_CHECK
+    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch0, flags=flags, ch1=ch1, qmin=-128, qmax=127, m2=m2[0], e2=e2[0],
+                           qmin2=-256, qmax2=255)
+    out = ops.alloc_codes(B, co, T, DEV)
+    ops.conv_gemm(ops.gemm_operand(x0, T, wp0, ci, 1, 1, 1, 0), ops.gemm_operand(x1, T, wp1, ci, 1, 1, 1, 0), out, B, co, T, ep)
+    torch.cuda.synchronize()
+    got = from_codes_tensor(out, T, signed=False)
+    assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("path", ["literal", "fast", "f32"])
 def test_dwconv_fast_paths_beyond_the_clamp_window(path, dw_engine):
     """Same argument on the depthwise engines: integer biases push acc + bias to ~2^24 on half of the channels."""
