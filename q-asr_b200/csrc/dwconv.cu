@@ -420,7 +420,9 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
   if (table_bytes == 0) use_tc = true;   // only the tensor-core kernel covers this tap window
   // 6 K steps (k = 87 dilated): the lanes' 8-byte fragment loads are 12 words apart and collide on banks
   // (30.9 us against 27.5 us on tcgen05, 512 channels, batch 64 x 800 frames)
-  if (knob < 0 && tc_ok && dw_ksteps(k, stride, dilation, pad) >= 6) use_tc = true;
+  // ... for layers of at least ~14 M outputs: the tcgen05 kernel pays 11 us per launch before its lower marginal cost shows
+  // (BASELINE config 1, batch 8 x 250 frames: 18 us against 4 us on the IMMA engine)
+  if (knob < 0 && tc_ok && dw_ksteps(k, stride, dilation, pad) >= 6 && (long long)B * C * T_out >= 14000000LL) use_tc = true;
   // tape engine (tcgen05 on the rows themselves): requantising launches with stride 1.  Bring-up knob 8 = 2 forces it,
   // 0 / 1 force the other engines.
   const bool tape_ok = epi->mode == QASR_EPI_REQUANT_I8 && qasr_dwconv_tape_supported(k, stride, dilation, pad) &&

@@ -14,7 +14,7 @@ import bench  # noqa: E402
 from qasr.params import synthetic_features  # noqa: E402
 
 dev = torch.device("cuda:0")
-wl = dict(bench.WORKLOAD_CFG1 if "cfg1" in sys.argv else bench.WORKLOAD)
+wl = dict(bench.WORKLOAD_CFG1 if "cfg1" in sys.argv else (bench.WORKLOAD_JASPER if "jasper" in sys.argv else bench.WORKLOAD))
 brief = "brief" in sys.argv
 from qasr import _lib as L  # noqa: E402
 for arg in sys.argv[1:]:
