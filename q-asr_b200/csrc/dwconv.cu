@@ -115,6 +115,10 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
   int buf = 0, nb = kBufs - 1;
   uint32_t par = 0;
   long long st_lo = 0x7fffffffffffffffLL, st_hi = -0x7fffffffffffffffLL - 1;   // QASR_EPI_STATS: this lane's extremes
+  // ... kept in 32 bits while acc + bias cannot leave int32 (|acc| < 2^22 for every depthwise window this kernel takes):
+  // two VIMNMX per counted output instead of 64-bit compares and selects
+  const bool st_narrow = c0.bias > -(1 << 30) && c0.bias < (1 << 30);
+  int st_lo32 = 2147483647, st_hi32 = -2147483647 - 1;
   for (int r = 0; r < nrows; ++r, out_row += out_row_step, x_next += xstep) {
     // keep kBufs-1 rows in flight: the buffer being refilled was consumed in iteration r-1
     if (lane == 0 && r + kBufs - 1 < nrows) {
@@ -167,12 +171,22 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
       } else if (a.ep.mode == QASR_EPI_STATS) {
         // statistics pass of dynamic quantisation: extremes of acc + bias over the counted frames of this channel
         const int offs[4] = {o0, o1, o2, o3};
+        if (st_narrow) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (t0 + offs[i] < len) {
-            const long long z = qasr_acc_bias64(acc[i], c0.bias);
-            st_lo = z < st_lo ? z : st_lo;
-            st_hi = z > st_hi ? z : st_hi;
+          for (int i = 0; i < 4; ++i) {
+            const bool counted = t0 + offs[i] < len;
+            const int z = acc[i] + c0.bias;
+            st_lo32 = min(st_lo32, counted ? z : 2147483647);
+            st_hi32 = max(st_hi32, counted ? z : -2147483647 - 1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (t0 + offs[i] < len) {
+              const long long z = qasr_acc_bias64(acc[i], c0.bias);
+              st_lo = z < st_lo ? z : st_lo;
+              st_hi = z > st_hi ? z : st_hi;
+            }
           }
         }
       } else if (a.ep.mode == QASR_EPI_DEQUANT_F32) {
@@ -263,6 +277,7 @@ __global__ void __launch_bounds__(kThreads, QASR_DW_MIN_BLOCKS) dwconv_mma_kerne
   }
   if (PROF && lane == 0) qasr_stamp_end(a.stamp);
   if (EK == 2 && a.ep.mode == QASR_EPI_STATS) {
+    if (st_narrow && st_hi32 >= st_lo32) { st_lo = st_lo32; st_hi = st_hi32; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const long long l2 = __shfl_xor_sync(0xffffffffu, st_lo, o), h2 = __shfl_xor_sync(0xffffffffu, st_hi, o);
@@ -453,7 +468,9 @@ extern "C" int qasr_dwconv1d_i8(const void* x, int32_t x_ld, const int8_t* w, vo
       qasr_dwconv_rt_supported(T_in, k, dilation, pad)) {
     const bool fast = !(epi->flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64 | QASR_F_STAGE2)) &&
                       epi->prev == nullptr;
-    const int ek = (epi->flags & QASR_F_FAST_F32) ? 3 : (fast ? 0 : 1);
+    int ek = (epi->flags & QASR_F_FAST_F32) ? 3 : (fast ? 0 : 1);
+    // device-written tables (dynamic quantisation): per-channel choice between the integer fast path and the literal recipe
+    if (ek == 1 && (epi->flags & QASR_F_DEVICE_TABLES) && !(epi->flags & QASR_F_STAGE2) && epi->prev == nullptr) ek = 4;
     if (ek != 1)
       return qasr_dwconv_rt_launch(x, x_ld, w, out, out_ld, B, C, T_in, T_out, k, dilation, pad, ek, epi, stream);
   }

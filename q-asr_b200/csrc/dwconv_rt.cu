@@ -23,7 +23,9 @@ namespace {
 
 constexpr int kMaxR = 8;   // rows per tape (mbarriers per warp)
 
-// EK: 0 = integer fast path, float fast path for the channels of the f32_mult table; 3 = float fast path everywhere
+// EK: 0 = integer fast path, float fast path for the channels of the f32_mult table; 3 = float fast path everywhere;
+//     4 = device-written tables (QASR_F_DEVICE_TABLES, dynamic quantisation): integer fast path for the channels
+//     qasr_dyn_finalize proved, literal recipe for the others
 template <int KS, bool XS, int EK, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) dwconv_rt_kernel(const DwArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -82,11 +84,13 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_rt_kernel(const DwArgs a) 
   uint8_t* out_row = reinterpret_cast<uint8_t*>(a.out) + ((size_t)b_begin * a.C + c) * a.out_ld;
 
   auto walk = [&](auto mode_tag) {
-    constexpr bool F32 = decltype(mode_tag)::value;
+    constexpr int MODE = decltype(mode_tag)::value;   // 0 = integer fast path, 1 = float fast path, 2 = literal recipe
+    constexpr bool F32 = MODE == 1;
     // float path: the MMA's initial accumulator is 0x4B400000 + bias (see dwconv.cu)
     const int acc_init = F32 ? kF32MagicBits + c0.bias : 0;
     auto code = [&](int v) -> uint8_t {
       if (F32) return (uint8_t)epilogue_f32_bits_biased(kc, v, c0);
+      if (MODE == 2) return (uint8_t)epilogue_exact(a.ep, kc, v, c0, false, 0, c0, 0);
       return (uint8_t)epilogue_fast<false, false, false>(a.ep, kc, v, c0, 0, c0, 0);
     };
     auto mma_one = [&](const uint32_t* tw0, int (&acc)[4]) {
@@ -178,8 +182,14 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv_rt_kernel(const DwArgs a) 
       len_r = len_n;
     }
   };
-  if (f32_path) walk(std::true_type{});
-  else walk(std::false_type{});
+  if (EK == 4) {
+    if (c0.literal) walk(std::integral_constant<int, 2>{});
+    else walk(std::integral_constant<int, 0>{});
+  } else if (f32_path) {
+    walk(std::integral_constant<int, 1>{});
+  } else {
+    walk(std::integral_constant<int, 0>{});
+  }
   if (PROF && lane == 0) qasr_stamp_end(a.stamp);   // spread over the kernel's tail: no burst on the address
 }
 
@@ -201,9 +211,9 @@ int launch_rt(const DwArgs& a, int ek, cudaStream_t stream) {
     QASR_CHECK_CUDA(qasr_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, a));                 \
   } while (0)
   if (xs) {
-    if (ek == 0) QASR_RT_GO(true, 0); else QASR_RT_GO(true, 3);
+    if (ek == 0) QASR_RT_GO(true, 0); else if (ek == 3) QASR_RT_GO(true, 3); else QASR_RT_GO(true, 4);
   } else {
-    if (ek == 0) QASR_RT_GO(false, 0); else QASR_RT_GO(false, 3);
+    if (ek == 0) QASR_RT_GO(false, 0); else if (ek == 3) QASR_RT_GO(false, 3); else QASR_RT_GO(false, 4);
   }
 #undef QASR_RT_GO
   return qasr_check_launch("dwconv_rt_kernel");
