@@ -45,6 +45,7 @@ struct Seg {
 struct Args {
   void* out;
   int out_ld, out_nct, B, C_out, T_out;
+  int ct_major;      // tile walk: 1 = contiguous range per CTA with the channel tile outermost (few slabs per tile), 0 = strided
   int nseg, t_tiles, c_tiles, total_tiles;
   Seg seg[2];
   unsigned long long* stamp;   // in-graph timing slot (qasr_profile_begin) or nullptr
@@ -131,15 +132,26 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   if (threadIdx.x == 0) qasr_stamp_begin(g.stamp);
+  // tile walk of this CTA: a CONTIGUOUS range with the channel tile outermost, so the epilogue refills its per-channel
+  // table (a global round trip between two barriers of all epilogue warps) once instead of per tile and consecutive tiles
+  // reuse the channel tile's weights.  Same-box A/B on Jasper10x5dr (B32 x T1600; the box-to-box spread of this
+  // power-limited workload is larger than the effect): 8.38 ms against 8.64-8.77 ms with the strided walk (bring-up
+  // knob 20 = 0), the 1x1 dense-residual chain launches gaining most (40.7 -> 34.5 us on 256 -> 768 channels).
+  const int tile0 = g.ct_major ? (int)((long long)blockIdx.x * g.total_tiles / gridDim.x) : (int)blockIdx.x;
+  const int tile1 = g.ct_major ? (int)((long long)(blockIdx.x + 1) * g.total_tiles / gridDim.x) : g.total_tiles;
+  const int tile_step = g.ct_major ? 1 : (int)gridDim.x;
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks with uniform values, one elected lane issues) =====================
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-      const int ct = tile % g.c_tiles;
-      const int rest = tile / g.c_tiles;
+    // A CTA walks a CONTIGUOUS range of tiles, channel tile outermost: its ~9 tiles share one channel tile, so the
+    // epilogue refills its per-channel table (a global round trip between two CTA-wide barriers) once, not per tile
+    const int per_ct = g.t_tiles * g.B;
+    for (int tile = tile0; tile < tile1; tile += tile_step) {
+      const int ct = g.ct_major ? tile / per_ct : tile % g.c_tiles;
+      const int rest = g.ct_major ? tile - ct * per_ct : tile / g.c_tiles;
       const int tt = rest % g.t_tiles, b = rest / g.t_tiles;
       for (int sg = 0; sg < g.nseg; ++sg) {
         const Seg& s = g.seg[sg];
@@ -175,7 +187,7 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
     uint32_t phase = 0, stage_lo = stage_lo0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < tile1; tile += tile_step) {
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       tc_fence_after();
 #pragma unroll
@@ -210,17 +222,22 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
     const bool need_exact = !(EPI & kEpiFast);
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-      const int ct = tile % g.c_tiles;
-      const int rest = tile / g.c_tiles;
+    const int per_ct = g.t_tiles * g.B;
+    int cur_ct = -1;
+    for (int tile = tile0; tile < tile1; tile += tile_step) {
+      const int ct = g.ct_major ? tile / per_ct : tile % g.c_tiles;
+      const int rest = g.ct_major ? tile - ct * per_ct : tile / g.c_tiles;
       const int tt = rest % g.t_tiles, b = rest / g.t_tiles;
-      // per-channel parameter table of this channel tile
-      asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");  // previous tile's readers are done
-      if (etid < BN) {
-        store_chan(tab + etid, tab + BN + etid, g.ep.ch0, ct * BN + etid, g.C_out);
-        if (g.nseg > 1) store_chan(tab + 2 * BN + etid, tab + 3 * BN + etid, g.ep.ch1, ct * BN + etid, g.C_out);
+      if (ct != cur_ct) {   // CTA-uniform
+        // per-channel parameter table of this channel tile
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");  // previous tile's readers are done
+        if (etid < BN) {
+          store_chan(tab + etid, tab + BN + etid, g.ep.ch0, ct * BN + etid, g.C_out);
+          if (g.nseg > 1) store_chan(tab + 2 * BN + etid, tab + 3 * BN + etid, g.ep.ch1, ct * BN + etid, g.C_out);
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");
+        cur_ct = ct;
       }
-      asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");
       const int t = tt * BM + quarter * 32 + lane;
       const bool t_ok = t < g.T_out;
       const int len = (g.ep.flags & QASR_F_MASK) ? min(g.ep.out_lens[b], g.T_out) : g.T_out;
@@ -426,6 +443,13 @@ extern "C" int qasr_conv1d_ntc_i8(const qasr_gemm_operand* op0, const qasr_gemm_
   g.t_tiles = (T_out + BM - 1) / BM;
   g.c_tiles = (C_out + BN - 1) / BN;
   g.total_tiles = g.t_tiles * g.c_tiles * B;
+  {
+    int slabs = 0;
+    for (int sg = 0; sg < g.nseg; ++sg) slabs += g.seg[sg].taps * g.seg[sg].cblocks;
+    (void)slabs;
+    g.ct_major = 1;
+    if (qasr_debug_get(20) >= 0) g.ct_major = qasr_debug_get(20) > 0 ? 1 : 0;   // bring-up knob 20: force the tile walk
+  }
   g.ep = make_epi_args(epi);
   g.stamp = qasr_next_stamp();
   const bool fast = !(epi->flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64)) &&
