@@ -245,23 +245,44 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
 
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      // single-operand fast launches drain their 32 columns in one go: the TMEM buffer goes back to the MMA warp before
+      // the arithmetic and every lane writes one full 32-byte sector (Jasper's 1x1 dense-residual chain is paced by this
+      // epilogue); two-operand and literal launches keep 16-column halves (registers)
+      constexpr int W = ((EPI & kEpiFast) && !(EPI & kEpiDual)) ? 32 : 16;
 #pragma unroll 1
-      for (int ch = 0; ch < 2; ++ch) {
-        const int col0 = cgroup * 32 + ch * 16;
+      for (int ch = 0; ch < 32 / W; ++ch) {
+        const int col0 = cgroup * 32 + ch * W;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * 2 * BN + col0);
-        int acc0[16], acc1[16];
-        tmem_ld16(taddr, acc0);
-        if (g.nseg > 1) tmem_ld16(taddr + BN, acc1);
+        int acc0[W], acc1[16];
+        if constexpr (W == 32) {
+          tmem_ld32(taddr, acc0);
+        } else {
+          tmem_ld16(taddr, acc0);
+          if (g.nseg > 1) tmem_ld16(taddr + BN, acc1);
+        }
         tmem_ld_wait();
+        if (W == 32) {
+          tc_fence_before();
+          mbar_arrive_warp(tempty_bar(as));
+        }
         const int c_first = ct * BN + col0;
         if (g.ep.mode == QASR_EPI_REQUANT_I8) {
-          uint4 pv = make_uint4(0, 0, 0, 0);
-          if ((EPI == 0 || (EPI & kEpiPrev)) && g.ep.prev != nullptr && t_ok && c_first < g.C_out)
-            pv = *reinterpret_cast<const uint4*>(g.ep.prev + trow * g.ep.prev_ld + c_first);
-          const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
-          uint32_t packed[4];
+          uint32_t pw[W / 4];
 #pragma unroll
-          for (int w4 = 0; w4 < 4; ++w4) {
+          for (int i = 0; i < W / 4; ++i) pw[i] = 0u;
+          if ((EPI == 0 || (EPI & kEpiPrev)) && g.ep.prev != nullptr && t_ok && c_first < g.C_out) {
+            const uint4* pp = reinterpret_cast<const uint4*>(g.ep.prev + trow * g.ep.prev_ld + c_first);
+#pragma unroll
+            for (int i = 0; i < W / 16; ++i) {
+              if (c_first + 16 * i < g.C_out) {
+                const uint4 pv = pp[i];
+                pw[4 * i] = pv.x; pw[4 * i + 1] = pv.y; pw[4 * i + 2] = pv.z; pw[4 * i + 3] = pv.w;
+              }
+            }
+          }
+          uint32_t packed[W / 4];
+#pragma unroll
+          for (int w4 = 0; w4 < W / 4; ++w4) {
             int q[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -273,22 +294,34 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
               const int prev = (int)(int8_t)((pw[w4] >> (8 * i)) & 0xff);
               if (EPI & kEpiFast)
                 q[i] = epilogue_fast<(EPI & kEpiDual) != 0, (EPI & kEpiPrev) != 0, (EPI & kEpiStage2) != 0, (EPI & kEpiRange) != 0>(
-                    g.ep, kc, acc0[j], c0, (EPI & kEpiDual) ? acc1[j] : 0, c1, prev);
+                    g.ep, kc, acc0[j], c0, (EPI & kEpiDual) ? acc1[j & 15] : 0, c1, prev);
               else
-                q[i] = epilogue_exact(g.ep, kc, acc0[j], c0, g.nseg > 1, g.nseg > 1 ? acc1[j] : 0, c1, prev);
+                q[i] = epilogue_exact(g.ep, kc, acc0[j], c0, g.nseg > 1, g.nseg > 1 ? acc1[j & 15] : 0, c1, prev);
             }
             packed[w4] = pack4(q[0], q[1], q[2], q[3]);
           }
-          if (t >= len) packed[0] = packed[1] = packed[2] = packed[3] = 0u;  // jasper.py:177-181
+          if (t >= len) {   // jasper.py:177-181
+#pragma unroll
+            for (int i = 0; i < W / 4; ++i) packed[i] = 0u;
+          }
           if (t_ok && c_first < g.C_out) {
-            uint8_t* orow = reinterpret_cast<uint8_t*>(g.out) + trow * g.out_ld;
-            *reinterpret_cast<uint4*>(orow + c_first) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            uint8_t* orow = reinterpret_cast<uint8_t*>(g.out) + trow * g.out_ld + c_first;
+            if (W == 32 && c_first + 16 < g.C_out && ((reinterpret_cast<uintptr_t>(orow) & 31) == 0)) {
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow), "r"(packed[0]), "r"(packed[1]),
+                           "r"(packed[2]), "r"(packed[3]), "r"(packed[W / 4 - 4]), "r"(packed[W / 4 - 3]), "r"(packed[W / 4 - 2]),
+                           "r"(packed[W / 4 - 1]) : "memory");
+            } else {
+#pragma unroll
+              for (int i = 0; i < W / 16; ++i)
+                if (c_first + 16 * i < g.C_out)
+                  *reinterpret_cast<uint4*>(orow + 16 * i) = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+            }
           }
         } else {
           // float32 / int32 outputs go to the reference's (B, C, T) layout: consecutive lanes = consecutive
           // frames of one channel -> coalesced
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < W; ++j) {
             const int c = c_first + j;
             if (!t_ok || c >= g.C_out) continue;
             const ChanRegs c0 = load_chan_smem(tab + col0 + j, tab + BN + col0 + j, true);
@@ -300,8 +333,10 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive_warp(tempty_bar(as));
+      if (W != 32) {
+        tc_fence_before();
+        mbar_arrive_warp(tempty_bar(as));
+      }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   }
