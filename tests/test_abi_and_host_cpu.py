@@ -211,6 +211,45 @@ model:
 """
 
 
+def test_plan_signature_follows_every_state_change():
+    """The compiled-plan key (qasr.plan._signature): the quant modules are listed once per state epoch (no module-tree walk
+    per forward), attribute assignments move the epoch and the stamps, in-place edits show in the tensor versions."""
+    from nemo.collections.asr.models.ctc_models import EncDecCTCModel
+    from nemo.quantization.utils import quant_modules as qmods
+    from qasr import plan as P
+    torch.manual_seed(0)
+    model = EncDecCTCModel.from_topology("tiny_quartznet")
+    model.eval()
+    enc, dec = model.encoder, model.decoder
+    s0 = P._signature(enc, dec)
+    mods = P._quant_modules(enc, dec)
+    assert P._quant_modules(enc, dec) is mods                      # same epoch: the cached list
+    assert P._signature(enc, dec) == s0
+    act = next(m for m in enc.modules() if type(m) is qmods.QuantAct)
+    conv = next(m for m in enc.modules() if isinstance(m, qmods.QuantConv1d))
+    act.x_max = act.x_max + 1.0                                    # reassignment: stamped
+    s1 = P._signature(enc, dec)
+    assert s1 != s0 and P._quant_modules(enc, dec) is not mods
+    with torch.no_grad():
+        act.x_min.mul_(2.0)                                        # in place: version counter only
+    s2 = P._signature(enc, dec)
+    assert s2 != s1
+    with torch.no_grad():
+        conv.weight.add_(1e-3)
+    s3 = P._signature(enc, dec)
+    assert s3 != s2
+    act.activation_bit = act.activation_bit                       # even a same-value assignment is a new state
+    assert P._signature(enc, dec) != s3
+    # the encoder's fusable verdict is cached per epoch and follows a flag change
+    x = torch.zeros(1, 64, 32)
+    assert enc._fusable(x) is False                                # CPU tensor: never fusable
+    enc2 = model.encoder
+    v = getattr(enc2, "_fusable_verdict", None)
+    act.running_stat = True
+    assert getattr(enc2, "_fusable_verdict", None) is v            # untouched until asked; the epoch moved, so it is stale
+    assert qmods._STATE_COUNTER[0] > 0
+
+
 def test_nemo_archive_round_trip(tmp_path):
     """.nemo checkpoints (reference modelPT.py:254-296 / :343-405): tar.gz of model_config.yaml + model_weights.ckpt;
     a reference-style yaml builds the same module tree, save_to -> restore_from gives back config and weights."""

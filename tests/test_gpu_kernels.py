@@ -425,7 +425,7 @@ def _literal_requant(acc_plus_bias, s_out, m, e, lo, hi, relu):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("path", ["literal", "fast", "f32"])
+@pytest.mark.parametrize("path", ["literal", "fast", "f32", "range_check"])
 @pytest.mark.parametrize("relu", [False, True], ids=["signed", "relu"])
 def test_fast_paths_beyond_the_clamp_window(path, relu, gemm_engine):
     """8-bit weights x 8-bit activations over 512 channels reach |acc| ~ 2^24, beyond the 2^22 up to which the
@@ -449,7 +449,8 @@ def test_fast_paths_beyond_the_clamp_window(path, relu, gemm_engine):
     m, e = norm_me(*rand_dyadic(r, co, 1.5e-3, 6e-3))
     for _ in range(200):   # dyadics the host can prove inside the window (what the plan would require)
         bad = [i for i in range(co) if not (P.fast_ok(min(bound, P.window_bound(m[i:i + 1], e[i:i + 1], lo, hi)), m[i:i + 1], e[i:i + 1])
-                                            and P.f32_ok(min(bound, P.window_bound(m[i:i + 1], e[i:i + 1], lo, hi)), m[i:i + 1], e[i:i + 1], lo, hi))]
+                                            and P.f32_ok(min(bound, P.window_bound(m[i:i + 1], e[i:i + 1], lo, hi)), m[i:i + 1], e[i:i + 1], lo, hi)
+                                            and (path != "range_check" or P.fast_ok(P.F32_IDENTITY, m[i:i + 1], e[i:i + 1])))]
         if not bad:
             break
         mm, ee = norm_me(*rand_dyadic(r, len(bad), 1.5e-3, 6e-3))
@@ -467,6 +468,8 @@ def test_fast_paths_beyond_the_clamp_window(path, relu, gemm_engine):
         flags |= L.F_EXACT_F32 | L.F_EXACT_DYAD
     elif path == "f32":
         flags |= L.F_FAST_F32
+    elif path == "range_check":   # what the plan falls back to when the window argument does not close a launch
+        flags |= L.F_RANGE_CHECK
     ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=flags, qmin=qmin, qmax=hi)
     out = ops.alloc_codes(B, co, T, DEV)
     ops.conv_gemm(ops.gemm_operand(x, T, wp, ci, 1, 1, 1, 0), None, out, B, co, T, ep)
