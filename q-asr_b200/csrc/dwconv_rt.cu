@@ -26,8 +26,11 @@ constexpr int kMaxR = 8;   // rows per tape (mbarriers per warp)
 // EK: 0 = integer fast path, float fast path for the channels of the f32_mult table; 3 = float fast path everywhere;
 //     4 = device-written tables (QASR_F_DEVICE_TABLES, dynamic quantisation): integer fast path for the channels
 //     qasr_dyn_finalize proved, literal recipe for the others
+#ifndef QASR_RT_MIN_BLOCKS
+#define QASR_RT_MIN_BLOCKS 1
+#endif
 template <int KS, bool XS, int EK, bool PROF>
-__global__ void __launch_bounds__(kThreads, 1) dwconv_rt_kernel(const DwArgs a) {
+__global__ void __launch_bounds__(kThreads, QASR_RT_MIN_BLOCKS) dwconv_rt_kernel(const DwArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(512) uint32_t stage[kWarps][128];   // four 128-byte transpose lines per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
