@@ -61,11 +61,22 @@ __global__ void quantize_f32_kernel(const float* __restrict__ x, int x_ld, const
     const int b = (int)(row / C);
     const int len = lens ? lens[b] : T;
     int q[4];
+    // four frames at once where the row allows it (16-byte aligned, inside T): one 16-byte load instead of four
+    // predicated 4-byte ones (the 26 MB feature tensor of the bench workload: 16.7 us -> the HBM time)
+    float v4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const float* px = x + row * x_ld + 4 * j;
+    if (4 * j + 4 <= T && (reinterpret_cast<uintptr_t>(px) & 15) == 0) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(px));
+      v4[0] = f.x; v4[1] = f.y; v4[2] = f.z; v4[3] = f.w;
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (4 * j + u < T) v4[u] = px[u];
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int t = 4 * j + u;
-      float v = 0.0f;
-      if (t < T && t < len) v = x[row * x_ld + t];
+      const float v = t < len ? v4[u] : 0.0f;
       float r = rintf(__fmul_rn(inv, v));
       r = fminf(fmaxf(r, (float)(-n)), (float)(n - 1));     // quant_utils.py:76
       // fixedpoint_mul with pre_sf == z_sf: z = rne((r*s)/s) == r; clamp [-n-1, n] is a no-op
