@@ -27,15 +27,22 @@ namespace {
 
 using namespace qasr_tc;
 
-constexpr int BM = 128, BN = 128, BK = 128;
-constexpr int kStages = 5;
+// Tile = BM frames x (128 NB) output channels.  NB = 2 (single-operand launches whose C_out is a multiple of 256): one
+// 16 KB activation slab feeds an N = 256 MMA, i.e. 48 KB of operands per 512 clk of MMAs instead of 64 KB -- the dense
+// convs of Jasper are bound by operand delivery (435 clk per slab pair against 256 clk of MMAs at NB = 1).
+constexpr int BM = 128, BN1 = 128, BK = 128;
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = 128 + 32 * kEpiWarps;
-constexpr uint32_t kABytes = BM * BK, kBBytes = BN * BK;
-constexpr uint32_t kStageBytes = kABytes + kBBytes;
-constexpr uint32_t kTabBytes = 2 /*operands*/ * 2 /*fast, exact*/ * BN * 16;
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kTabBytes;
+constexpr uint32_t kABytes = BM * BK, kBBytes1 = BN1 * BK;
 constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kAccStride = 256;   // TMEM columns per accumulator stage: 2 operands x 128 (NB = 1) or 1 x 256 (NB = 2)
+template <int NB> struct Geo {
+  static constexpr int BN = BN1 * NB;
+  static constexpr int kStages = NB == 1 ? 5 : 4;
+  static constexpr uint32_t kStageBytes = kABytes + NB * kBBytes1;
+  static constexpr uint32_t kTabBytes = 2 /*operands*/ * 2 /*fast, exact*/ * BN * 16;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kTabBytes;
+};
 
 struct Seg {
   int taps, cblocks, stride, dil, pad, c_out_pad;
@@ -92,10 +99,13 @@ __device__ __forceinline__ bool elect_one() {
   return p != 0;
 }
 
-template <int EPI>
+template <int EPI, int NB>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmW0,
                 const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmW1, const Args g) {
+  constexpr int BN = Geo<NB>::BN, kStages = Geo<NB>::kStages;
+  constexpr uint32_t kStageBytes = Geo<NB>::kStageBytes;
+  static_assert(NB == 1 || !(EPI & kEpiDual), "NB = 2 tiles hold one operand's accumulators");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + kStages * kStageBytes;
@@ -193,7 +203,7 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
 #pragma unroll
       for (int sg = 0; sg < 2; ++sg) {
         if (sg >= nseg) break;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 2 * BN + sg * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccStride + sg * BN1);
         const int slabs = seg_slabs[sg];
         const uint32_t idesc = seg_idesc[sg];
         for (int it = 0; it < slabs; ++it) {
@@ -249,19 +259,21 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
       // the arithmetic and every lane writes one full 32-byte sector (Jasper's 1x1 dense-residual chain is paced by this
       // epilogue); two-operand and literal launches keep 16-column halves (registers)
       constexpr int W = ((EPI & kEpiFast) && !(EPI & kEpiDual)) ? 32 : 16;
+      constexpr int kCols = BN / 4;          // columns of this warp's column group
+      constexpr int kChunks = kCols / W;
 #pragma unroll 1
-      for (int ch = 0; ch < 32 / W; ++ch) {
-        const int col0 = cgroup * 32 + ch * W;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * 2 * BN + col0);
+      for (int ch = 0; ch < kChunks; ++ch) {
+        const int col0 = cgroup * kCols + ch * W;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccStride + col0);
         int acc0[W], acc1[16];
         if constexpr (W == 32) {
           tmem_ld32(taddr, acc0);
         } else {
           tmem_ld16(taddr, acc0);
-          if (g.nseg > 1) tmem_ld16(taddr + BN, acc1);
+          if (g.nseg > 1) tmem_ld16(taddr + BN1, acc1);
         }
         tmem_ld_wait();
-        if (W == 32) {
+        if (W == 32 && ch == kChunks - 1) {   // the last load of this buffer has landed
           tc_fence_before();
           mbar_arrive_warp(tempty_bar(as));
         }
@@ -351,12 +363,12 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-int make_map_weights(CUtensorMap* map, const int8_t* wp, int rows, int c_in_pad) {
+int make_map_weights(CUtensorMap* map, const int8_t* wp, int rows, int c_in_pad, int bn) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { qasr_set_error("cuTensorMapEncodeTiled entry point not available"); return QASR_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)c_in_pad, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)c_in_pad};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(wp), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -446,6 +458,15 @@ extern "C" int qasr_conv1d_ntc_i8(const qasr_gemm_operand* op0, const qasr_gemm_
   memset(maps, 0, sizeof(maps));
   const qasr_gemm_operand* ops[2] = {op0, op1};
   g.nseg = op1 ? 2 : 1;
+  const bool fast = !(epi->flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64)) &&
+                    epi->mode == QASR_EPI_REQUANT_I8;
+  // 256-channel tiles: single-operand fast launches (conv -> act) with C_out a multiple of 256 and enough slabs per tile
+  // for the operand traffic to matter; bring-up knob 21 = 0 keeps 128-channel tiles
+  int nb = 1;
+  if (fast && !op1 && !epi->prev && !(epi->flags & QASR_F_STAGE2) && C_out % 256 == 0 && qasr_debug_get(21) != 0 &&
+      (long long)op0->k * ((op0->C_in + BK - 1) / BK) >= 8)
+    nb = 2;
+  const int BN = BN1 * nb;
   for (int i = 0; i < g.nseg; ++i) {
     const qasr_gemm_operand* o = ops[i];
     QASR_CHECK_ARG(o->x && o->wp && o->C_in > 0 && o->T_in > 0 && o->k > 0, "conv1d_ntc: operand %d bad", i);
@@ -460,13 +481,13 @@ extern "C" int qasr_conv1d_ntc_i8(const qasr_gemm_operand* op0, const qasr_gemm_
     s.stride = o->stride;
     s.dil = o->dilation;
     s.pad = o->pad;
-    s.c_out_pad = round_up(C_out, BN);
+    s.c_out_pad = round_up(C_out, BN1);   // the packing of qasr_pack_conv_weights
     const uint32_t a_signed = (epi->flags & (i == 0 ? QASR_F_B_SIGNED : QASR_F_B1_SIGNED)) ? 1u : 0u;
     // D=S32, A = activations (un)signed K-major, B = weights signed K-major, N=128, M=128
     s.idesc = (2u << 4) | (a_signed << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     rc = make_map_acts(&maps[2 * i], o->x, o->C_in, o->T_in, B, o->x_ld, o->stride);
     if (rc) return rc;
-    rc = make_map_weights(&maps[2 * i + 1], o->wp, o->k * s.c_out_pad, round_up(o->C_in, BK));
+    rc = make_map_weights(&maps[2 * i + 1], o->wp, o->k * s.c_out_pad, round_up(o->C_in, BK), BN);
     if (rc) return rc;
   }
   if (g.nseg == 1) { maps[2] = maps[0]; maps[3] = maps[1]; }
@@ -487,8 +508,6 @@ extern "C" int qasr_conv1d_ntc_i8(const qasr_gemm_operand* op0, const qasr_gemm_
   }
   g.ep = make_epi_args(epi);
   g.stamp = qasr_next_stamp();
-  const bool fast = !(epi->flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64)) &&
-                    epi->mode == QASR_EPI_REQUANT_I8;
   int variant = 0;
   if (fast)
     variant = kEpiFast | (op1 ? kEpiDual : 0) | (epi->prev ? kEpiPrev : 0) | ((epi->flags & QASR_F_STAGE2) ? kEpiStage2 : 0);
@@ -503,10 +522,24 @@ extern "C" int qasr_conv1d_ntc_i8(const qasr_gemm_operand* op0, const qasr_gemm_
 #define QASR_NTC_CASE(V_)                                                                                      \
   case V_:                                                                                                     \
     if (need_attr)                                                                                             \
-      QASR_CHECK_CUDA(cudaFuncSetAttribute(conv_ntc_kernel<V_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                           (int)kSmemBytes));                                                  \
-    conv_ntc_kernel<V_><<<grid, kThreads, kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);            \
+      QASR_CHECK_CUDA(cudaFuncSetAttribute(conv_ntc_kernel<V_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)Geo<1>::kSmemBytes));                                          \
+    conv_ntc_kernel<V_, 1><<<grid, kThreads, Geo<1>::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g); \
     break;
+  if (nb == 2) {   // 256-channel tiles: variants 1 and 65 only (see the choice of nb above)
+    static bool attr2_set[2][64] = {};
+    const int vi = variant == 1 ? 0 : 1;
+    if (dev >= 0 && dev < 64 && !attr2_set[vi][dev]) {
+      if (variant == 1)
+        QASR_CHECK_CUDA(cudaFuncSetAttribute(conv_ntc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<2>::kSmemBytes));
+      else
+        QASR_CHECK_CUDA(cudaFuncSetAttribute(conv_ntc_kernel<65, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<2>::kSmemBytes));
+      attr2_set[vi][dev] = true;
+    }
+    if (variant == 1) conv_ntc_kernel<1, 2><<<grid, kThreads, Geo<2>::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);
+    else conv_ntc_kernel<65, 2><<<grid, kThreads, Geo<2>::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);
+    return qasr_check_launch("conv_ntc_kernel");
+  }
   switch (variant) {
     QASR_NTC_CASE(0)
     QASR_NTC_CASE(1)

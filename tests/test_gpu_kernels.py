@@ -363,6 +363,53 @@ def test_conv_ntc_requant_dual_prev(case, fast):
     assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
 
 
+NTC_SINGLE_CASES = [
+    # name, B, C_in, C_out, T, k, stride, dil, signed: C_out multiples of 256 with >= 8 slabs per tile take 256-channel tiles
+    ("ntc1_k5_256_512", 2, 256, 512, 300, 5, 1, 1, False),
+    ("ntc1_k3_384_768", 1, 384, 768, 260, 3, 1, 1, True),
+    ("ntc1_k11_s2_128_256", 2, 128, 256, 301, 11, 2, 1, False),
+    ("ntc1_k9_dil2_128_1024", 1, 128, 1024, 140, 9, 1, 2, False),
+    ("ntc1_k7_96_160", 2, 96, 160, 150, 7, 1, 1, True),          # not a multiple of 256: 128-channel tiles either way
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tiles", [128, 256])
+@pytest.mark.parametrize("path", ["exact", "fast", "range_check"])
+@pytest.mark.parametrize("case", NTC_SINGLE_CASES, ids=lambda c: c[0])
+def test_conv_ntc_single_operand(case, path, tiles):
+    """conv -> ReLU -> act on the channels-last kernel (Jasper's dense convs): 128- and 256-channel tiles (bring-up knob
+    21), literal / integer fast / range-checked epilogues, ragged lengths."""
+    name, B, ci, co, T, k, stride, dil, signed = case
+    r = rng(23)
+    q = r.integers(-128, 128, (B, ci, T)) if signed else r.integers(0, 256, (B, ci, T))
+    w = r.integers(-20, 20, (co, ci, k))
+    bias = r.integers(-3000, 3000, co)
+    pad = (dil * k) // 2 - 1 if dil > 1 else k // 2
+    acc = O.conv1d_int(q, w, bias, stride, pad, dil, 1)
+    T_out = acc.shape[2]
+    m, e = norm_me(*rand_dyadic(r, co, 1e-5, 1e-4))
+    lens = r.integers(T_out // 2, T_out + 1, B).astype(np.int32)
+    want = expected_requant(acc, m, e, -256, 255, relu0=True, lens=lens)
+    wp = ops.pack_weights(torch.from_numpy(w.astype(np.int8)).to(DEV))
+    ch = ops.chan_table(np.full(co, 1e-4, np.float32), bias, m, e, DEV)
+    flags = L.F_RELU0 | L.F_MASK | (L.F_B_SIGNED if signed else 0)
+    if path == "exact":
+        flags |= L.F_EXACT_F32 | L.F_EXACT_DYAD
+    elif path == "range_check":
+        flags |= L.F_RANGE_CHECK
+    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=flags, qmin=-256, qmax=255, out_lens=torch.from_numpy(lens).to(DEV))
+    out = ops.alloc_codes_ntc(B, co, T_out, DEV)
+    L.lib().qasr_debug_set(21, 0 if tiles == 128 else -1)
+    try:
+        ops.conv_ntc(ops.gemm_operand(to_ntc_tensor(q, signed), T, wp, ci, k, stride, dil, pad), None, out, B, co, T_out, ep)
+        torch.cuda.synchronize()
+    finally:
+        L.lib().qasr_debug_set(21, -1)
+    got = from_ntc_tensor(out, co, signed=False)
+    assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
+
+
 def test_quantize_f32_ntc():
     r = rng(21)
     B, Cn, T = 3, 40, 70
