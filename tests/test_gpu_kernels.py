@@ -369,7 +369,8 @@ NTC_SINGLE_CASES = [
     ("ntc1_k3_384_768", 1, 384, 768, 260, 3, 1, 1, True),
     ("ntc1_k11_s2_128_256", 2, 128, 256, 301, 11, 2, 1, False),
     ("ntc1_k9_dil2_128_1024", 1, 128, 1024, 140, 9, 1, 2, False),
-    ("ntc1_k7_96_160", 2, 96, 160, 150, 7, 1, 1, True),          # not a multiple of 256: 128-channel tiles either way
+    ("ntc1_k9_128_896", 1, 128, 896, 200, 9, 1, 1, False),       # 3.5 x 256: the last 256-channel tile is half empty
+    ("ntc1_k7_96_160", 2, 96, 160, 150, 7, 1, 1, True),          # 128-channel tiles either way
 ]
 
 
