@@ -463,10 +463,10 @@ extern "C" int qasr_conv1d_ntc_i8(const qasr_gemm_operand* op0, const qasr_gemm_
   // 256-channel tiles: single-operand fast launches (conv -> act) with C_out a multiple of 256 and enough slabs per tile
   // for the operand traffic to matter; bring-up knob 21 = 0 keeps 128-channel tiles
   int nb = 1;
-  // (a last half-empty tile is accepted up to 15 % extra work: C_out = 896; its surplus channels are computed on whatever
+  // (a last half-empty tile is accepted up to 20 % extra work: C_out = 896, 640; its surplus channels are computed on whatever
   // weight rows follow and never stored)
   const int c256 = (C_out + 255) / 256 * 256;
-  if (fast && !op1 && !epi->prev && !(epi->flags & QASR_F_STAGE2) && (c256 - C_out) * 100 <= 15 * C_out && qasr_debug_get(21) != 0 &&
+  if (fast && !op1 && !epi->prev && !(epi->flags & QASR_F_STAGE2) && (c256 - C_out) * 100 <= 20 * C_out && qasr_debug_get(21) != 0 &&
       (long long)op0->k * ((op0->C_in + BK - 1) / BK) >= 8)
     nb = 2;
   const int BN = BN1 * nb;
