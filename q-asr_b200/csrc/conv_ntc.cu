@@ -35,7 +35,8 @@ constexpr int kEpiWarps = 16;
 constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = BM * BK, kBBytes1 = BN1 * BK;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kAccStride = 256;   // TMEM columns per accumulator stage: 2 operands x 128 (NB = 1) or 1 x 256 (NB = 2)
+constexpr uint32_t kAccStride = 256;   // TMEM columns per accumulator stage: 2 operands x 128 (NB = 1) or 1 x 256 (NB = 2);
+                                       // two operands x 256 (NB = 2, res_act) take all 512 columns: ONE stage
 template <int NB> struct Geo {
   static constexpr int BN = BN1 * NB;
   static constexpr int kStages = NB == 1 ? 5 : 4;
@@ -105,7 +106,9 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmW1, const Args g) {
   constexpr int BN = Geo<NB>::BN, kStages = Geo<NB>::kStages;
   constexpr uint32_t kStageBytes = Geo<NB>::kStageBytes;
-  static_assert(NB == 1 || !(EPI & kEpiDual), "NB = 2 tiles hold one operand's accumulators");
+  // accumulator stages in TMEM: the MMAs of tile i + 1 overlap the epilogue of tile i, except for two-operand 256-channel
+  // tiles, whose accumulators fill the 512 columns (the drain is a few percent of a dense tile's MMA time)
+  constexpr int kAccStages = (NB == 2 && (EPI & kEpiDual)) ? 1 : 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + kStages * kStageBytes;
@@ -203,7 +206,7 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
 #pragma unroll
       for (int sg = 0; sg < 2; ++sg) {
         if (sg >= nseg) break;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccStride + sg * BN1);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccStride + sg * BN);
         const int slabs = seg_slabs[sg];
         const uint32_t idesc = seg_idesc[sg];
         for (int it = 0; it < slabs; ++it) {
@@ -221,7 +224,7 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
         }
       }
       if (leader) tc_commit(tfull_bar(as));
-      if (++as == 2) { as = 0; aphase ^= 1u; }
+      if (++as == kAccStages) { as = 0; aphase ^= 1u; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -270,7 +273,7 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
           tmem_ld32(taddr, acc0);
         } else {
           tmem_ld16(taddr, acc0);
-          if (g.nseg > 1) tmem_ld16(taddr + BN1, acc1);
+          if (g.nseg > 1) tmem_ld16(taddr + BN, acc1);
         }
         tmem_ld_wait();
         if (W == 32 && ch == kChunks - 1) {   // the last load of this buffer has landed
@@ -349,7 +352,7 @@ conv_ntc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant_
         tc_fence_before();
         mbar_arrive_warp(tempty_bar(as));
       }
-      if (++as == 2) { as = 0; aphase ^= 1u; }
+      if (++as == kAccStages) { as = 0; aphase ^= 1u; }
     }
   }
 
@@ -466,8 +469,11 @@ extern "C" int qasr_conv1d_ntc_i8(const qasr_gemm_operand* op0, const qasr_gemm_
   // (a last half-empty tile is accepted up to 20 % extra work: C_out = 896, 640; its surplus channels are computed on whatever
   // weight rows follow and never stored)
   const int c256 = (C_out + 255) / 256 * 256;
-  if (fast && !op1 && !epi->prev && !(epi->flags & QASR_F_STAGE2) && (c256 - C_out) * 100 <= 20 * C_out && qasr_debug_get(21) != 0 &&
-      (long long)op0->k * ((op0->C_in + BK - 1) / BK) >= 8)
+  long long slabs_tile = (long long)op0->k * ((op0->C_in + BK - 1) / BK);
+  if (op1) slabs_tile += (long long)op1->k * ((op1->C_in + BK - 1) / BK);
+  // single operand: conv -> act (variants 1, 65); two operands: res_act with or without the second stage (3, 11, 67, 75)
+  const bool nb2_shape = op1 ? !epi->prev : (!epi->prev && !(epi->flags & QASR_F_STAGE2));
+  if (fast && nb2_shape && (c256 - C_out) * 100 <= 20 * C_out && qasr_debug_get(21) != 0 && slabs_tile >= 8)
     nb = 2;
   const int BN = BN1 * nb;
   for (int i = 0; i < g.nseg; ++i) {
@@ -529,18 +535,29 @@ extern "C" int qasr_conv1d_ntc_i8(const qasr_gemm_operand* op0, const qasr_gemm_
                                            (int)Geo<1>::kSmemBytes));                                          \
     conv_ntc_kernel<V_, 1><<<grid, kThreads, Geo<1>::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g); \
     break;
-  if (nb == 2) {   // 256-channel tiles: variants 1 and 65 only (see the choice of nb above)
-    static bool attr2_set[2][64] = {};
-    const int vi = variant == 1 ? 0 : 1;
-    if (dev >= 0 && dev < 64 && !attr2_set[vi][dev]) {
-      if (variant == 1)
-        QASR_CHECK_CUDA(cudaFuncSetAttribute(conv_ntc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<2>::kSmemBytes));
-      else
-        QASR_CHECK_CUDA(cudaFuncSetAttribute(conv_ntc_kernel<65, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<2>::kSmemBytes));
-      attr2_set[vi][dev] = true;
+  if (nb == 2) {   // 256-channel tiles: variants 1, 65 (single operand) and 3, 11, 67, 75 (res_act), see the choice of nb
+    static bool attr2_set[128][64] = {};
+    const bool need2 = dev >= 0 && dev < 64 && !attr2_set[variant][dev];
+#define QASR_NTC2_CASE(V_)                                                                                         \
+  case V_:                                                                                                         \
+    if (need2)                                                                                                     \
+      QASR_CHECK_CUDA(cudaFuncSetAttribute(conv_ntc_kernel<V_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                           (int)Geo<2>::kSmemBytes));                                              \
+    conv_ntc_kernel<V_, 2><<<grid, kThreads, Geo<2>::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);     \
+    break;
+    switch (variant) {
+      QASR_NTC2_CASE(1)
+      QASR_NTC2_CASE(65)
+      QASR_NTC2_CASE(3)
+      QASR_NTC2_CASE(11)
+      QASR_NTC2_CASE(67)
+      QASR_NTC2_CASE(75)
+      default:
+        qasr_set_error("conv1d_ntc: internal: no 256-channel kernel variant %d", variant);
+        return QASR_ERR_INVALID;
     }
-    if (variant == 1) conv_ntc_kernel<1, 2><<<grid, kThreads, Geo<2>::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);
-    else conv_ntc_kernel<65, 2><<<grid, kThreads, Geo<2>::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], g);
+#undef QASR_NTC2_CASE
+    if (need2) attr2_set[variant][dev] = true;
     return qasr_check_launch("conv_ntc_kernel");
   }
   switch (variant) {

@@ -411,6 +411,55 @@ def test_conv_ntc_single_operand(case, path, tiles):
     assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("tiles", [128, 256])
+@pytest.mark.parametrize("stage2", [False, True], ids=["plain", "stage2"])
+@pytest.mark.parametrize("path", ["exact", "fast", "range_check"])
+@pytest.mark.parametrize("case", NTC_SINGLE_CASES[:2] + NTC_SINGLE_CASES[4:5], ids=lambda c: c[0])
+def test_conv_ntc_res_act(case, path, stage2, tiles):
+    """res_act on the channels-last kernel (jasper.py:681): main dense conv + residual 1x1 conv, no previous addend;
+    with 256-channel tiles the two operands' accumulators take all 512 TMEM columns (one accumulator stage)."""
+    name, B, ci, co, T, k, stride, dil, signed = case
+    r = rng(24)
+    q = r.integers(-128, 128, (B, ci, T)) if signed else r.integers(0, 256, (B, ci, T))
+    w = r.integers(-20, 20, (co, ci, k))
+    bias = r.integers(-3000, 3000, co)
+    pad = (dil * k) // 2 - 1 if dil > 1 else k // 2
+    acc0 = O.conv1d_int(q, w, bias, stride, pad, dil, 1)
+    T_out = acc0.shape[2]
+    ci1 = 192
+    q1 = r.integers(0, 256, (B, ci1, T_out))
+    w1 = r.integers(-60, 60, (co, ci1, 1))
+    acc1 = O.conv1d_int(q1, w1, None, 1, 0, 1, 1)
+    m0, e0 = norm_me(*rand_dyadic(r, co, 1e-5, 1e-4))
+    m1, e1 = norm_me(*rand_dyadic(r, co, 1e-5, 2e-4))
+    m2, e2 = norm_me(*O.batch_frexp(np.array([2.01])))
+    lens = r.integers(T_out // 2, T_out + 1, B).astype(np.int32)
+    want = expected_requant(acc0, m0, e0, -128, 127, acc1=acc1, m1=m1, e1=e1, relu1=stage2,
+                            stage2=(m2[0], e2[0], -256, 255) if stage2 else None, lens=lens)
+    wp = ops.pack_weights(torch.from_numpy(w.astype(np.int8)).to(DEV))
+    wp1 = ops.pack_weights(torch.from_numpy(w1.astype(np.int8)).to(DEV))
+    one = np.full(co, 1e-4, np.float32)
+    ch0, ch1 = ops.chan_table(one, bias, m0, e0, DEV), ops.chan_table(one, None, m1, e1, DEV)
+    flags = L.F_MASK | (L.F_B_SIGNED if signed else 0) | ((L.F_RELU1 | L.F_STAGE2) if stage2 else 0)
+    if path == "exact":
+        flags |= L.F_EXACT_F32 | L.F_EXACT_DYAD
+    elif path == "range_check":
+        flags |= L.F_RANGE_CHECK
+    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch0, flags=flags, ch1=ch1, qmin=-128, qmax=127, m2=m2[0], e2=e2[0],
+                           qmin2=-256, qmax2=255, out_lens=torch.from_numpy(lens).to(DEV))
+    out = ops.alloc_codes_ntc(B, co, T_out, DEV)
+    L.lib().qasr_debug_set(21, 0 if tiles == 128 else -1)
+    try:
+        ops.conv_ntc(ops.gemm_operand(to_ntc_tensor(q, signed), T, wp, ci, k, stride, dil, pad),
+                     ops.gemm_operand(to_ntc_tensor(q1, False), T_out, wp1, ci1, 1), out, B, co, T_out, ep)
+        torch.cuda.synchronize()
+    finally:
+        L.lib().qasr_debug_set(21, -1)
+    got = from_ntc_tensor(out, co, signed=not stage2)
+    assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
+
+
 def test_quantize_f32_ntc():
     r = rng(21)
     B, Cn, T = 3, 40, 70
