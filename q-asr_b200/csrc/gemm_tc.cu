@@ -941,6 +941,10 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   g.n_total = g.n_tiles * B;
   // M tiles per CTA: two when both accumulator sets still double-buffer in TMEM (512 columns)
   g.MT = (g.nseg == 1 && g.m_tiles % 2 == 0) ? 2 : 1;
+  // less than one wave of (M tile, time tile) pairs (BASELINE config 1: batch 8 x 250 frames): one M tile per CTA doubles
+  // the CTAs at work and halves the weights each loads before its only tile (256 x 256: 3.8 -> 3.0 us)
+  const bool sub_wave = (long long)g.n_total * g.m_tiles <= qasr_sm_count();
+  if (sub_wave) g.MT = 1;
   const uint32_t budget = kSmemBudget - kSmemSlack;
   auto a_bytes = [&](int mt) { return (uint32_t)(mt * g.a_slabs) * kABytes; };
   if (g.MT == 2 && a_bytes(2) + 4 * kBBytes > budget && a_bytes(1) + 4 * kBBytes <= budget) g.MT = 1;
@@ -985,7 +989,7 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   // epilogue): single-operand layers with K >= 512 and 4 M tiles (15.6 us against 16.9 us), or K >= 1024 (41.6 us
   // against 56.8 us, where one CTA cannot keep two M tiles resident); 256-channel and two-operand layers stay on the
   // 1-CTA kernel (8.5 / 12.6 / 36.1 us against 9.7 / 14.1 / 35.6 us).  Bring-up knob 12 forces either (0 / 1).
-  const bool pair_auto = g.nseg == 1 && g.m_tiles >= 4 && (g.a_slabs >= 8 || (g.a_slabs >= 4 && g.m_tiles == 4));
+  const bool pair_auto = !sub_wave && g.nseg == 1 && g.m_tiles >= 4 && (g.a_slabs >= 8 || (g.a_slabs >= 4 && g.m_tiles == 4));
   bool pair = (qasr_debug_get(12) == 1 || (qasr_debug_get(12) != 0 && pair_auto)) && g.m_tiles % 2 == 0 &&
               a_bytes(1) + 4 * kBBytes <= budget && qasr_sm_count() >= 2;
   for (int i = 0; i < g.nseg; ++i) pair = pair && g.seg[i].stride == 1;

@@ -156,13 +156,16 @@ def test_gemm_raw_i32(case):
     assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
 
 
-@pytest.fixture(params=[0, 1], ids=["cta1", "cta_pair"])
+@pytest.fixture(params=[0, 1, 2], ids=["cta1", "cta_pair", "cta1_mt2"])
 def gemm_engine(request):
-    """Both GEMM schedules on every requantising case: one CTA per SM, and CTA pairs issuing tcgen05 cta_group::2
-    (bring-up knob 12; shapes with an odd number of 128-row tiles fall back to one CTA either way)."""
-    L.lib().qasr_debug_set(12, request.param)
+    """The GEMM schedules on every requantising case: one CTA per SM, CTA pairs issuing tcgen05 cta_group::2 (bring-up
+    knob 12; shapes with an odd number of 128-row tiles fall back to one CTA either way), and one CTA with two resident M
+    tiles forced (knob 5 = 2: the test shapes are below one wave of tiles, where the library picks one M tile per CTA)."""
+    L.lib().qasr_debug_set(12, 1 if request.param == 1 else 0)
+    L.lib().qasr_debug_set(5, 2 if request.param == 2 else -1)
     yield request.param
     L.lib().qasr_debug_set(12, -1)
+    L.lib().qasr_debug_set(5, -1)
 
 
 @pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
