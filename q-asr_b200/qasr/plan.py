@@ -93,7 +93,29 @@ def f32_ok(bound, m, e, lo, hi):
     return bool(f32_ok_channels(bound, m, e, lo, hi).all())
 
 
-def f32_ok_channels(bound, m, e, lo, hi):
+def f32_multipliers(bound, m, e, lo, hi, spread=1):
+    """Per channel: a float32 multiplier r' for which the one-FMA float epilogue clamp(rint(f32(z) * r'), lo, hi) equals the
+    dyadic rne(z * m / 2^e) for every integer |z| <= bound, or 0.0 when none is found.  The canonical choice is
+    r32 = f32(m * 2^-e); where its rounding error moves one of the (hi - lo + 2) jumps across an integer z, a neighbour
+    r32 +- 1 ulp may not (the multipliers that satisfy every jump form an interval of about one ulp around m 2^-e): with
+    255 jumps (8-bit codes) 82 % of the channels pass on r32 and 91 % on a neighbour, with 64 jumps (6-bit) 99 % and 100 %,
+    which matters because the GEMM picks its float path per WARP of 32 channels.  The proof
+    is the one of f32_ok_channels(), run on the multiplier that is actually handed to the kernel (qasr_epilogue.f32_mult).
+    Call only when fast_ok() already holds."""
+    m1 = np.atleast_1d(m).astype(np.int64)
+    e1 = np.atleast_1d(e).astype(np.int64)
+    r32 = (np.where(m1 > 0, m1, 1).astype(F64) * np.exp2(-np.clip(e1, 1, 62).astype(F64))).astype(F32)
+    out = np.zeros(m1.shape[0], F32)
+    for k in sorted(range(-spread, spread + 1), key=abs):
+        cand = r32.copy()
+        for _ in range(abs(k)):
+            cand = np.nextafter(cand, F32(np.inf) if k > 0 else F32(0), dtype=F32)
+        ok = f32_ok_channels(bound, m, e, lo, hi, mult=cand) & (out == 0) & (cand > 0)
+        out = np.where(ok, cand, out)
+    return out
+
+
+def f32_ok_channels(bound, m, e, lo, hi, mult=None):
     """Per channel: may the one-FMA float epilogue clamp(rint(f32(z) * f32(m * 2^-e)), lo, hi) (QASR_F_FAST_F32) replace the
     dyadic rne(z * m / 2^e) for every integer |z| <= bound?  Call only when fast_ok() already holds (so the
     dyadic has no ties and equals (z*m + 2^(e-1)) >> e).  Both functions are non-decreasing in z, so they agree
@@ -106,7 +128,7 @@ def f32_ok_channels(bound, m, e, lo, hi):
     sane = ((m > 0) & (e >= 1) & (e <= 62)).reshape(-1)
     m, e = np.where(m > 0, m, 1), np.clip(e, 1, 62)
     r64 = m.astype(F64) * np.exp2(-e.astype(F64))          # exact: 31-bit integer times a power of two
-    r32 = r64.astype(F32).astype(F64)
+    r32 = r64.astype(F32).astype(F64) if mult is None else np.asarray(mult, F32).astype(F64).reshape(-1, 1)
     sane &= (bound * r64.reshape(-1)) < 2 ** 21
     h = np.arange(lo - 1, hi + 1, dtype=F64).reshape(1, -1) + 0.5     # exact jumps happen where z*r crosses h
     z0 = np.floor(h / r64)
@@ -451,13 +473,14 @@ class FusedPlan:
                     eff = 0          # no float path on top of a range-checked launch
             kw = dict(qmin=qmin, qmax=qmax)
             if fast and not (flags & L.F_RANGE_CHECK) and os.environ.get("QASR_NO_F32") != "1":   # float epilogue where the host can prove it, channel by channel
-                okc = f32_ok_channels(eff, m, e, lo_eff, qmax)
+                rf = f32_multipliers(eff, m, e, lo_eff, qmax)
+                okc = rf != 0
                 self.stats["f32_channels"] += int(okc.sum())
                 self.stats["channels"] += int(okc.size)
-                if okc.all():
-                    flags |= L.F_FAST_F32
+                canonical = (m.astype(F64) * np.exp2(-e.astype(F64))).astype(F32)
+                if okc.all() and np.array_equal(rf, canonical):
+                    flags |= L.F_FAST_F32          # the kernels derive r32 from (m, e) themselves
                 elif okc.any():
-                    rf = np.where(okc, (m.astype(F64) * np.exp2(-e.astype(F64))).astype(F32), F32(0.0)).astype(F32)
                     kw["f32_mult"] = rf
             self._emit_conv([(base, cp, m, e)], out, flags, fast, kw, lens, "conv->act")
         elif isinstance(base, ResActVal):

@@ -37,11 +37,11 @@ def kernel_integer(z, m, e, lo, hi):
     return np.clip((p >> np.int64(32)) >> np.int64(e - 32), lo, hi)
 
 
-def kernel_float(z, m, e, lo, hi):
+def kernel_float(z, m, e, lo, hi, mult=None):
     """epilogue_f32_bits: bits = 0x4B400000 + z reinterpreted as float32, minus 1.5 * 2^23, FMA with f32(m 2^-e) and the
     magic, float clamp, low byte.  The FMA is evaluated exactly here: f and r are float32 values, so f * r is exact in
     float64, and rounding (f * r + magic) to float32 = rounding f * r to the grid of spacing ulp(result)."""
-    r32 = F64(F32(F64(m) * 2.0 ** -e))
+    r32 = F64(F32(F64(m) * 2.0 ** -e)) if mult is None else F64(F32(mult))
     bits = (np.int64(MAGIC_BITS) + z).astype(np.int32)
     f = (bits.view(F32) - MAGIC).astype(F64)          # FADD: exact (both operands on one binade grid or coarser)
     t = f * r32                                        # exact in float64
@@ -113,3 +113,28 @@ def test_fast_ok_checked_asks_for_the_range_check_beyond_2_22():
     assert P.fast_ok_checked(2 ** 20, m, e) == (True, False)
     assert P.fast_ok_checked(2 ** 24, m, e) == (True, True)
     assert P.fast_ok_checked(2 ** 31, m, e) == (False, False)
+
+
+def test_neighbouring_float_multipliers_are_proved_too():
+    """f32_multipliers(): where f32(m 2^-e) fails a jump, the neighbouring float may satisfy all of them; whatever it hands
+    to the kernel must equal the literal recipe on every accumulator."""
+    rng = np.random.default_rng(11)
+    m, e = O.batch_frexp(rng.uniform(5e-4, 8e-3, 512))
+    m, e = np.asarray(m, np.int64), np.asarray(e, np.int64)
+    big = m >= 2 ** 31
+    m, e = np.where(big, m // 2, m), np.where(big, e - 1, e)
+    lo, hi = 0, 255
+    eff = min(2 ** 24, P.window_bound(m, e, lo, hi))
+    ok = np.array([P.fast_ok(eff, m[i:i + 1], e[i:i + 1]) for i in range(m.size)])
+    canon = P.f32_ok_channels(eff, m, e, lo, hi)
+    rf = P.f32_multipliers(eff, m, e, lo, hi)
+    rescued = np.nonzero(ok & ~canon & (rf != 0))[0]
+    assert rescued.size >= 10 and (rf != 0).sum() > canon.sum()
+    r32 = (m.astype(F64) * np.exp2(-e.astype(F64))).astype(F32)
+    assert (rf[rescued] != r32[rescued]).all() and np.array_equal(rf[canon], r32[canon])
+    s = F32(3e-4)
+    for i in rescued[:3]:
+        for start in range(-2 ** 24, 2 ** 24 + 1, 1 << 22):
+            z = np.arange(start, min(start + (1 << 22), 2 ** 24 + 1), dtype=np.int64)
+            want = literal(z, s, int(m[i]), int(e[i]), lo, hi, True)
+            assert np.array_equal(kernel_float(z, int(m[i]), int(e[i]), lo, hi, mult=rf[i]), want)
