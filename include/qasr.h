@@ -114,6 +114,11 @@ typedef struct {
                                  with a single rounding, equals the dyadic result for every
                                  reachable accumulator (|acc+bias| < 2^22); kernels then run
                                  the epilogue on the FP32 pipe (2x the IMAD.HI rate on B200) */
+#define QASR_F_CLAMP16   4096 /* with FAST_F32 or f32_mult: the host ALSO proved |rint((acc+bias) * r)| < 2^15 for every
+                                 reachable accumulator of every float-path channel (the worst-case bound, not the clamp
+                                 window), and the clamp is the ReLU-folded [0, qmax] (RELU0 set, qmin <= 0), so kernels
+                                 may clamp two outputs at a time on packed 16-bit lanes (one VIMNMX.S16x2.RELU) instead
+                                 of two FMNMX per output.  A hint: kernels without a 16-bit epilogue ignore it         */
 
 typedef struct {
   int32_t mode;              /* QASR_EPI_*                                               */

@@ -114,6 +114,9 @@ int qasr_validate_epilogue(const qasr_epilogue* e, bool allow_second_operand) {
                      (e->mode == QASR_EPI_REQUANT_I8 && e->f32_mult == nullptr &&
                       !(e->flags & (QASR_F_FAST_F32 | QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64 | QASR_F_DEVICE_TABLES))),
                  "epilogue: RANGE_CHECK belongs to the integer fast path of a REQUANT launch");
+  QASR_CHECK_ARG(!(e->flags & QASR_F_CLAMP16) || (e->mode == QASR_EPI_REQUANT_I8 && (e->flags & QASR_F_RELU0) && e->qmin <= 0 &&
+                                                  e->ch1 == nullptr && e->prev == nullptr),
+                 "epilogue: CLAMP16 belongs to a single-operand REQUANT launch with the ReLU-folded clamp [0, qmax]");
   QASR_CHECK_ARG(!(e->flags & QASR_F_BIAS64) || (e->flags & QASR_F_EXACT_F32) || e->mode != QASR_EPI_REQUANT_I8,
                  "epilogue: BIAS64 requires EXACT_F32");
   return QASR_OK;

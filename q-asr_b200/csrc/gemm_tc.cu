@@ -91,6 +91,8 @@ constexpr int kEpiFast = 1, kEpiDual = 2, kEpiPrev = 4, kEpiStage2 = 8, kEpiF32 
 constexpr int kEpiDyn = 32;
 // QASR_F_RANGE_CHECK: integer fast path with the per-element |acc + bias| < 2^22 test (literal recipe beyond)
 constexpr int kEpiRange = 64;
+// QASR_F_CLAMP16: the float path clamps on packed 16-bit lanes (epilogue_f32_pack16)
+constexpr int kEpiC16 = 128;
 
 constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kAllocWarp = kEpiWarps + 2;
 
@@ -118,6 +120,9 @@ __device__ __forceinline__ void finish32(const GemmArgs& g, const EpiConsts& kc,
       uint32_t packed[8];
 #pragma unroll
       for (int w4 = 0; w4 < 8; ++w4) {
+        if (F32 && (EPI & kEpiC16)) {
+          packed[w4] = epilogue_f32_pack16(kc, a0[4 * w4], a0[4 * w4 + 1], a0[4 * w4 + 2], a0[4 * w4 + 3], c0);
+        } else {
         int q[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -134,6 +139,7 @@ __device__ __forceinline__ void finish32(const GemmArgs& g, const EpiConsts& kc,
           }
         }
         packed[w4] = pack4(q[0], q[1], q[2], q[3]);
+        }
       }
       if (tv + 32 > len) {  // length mask / row tail: zero the bytes at t >= len
 #pragma unroll
@@ -444,7 +450,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (tv >= T_out) return;   // warp-uniform: this column group lies past the end of the utterance
       if (stats_mode) { stats32(stats_dual, c0[ms], c1[ms], tv, len, a0, a1, st_lo[ms], st_hi[ms]); return; }
       if ((EPI & kEpiDyn) && warp_lit[ms]) { finish32<0, false>(g, kc, c0[ms], c1[ms], row_ok[ms], cc[ms], b, tv, len, wide_ok, a0, a1); return; }
-      if ((EPI & kEpiF32) || (EPI == kEpiFast && warp_f32[ms])) finish_t(std::true_type{}, ms, b, tv, len, a0, a1);
+      if ((EPI & kEpiF32) || ((EPI & ~kEpiC16) == kEpiFast && warp_f32[ms])) finish_t(std::true_type{}, ms, b, tv, len, a0, a1);
       else finish_t(std::false_type{}, ms, b, tv, len, a0, a1);
     };
 
@@ -745,7 +751,7 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       if (tv >= T_out) return;   // warp-uniform: past the end of the utterance
       if (stats_mode) { stats32(stats_dual, c0, c1, tv, len, a0, a1, st_lo, st_hi); return; }
       if ((EPI & kEpiDyn) && warp_lit) { finish32<0, false>(g, kc, c0, c1, row_ok, cc, b, tv, len, wide_ok, a0, a1); return; }
-      if ((EPI & kEpiF32) || (EPI == kEpiFast && warp_f32)) finish32<EPI, true>(g, kc, c0, c1, row_ok, cc, b, tv, len, wide_ok, a0, a1);
+      if ((EPI & kEpiF32) || ((EPI & ~kEpiC16) == kEpiFast && warp_f32)) finish32<EPI, true>(g, kc, c0, c1, row_ok, cc, b, tv, len, wide_ok, a0, a1);
       else finish32<EPI, false>(g, kc, c0, c1, row_ok, cc, b, tv, len, wide_ok, a0, a1);
     };
     int nt = n_first % n_tiles, b = n_first / n_tiles;
@@ -977,6 +983,7 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
     variant = kEpiFast | (op1 ? kEpiDual : 0) | (epi->prev ? kEpiPrev : 0) | ((epi->flags & QASR_F_STAGE2) ? kEpiStage2 : 0);
   if (fast && (epi->flags & QASR_F_RANGE_CHECK)) variant |= kEpiRange;
   if (fast && (epi->flags & QASR_F_FAST_F32)) variant = kEpiFast | kEpiF32;
+  if ((variant == kEpiFast || variant == (kEpiFast | kEpiF32)) && (epi->flags & QASR_F_CLAMP16)) variant |= kEpiC16;
   // dynamic quantisation: the tables come from the device, the literal flags stay set for the channels whose fast path
   // qasr_dyn_finalize could not prove; everything else runs the integer fast path
   if ((epi->flags & QASR_F_DEVICE_TABLES) && epi->mode == QASR_EPI_REQUANT_I8 && !epi->prev && !(epi->flags & QASR_F_STAGE2))
@@ -1025,7 +1032,7 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
     g.n_step = pairs_per_group;
     const int pair_grid = 2 * pairs_per_group * g.m_groups;
     cudaStream_t pst = (cudaStream_t)stream;
-    static bool pair_attr_set[128][64] = {};
+    static bool pair_attr_set[256][64] = {};
     int pdev = 0;
     QASR_CHECK_CUDA(cudaGetDevice(&pdev));
     const bool pneed = pdev >= 0 && pdev < 64 && !pair_attr_set[variant][pdev];
@@ -1058,6 +1065,8 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
       QASR_PAIR_CASE(75)
       QASR_PAIR_CASE(77)
       QASR_PAIR_CASE(79)
+      QASR_PAIR_CASE(129)
+      QASR_PAIR_CASE(145)
       default:
         qasr_set_error("conv1d_gemm: internal: no pair kernel variant %d", variant);
         return QASR_ERR_INVALID;
@@ -1072,7 +1081,7 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   g.n_step = per_group;
   const int grid = per_group * g.m_groups;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set[128][64] = {};
+  static bool attr_set[256][64] = {};
   int dev = 0;
   QASR_CHECK_CUDA(cudaGetDevice(&dev));
   const bool need_attr = dev >= 0 && dev < 64 && !attr_set[variant][dev];
@@ -1105,6 +1114,8 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
     QASR_GEMM_CASE(75)
     QASR_GEMM_CASE(77)
     QASR_GEMM_CASE(79)
+    QASR_GEMM_CASE(129)
+    QASR_GEMM_CASE(145)
     default:
       qasr_set_error("conv1d_gemm: internal: no kernel variant %d", variant);
       return QASR_ERR_INVALID;

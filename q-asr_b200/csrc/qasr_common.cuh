@@ -228,6 +228,7 @@ struct EpiConsts {
   long long half2;
   double mult2;
   float flo, fhi;           // float fast path: kF32Magic + lo1 / hi1
+  uint32_t hi16;            // QASR_F_CLAMP16: hi1 in both 16-bit halves
 };
 
 __device__ __forceinline__ EpiConsts make_epi_consts(const EpiArgs& ep, bool has1) {
@@ -243,6 +244,7 @@ __device__ __forceinline__ EpiConsts make_epi_consts(const EpiArgs& ep, bool has
   k.mult2 = dyad_mult(ep.m2, ep.e2);
   k.flo = kF32Magic + (float)k.lo1;
   k.fhi = kF32Magic + (float)k.hi1;
+  k.hi16 = ((uint32_t)k.hi1 & 0xffffu) * 0x10001u;
   return k;
 }
 
@@ -284,6 +286,27 @@ __device__ __forceinline__ uint32_t epilogue_f32_bits(const EpiConsts& k, int ac
   const float f = __int_as_float(acc + (c.bias + 0x4B400000)) - kF32Magic;
   const float y = fmaf(f, c.r, kF32Magic);
   return __float_as_uint(fminf(fmaxf(y, k.flo), k.fhi));
+}
+
+// QASR_F_CLAMP16: the float fast path of FOUR outputs with the clamp done on packed 16-bit lanes.  The FMA result's bit
+// pattern is 0x4B400000 + n (n = the requantised integer before the clamp), and the low half of 0x4B400000 is zero, so
+// the low 16 bits ARE n as an int16 whenever |n| < 2^15 -- which the host proves for every reachable accumulator
+// (qasr/plan.py clamp16_ok; the window argument does not apply here: an accumulator beyond the clamp window must still
+// not wrap).  One PRMT gathers two low halves, one VIMNMX.S16x2.RELU clamps both to [0, hi], one PRMT packs four bytes:
+// 5 ALU-pipe instructions per 4 outputs instead of 8 FMNMX + 3 PRMT (the ALU pipe -- IADD / FMNMX / PRMT at 16 lanes per
+// clk per scheduler -- is what paces the pointwise GEMMs' epilogue warps).
+__device__ __forceinline__ uint32_t f32_pair16(int acc0, int acc1, const ChanRegs& c) {
+  const int kb = c.bias + 0x4B400000;
+  const float y0 = fmaf(__int_as_float(acc0 + kb) - kF32Magic, c.r, kF32Magic);
+  const float y1 = fmaf(__int_as_float(acc1 + kb) - kF32Magic, c.r, kF32Magic);
+  return __byte_perm(__float_as_uint(y0), __float_as_uint(y1), 0x5410);
+}
+__device__ __forceinline__ uint32_t epilogue_f32_pack16(const EpiConsts& k, int a0, int a1, int a2, int a3, const ChanRegs& c) {
+  uint32_t p01 = f32_pair16(a0, a1, c), p23 = f32_pair16(a2, a3, c);
+  // the flag is only set for ReLU-folded clamps [0, hi] (validated in api.cu): max(min(x, hi), 0) is ONE instruction
+  p01 = __vimin_s16x2_relu(p01, k.hi16);
+  p23 = __vimin_s16x2_relu(p23, k.hi16);
+  return __byte_perm(p01, p23, 0x6420);
 }
 
 // Same, for an accumulator that was STARTED at 0x4B400000 + bias (the bit pattern of 1.5 * 2^23 + bias): its bits

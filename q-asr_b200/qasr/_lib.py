@@ -18,6 +18,7 @@ F_EXACT_F32, F_EXACT_DYAD, F_B_SIGNED, F_B1_SIGNED, F_BIAS64 = 16, 32, 64, 128, 
 F_FAST_F32 = 512
 F_DEVICE_TABLES = 1024
 F_RANGE_CHECK = 2048
+F_CLAMP16 = 4096
 DYN_MAX_CAND = 4
 
 

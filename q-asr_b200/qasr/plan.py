@@ -141,6 +141,18 @@ def f32_ok_channels(bound, m, e, lo, hi, mult=None):
     return sane & (np.clip(exact, lo, hi) == np.clip(fl, lo, hi).astype(np.int64)).all(axis=1)
 
 
+def clamp16_ok(bounds, mult):
+    """QASR_F_CLAMP16: may the float epilogue clamp on 16-bit lanes?  The kernel takes the low 16 bits of the FMA result
+    fl(f32(z) * r + 1.5 * 2^23) as an int16, which is the rounded product n as long as |n| < 2^15 -- for EVERY accumulator
+    the channel can reach (its worst-case bound: beyond the clamp window n only has to stay saturated, but it must not
+    wrap), with f32(z) = z exactly (|z| < 2^22, so that 0x4B400000 + z is the float 1.5 * 2^23 + z)."""
+    bounds = np.atleast_1d(bounds).astype(F64)
+    mult = np.atleast_1d(mult).astype(F64)
+    if bounds.size == 0 or bounds.max() >= 2 ** 22:
+        return False
+    return bool((bounds * mult + 1.0 < 2 ** 15 - 1).all())
+
+
 def window_bound(m, e, lo, hi):
     """Smallest Z such that the requantised value of every accumulator |z| >= Z lies outside the clamp window [lo, hi]
     for EVERY channel: (Z * m) >> e >= max(|lo|, |hi|) + 2.  All epilogue recipes (the reference's float one, the integer
@@ -257,7 +269,8 @@ class ConvParams:
             self.b_int = bi.astype(F64).astype(np.int64)
         else:
             self.b_int = np.zeros(conv.out_channels, np.int64)
-        self.bound = int((w_abs * in_qabs + np.abs(self.b_int)).max())
+        self.bounds = w_abs * in_qabs + np.abs(self.b_int)          # per output channel: largest |acc + bias|
+        self.bound = int(self.bounds.max())
         self.bias64 = self.bound >= 2 ** 31 - 1
         self.w8, self.packed = p["w8"], p["packed"]
         self.k, self.stride = conv.kernel_size[0], conv.stride[0]
@@ -482,6 +495,9 @@ class FusedPlan:
                     flags |= L.F_FAST_F32          # the kernels derive r32 from (m, e) themselves
                 elif okc.any():
                     kw["f32_mult"] = rf
+                if okc.any() and lo_eff == 0 and relu and clamp16_ok(cp.bounds[okc], rf[okc]) and os.environ.get("QASR_NO_CLAMP16") != "1":
+                    flags |= L.F_CLAMP16
+                    self.stats["clamp16"] = self.stats.get("clamp16", 0) + 1
             self._emit_conv([(base, cp, m, e)], out, flags, fast, kw, lens, "conv->act")
         elif isinstance(base, ResActVal):
             ra = ActInfo(base.act, False)

@@ -138,3 +138,49 @@ def test_neighbouring_float_multipliers_are_proved_too():
             z = np.arange(start, min(start + (1 << 22), 2 ** 24 + 1), dtype=np.int64)
             want = literal(z, s, int(m[i]), int(e[i]), lo, hi, True)
             assert np.array_equal(kernel_float(z, int(m[i]), int(e[i]), lo, hi, mult=rf[i]), want)
+
+
+def kernel_float_clamp16(z, m, e, hi, mult=None):
+    """epilogue_f32_pack16 (QASR_F_CLAMP16): the FMA result's bit pattern, its LOW 16 BITS read as an int16, then
+    max(min(x, hi), 0) on the 16-bit lane (VIMNMX.S16x2.RELU), low byte."""
+    r32 = F32(F64(m) * 2.0 ** -e) if mult is None else F32(mult)
+    bits = (np.int64(MAGIC_BITS) + z).astype(np.int32)
+    f = (bits.view(F32) - MAGIC).astype(F64)
+    y = (f * F64(r32) + F64(MAGIC)).astype(F32)          # one rounding: the product is exact in float64, |sum| < 2^53
+    low = (y.view(np.int32).astype(np.int64) & 0xFFFF).astype(np.uint16).view(np.int16).astype(np.int64)
+    return np.clip(np.minimum(low, hi), 0, None) & 0xFF
+
+
+@pytest.mark.parametrize("case", [(4.4e-3, 255, 2 ** 22 - 1), (3.1e-4, 63, 2 ** 22 - 1), (7.0e-3, 255, 4_000_000), (1.3e-2, 255, 4_000_000)],
+                         ids=lambda c: "r%.0e_%d" % (c[0], c[1]))
+def test_clamp16_equals_the_literal_recipe_up_to_the_worst_case_bound(case):
+    """clamp16_ok(): the 16-bit clamp needs |rint(z r)| < 2^15 over the WHOLE reachable range (no window argument); where
+    it says yes the kernel arithmetic equals the literal recipe on every accumulator up to the bound, where the product
+    passes 2^15 it must say no (and the wrapped lanes indeed differ)."""
+    ratio, hi, bound = case
+    rng = np.random.default_rng(5)
+    m = e = rf = None
+    for _ in range(200):
+        mm, ee = O.batch_frexp(np.array([ratio * rng.uniform(0.9, 1.1)]))
+        mm, ee = int(np.asarray(mm).reshape(-1)[0]), int(np.asarray(ee).reshape(-1)[0])
+        if mm >= 2 ** 31:
+            mm, ee = mm // 2, ee - 1
+        ma, ea = np.array([mm], np.int64), np.array([ee], np.int64)
+        eff = min(bound, P.window_bound(ma, ea, 0, hi))
+        if not P.fast_ok(eff, ma, ea):
+            continue
+        r = P.f32_multipliers(eff, ma, ea, 0, hi)
+        if r[0] != 0:
+            m, e, rf = mm, ee, r[0]
+            break
+    assert m is not None
+    ok = P.clamp16_ok(np.array([bound]), np.array([rf]))
+    assert ok == (bound * float(rf) + 1.0 < 2 ** 15 - 1)
+    s = F32(3e-4)
+    equal = True
+    for start in range(-bound, bound + 1, 1 << 21):
+        z = np.arange(start, min(start + (1 << 21), bound + 1), dtype=np.int64)
+        want = literal(z, s, m, e, 0, hi, True) & 0xFF
+        equal &= bool(np.array_equal(kernel_float_clamp16(z, m, e, hi, mult=rf), want))
+    assert equal == ok
+    assert not P.clamp16_ok(np.array([2 ** 22]), np.array([1e-6]))      # f32(z) = z needs |z| < 2^22

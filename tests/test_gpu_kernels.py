@@ -199,9 +199,11 @@ def test_gemm_requant(case, fast, gemm_engine):
     assert int(out[:, :, T_out:].abs().sum()) == 0  # pitch padding stays zero
 
 
+@pytest.mark.parametrize("clamp16", [False, True], ids=["clamp32", "clamp16"])
 @pytest.mark.parametrize("case", GEMM_CASES[:8], ids=lambda c: c[0])
-def test_gemm_requant_f32(case, gemm_engine):
-    """Float fast path (QASR_F_FAST_F32): single operand, ReLU folded into the clamp, host-proved dyadics."""
+def test_gemm_requant_f32(case, gemm_engine, clamp16):
+    """Float fast path (QASR_F_FAST_F32): single operand, ReLU folded into the clamp, host-proved dyadics; with
+    QASR_F_CLAMP16 the clamp runs on packed 16-bit lanes (host proof: plan.clamp16_ok)."""
     name, B, ci, co, T, k, dil, signed = case
     q, w, bias, pad = _gemm_inputs(case, seed=1)
     acc = O.conv1d_int(q, w, bias, 1, pad, dil, 1)
@@ -216,6 +218,10 @@ def test_gemm_requant_f32(case, gemm_engine):
     wp = ops.pack_weights(torch.from_numpy(w.astype(np.int8)).to(DEV))
     ch = ops.chan_table(r.uniform(1e-5, 1e-3, co).astype(np.float32), bias, m, e, DEV)
     flags = L.F_RELU0 | L.F_MASK | L.F_FAST_F32 | (L.F_B_SIGNED if signed else 0)
+    if clamp16:
+        from qasr import plan as P
+        assert P.clamp16_ok(np.full(co, bound), (m.astype(np.float64) * np.exp2(-e.astype(np.float64))).astype(np.float32))
+        flags |= L.F_CLAMP16
     ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=flags, qmin=-64, qmax=63, out_lens=torch.from_numpy(lens).to(DEV))
     out = ops.alloc_codes(B, co, T_out, DEV)
     ops.conv_gemm(ops.gemm_operand(x, T, wp, ci, k, 1, dil, pad), None, out, B, co, T_out, ep)
@@ -275,6 +281,13 @@ def test_f32_mult_table_mixed(dw_engine):
     ops.conv_gemm(ops.gemm_operand(to_codes_tensor(q2, False), T, wp, ci, 1), None, out2, B, Cn, T, ep2)
     torch.cuda.synchronize()
     assert np.array_equal(from_codes_tensor(out2, T, signed=False), want2)
+    # and with the 16-bit clamp on the float warps (QASR_F_CLAMP16)
+    assert P.clamp16_ok(np.full(int(ok2.sum()), bound2), rf2[ok2])
+    ep3 = ops.make_epilogue(L.EPI_REQUANT_I8, ch2, flags=L.F_RELU0 | L.F_CLAMP16, qmin=-64, qmax=63, f32_mult=torch.from_numpy(rf2).to(DEV))
+    out3 = ops.alloc_codes(B, Cn, T, DEV)
+    ops.conv_gemm(ops.gemm_operand(to_codes_tensor(q2, False), T, wp, ci, 1), None, out3, B, Cn, T, ep3)
+    torch.cuda.synchronize()
+    assert np.array_equal(from_codes_tensor(out3, T, signed=False), want2)
 
 
 @pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
