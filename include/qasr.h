@@ -119,6 +119,11 @@ typedef struct {
                                  window), and the clamp is the ReLU-folded [0, qmax] (RELU0 set, qmin <= 0), so kernels
                                  may clamp two outputs at a time on packed 16-bit lanes (one VIMNMX.S16x2.RELU) instead
                                  of two FMNMX per output.  A hint: kernels without a 16-bit epilogue ignore it         */
+#define QASR_F_STAGE2_16 8192 /* with STAGE2 + RELU1 on the integer fast path: the host checked for EVERY code q in
+                                 [0, qmax] (the first clamp with the block ReLU folded in; qmax <= 127) that
+                                 (q * M16 + 2^15) >> 16, M16 = rne(m2 * 2^(16 - e2)), equals rne(q * m2 / 2^e2), and
+                                 qmin2 <= 0 <= qmax2 < 2^15: kernels may run the second stage in 16-bit fixed point, two
+                                 outputs per clamp.  A hint: kernels without that epilogue ignore it                   */
 
 typedef struct {
   int32_t mode;              /* QASR_EPI_*                                               */

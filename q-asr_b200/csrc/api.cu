@@ -117,6 +117,11 @@ int qasr_validate_epilogue(const qasr_epilogue* e, bool allow_second_operand) {
   QASR_CHECK_ARG(!(e->flags & QASR_F_CLAMP16) || (e->mode == QASR_EPI_REQUANT_I8 && (e->flags & QASR_F_RELU0) && e->qmin <= 0 &&
                                                   e->ch1 == nullptr && e->prev == nullptr),
                  "epilogue: CLAMP16 belongs to a single-operand REQUANT launch with the ReLU-folded clamp [0, qmax]");
+  QASR_CHECK_ARG(!(e->flags & QASR_F_STAGE2_16) ||
+                     (e->mode == QASR_EPI_REQUANT_I8 && (e->flags & QASR_F_STAGE2) && (e->flags & QASR_F_RELU1) && e->qmin <= 0 &&
+                      e->qmax <= 127 && e->qmin2 <= 0 && e->qmax2 >= 0 && e->e2 >= 17 &&
+                      !(e->flags & (QASR_F_EXACT_F32 | QASR_F_EXACT_DYAD | QASR_F_BIAS64))),
+                 "epilogue: STAGE2_16 belongs to a fast-path STAGE2 + RELU1 launch with qmax <= 127 and e2 >= 17");
   QASR_CHECK_ARG(!(e->flags & QASR_F_BIAS64) || (e->flags & QASR_F_EXACT_F32) || e->mode != QASR_EPI_REQUANT_I8,
                  "epilogue: BIAS64 requires EXACT_F32");
   return QASR_OK;

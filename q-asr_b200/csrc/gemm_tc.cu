@@ -93,6 +93,8 @@ constexpr int kEpiDyn = 32;
 constexpr int kEpiRange = 64;
 // QASR_F_CLAMP16: the float path clamps on packed 16-bit lanes (epilogue_f32_pack16)
 constexpr int kEpiC16 = 128;
+// QASR_F_STAGE2_16: second requantisation stage in 16-bit fixed point (epilogue_fast_s16x4)
+constexpr int kEpiS16 = 256;
 
 constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kAllocWarp = kEpiWarps + 2;
 
@@ -122,6 +124,9 @@ __device__ __forceinline__ void finish32(const GemmArgs& g, const EpiConsts& kc,
       for (int w4 = 0; w4 < 8; ++w4) {
         if (F32 && (EPI & kEpiC16)) {
           packed[w4] = epilogue_f32_pack16(kc, a0[4 * w4], a0[4 * w4 + 1], a0[4 * w4 + 2], a0[4 * w4 + 3], c0);
+        } else if ((EPI & kEpiFast) && (EPI & kEpiS16)) {
+          packed[w4] = epilogue_fast_s16x4<(EPI & kEpiDual) != 0, (EPI & kEpiPrev) != 0, (EPI & kEpiRange) != 0>(
+              g.ep, kc, &a0[4 * w4], c0, &a1[(EPI & kEpiDual) ? 4 * w4 : 0], c1, pw[w4]);
         } else {
         int q[4];
 #pragma unroll
@@ -984,6 +989,7 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   if (fast && (epi->flags & QASR_F_RANGE_CHECK)) variant |= kEpiRange;
   if (fast && (epi->flags & QASR_F_FAST_F32)) variant = kEpiFast | kEpiF32;
   if ((variant == kEpiFast || variant == (kEpiFast | kEpiF32)) && (epi->flags & QASR_F_CLAMP16)) variant |= kEpiC16;
+  if ((variant & ~kEpiRange) == (kEpiFast | kEpiDual | kEpiStage2) && (epi->flags & QASR_F_STAGE2_16)) variant |= kEpiS16;
   // dynamic quantisation: the tables come from the device, the literal flags stay set for the channels whose fast path
   // qasr_dyn_finalize could not prove; everything else runs the integer fast path
   if ((epi->flags & QASR_F_DEVICE_TABLES) && epi->mode == QASR_EPI_REQUANT_I8 && !epi->prev && !(epi->flags & QASR_F_STAGE2))
@@ -1032,7 +1038,7 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
     g.n_step = pairs_per_group;
     const int pair_grid = 2 * pairs_per_group * g.m_groups;
     cudaStream_t pst = (cudaStream_t)stream;
-    static bool pair_attr_set[256][64] = {};
+    static bool pair_attr_set[512][64] = {};
     int pdev = 0;
     QASR_CHECK_CUDA(cudaGetDevice(&pdev));
     const bool pneed = pdev >= 0 && pdev < 64 && !pair_attr_set[variant][pdev];
@@ -1067,6 +1073,8 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
       QASR_PAIR_CASE(79)
       QASR_PAIR_CASE(129)
       QASR_PAIR_CASE(145)
+      QASR_PAIR_CASE(267)
+      QASR_PAIR_CASE(331)
       default:
         qasr_set_error("conv1d_gemm: internal: no pair kernel variant %d", variant);
         return QASR_ERR_INVALID;
@@ -1081,7 +1089,7 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   g.n_step = per_group;
   const int grid = per_group * g.m_groups;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set[256][64] = {};
+  static bool attr_set[512][64] = {};
   int dev = 0;
   QASR_CHECK_CUDA(cudaGetDevice(&dev));
   const bool need_attr = dev >= 0 && dev < 64 && !attr_set[variant][dev];
@@ -1116,6 +1124,8 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
     QASR_GEMM_CASE(79)
     QASR_GEMM_CASE(129)
     QASR_GEMM_CASE(145)
+    QASR_GEMM_CASE(267)
+    QASR_GEMM_CASE(331)
     default:
       qasr_set_error("conv1d_gemm: internal: no kernel variant %d", variant);
       return QASR_ERR_INVALID;

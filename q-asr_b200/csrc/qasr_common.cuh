@@ -229,6 +229,8 @@ struct EpiConsts {
   double mult2;
   float flo, fhi;           // float fast path: kF32Magic + lo1 / hi1
   uint32_t hi16;            // QASR_F_CLAMP16: hi1 in both 16-bit halves
+  int m16;                  // QASR_F_STAGE2_16: rne(m2 * 2^(16 - e2))
+  uint32_t hi16_2;          // QASR_F_STAGE2_16: hi2 in both 16-bit halves
 };
 
 __device__ __forceinline__ EpiConsts make_epi_consts(const EpiArgs& ep, bool has1) {
@@ -245,6 +247,8 @@ __device__ __forceinline__ EpiConsts make_epi_consts(const EpiArgs& ep, bool has
   k.flo = kF32Magic + (float)k.lo1;
   k.fhi = kF32Magic + (float)k.hi1;
   k.hi16 = ((uint32_t)k.hi1 & 0xffffu) * 0x10001u;
+  k.m16 = (ep.e2 >= 17 && ep.e2 <= 62) ? (int)(((long long)ep.m2 + (1ll << (ep.e2 - 17))) >> (ep.e2 - 16)) : 0;
+  k.hi16_2 = ((uint32_t)k.hi2 & 0xffffu) * 0x10001u;
   return k;
 }
 
@@ -272,6 +276,27 @@ __device__ __forceinline__ int epilogue_fast(const EpiArgs& ep, const EpiConsts&
     q = min(max(q, k.lo2), k.hi2);
   }
   return q;
+}
+
+// QASR_F_STAGE2_16: the second requantisation of FOUR outputs in 16-bit fixed point.  After the first clamp and the block
+// ReLU the code q lies in [0, hi1] (hi1 <= 127), so rne(q * m2 / 2^e2) has at most 128 arguments: the host checks
+// EXHAUSTIVELY (qasr/plan.py stage2_16_ok) that (q * M16 + 2^15) >> 16 with M16 = rne(m2 * 2^(16 - e2)) gives the same
+// value for every one of them.  One IMAD per output on the FMA pipe; the shift by 16 and the pairing are ONE PRMT per two
+// outputs (the high halves), the upper clamp one VIMNMX.S16x2 per two outputs (q2 >= 0 already): 1.25 ALU-pipe
+// instructions per output instead of IMAD.WIDE + 64-bit shift + 2 VIMNMX + 0.75 PRMT.
+template <bool DUAL, bool PREV, bool RC>
+__device__ __forceinline__ uint32_t epilogue_fast_s16x4(const EpiArgs& ep, const EpiConsts& k, const int* a0, const ChanRegs& c0,
+                                                        const int* a1, const ChanRegs& c1, uint32_t prev4) {
+  int p[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int prev = PREV ? (int)(int8_t)(prev4 >> (8 * i)) : 0;
+    const int q = epilogue_fast<DUAL, PREV, false, RC>(ep, k, a0[i], c0, DUAL ? a1[i] : 0, c1, prev);   // first clamp: [0, hi1]
+    p[i] = q * k.m16 + 0x8000;
+  }
+  const uint32_t q01 = __vmins2(__byte_perm((uint32_t)p[0], (uint32_t)p[1], 0x7632), k.hi16_2);
+  const uint32_t q23 = __vmins2(__byte_perm((uint32_t)p[2], (uint32_t)p[3], 0x7632), k.hi16_2);
+  return __byte_perm(q01, q23, 0x6420);
 }
 
 // Float fast path (QASR_F_FAST_F32, single operand, single stage): I2F + FFMA + 2 FMNMX on the 128-lane FP32

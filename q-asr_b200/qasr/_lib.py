@@ -19,6 +19,7 @@ F_FAST_F32 = 512
 F_DEVICE_TABLES = 1024
 F_RANGE_CHECK = 2048
 F_CLAMP16 = 4096
+F_STAGE2_16 = 8192
 DYN_MAX_CAND = 4
 
 

@@ -153,6 +153,20 @@ def clamp16_ok(bounds, mult):
     return bool((bounds * mult + 1.0 < 2 ** 15 - 1).all())
 
 
+def stage2_16_ok(hi1, m2, e2, lo2, hi2):
+    """QASR_F_STAGE2_16: may the second requantisation run in 16-bit fixed point?  Its argument is a code q of [0, hi1]
+    (first clamp with the block ReLU folded in), so the check is exhaustive: (q * M16 + 2^15) >> 16 with
+    M16 = rne(m2 * 2^(16 - e2)) must equal (q * m2 + 2^(e2-1)) >> e2 -- what stage2_fast_ok() proved equal to the
+    reference's rne(q * m2 / 2^e2) -- for every q, and everything must fit the kernel's 32- / 16-bit lanes."""
+    m2, e2 = int(np.atleast_1d(m2)[0]), int(np.atleast_1d(e2)[0])
+    if not (0 <= hi1 <= 127 and 17 <= e2 <= 62 and m2 > 0 and lo2 <= 0 <= hi2 < 2 ** 15):
+        return False
+    m16 = (m2 + (1 << (e2 - 17))) >> (e2 - 16)
+    if hi1 * m16 + 0x8000 >= 2 ** 31:
+        return False
+    return all(((q * m16 + 0x8000) >> 16) == ((q * m2 + (1 << (e2 - 1))) >> e2) for q in range(hi1 + 1))
+
+
 def window_bound(m, e, lo, hi):
     """Smallest Z such that the requantised value of every accumulator |z| >= Z lies outside the clamp window [lo, hi]
     for EVERY channel: (Z * m) >> e >= max(|lo|, |hi|) + 2.  All epilogue recipes (the reference's float one, the integer
@@ -509,6 +523,9 @@ class FusedPlan:
                 flags |= L.F_RELU1
             flags |= L.F_STAGE2
             fast2 = stage2_fast_ok(ra.n + 1, m2, e2)
+            if (fast2 and relu and stage2_16_ok(ra.n, m2, e2, qmin, qmax) and os.environ.get("QASR_NO_STAGE2_16") != "1"):
+                flags |= L.F_STAGE2_16
+                self.stats["stage2_16"] = self.stats.get("stage2_16", 0) + 1
             self._emit_resact(base, ra, out, flags, fast2, stage2, lens)
         else:
             raise NotImplementedError(type(base))
@@ -572,6 +589,7 @@ class FusedPlan:
         if len(operands) > 1 and operands[1][0].src.signed:
             flags |= L.F_B1_SIGNED
         if not fast:
+            flags &= ~(L.F_STAGE2_16 | L.F_CLAMP16)      # hints of the fast paths
             flags |= L.F_EXACT_F32 | L.F_EXACT_DYAD
             if any(cp.bias64 for (_, cp, _, _) in operands):
                 flags |= L.F_BIAS64

@@ -184,3 +184,33 @@ def test_clamp16_equals_the_literal_recipe_up_to_the_worst_case_bound(case):
         equal &= bool(np.array_equal(kernel_float_clamp16(z, m, e, hi, mult=rf), want))
     assert equal == ok
     assert not P.clamp16_ok(np.array([2 ** 22]), np.array([1e-6]))      # f32(z) = z needs |z| < 2^22
+
+
+def test_stage2_16_equals_the_literal_second_requantisation():
+    """stage2_16_ok(): whenever it says yes, the kernel's 16-bit fixed-point stage ((q * M16 + 2^15) >> 16, upper clamp) equals
+    the reference's clamp(rne(q * m2 / 2^e2)) (quant_utils.py:195-214, float64) on every code q of [0, hi1]; it refuses
+    ratios whose rounding it cannot reproduce, wide codes and exponents below 17."""
+    rng = np.random.default_rng(8)
+    yes = no = 0
+    for hi1, hi2 in ((31, 31), (127, 127), (127, 255), (63, 63)):
+        for _ in range(300):
+            m2, e2 = O.batch_frexp(np.array([rng.uniform(0.1, 4.0)]))
+            m2, e2 = int(np.asarray(m2).reshape(-1)[0]), int(np.asarray(e2).reshape(-1)[0])
+            if m2 >= 2 ** 31:
+                m2, e2 = m2 // 2, e2 - 1
+            if not P.stage2_fast_ok(hi1 + 1, np.array([m2]), np.array([e2])):
+                continue
+            q = np.arange(hi1 + 1, dtype=np.int64)
+            want = np.clip(np.round(q.astype(F64) * F64(m2) / F64(2.0 ** e2)), -hi2 - 1, hi2).astype(np.int64)
+            m16 = (m2 + (1 << (e2 - 17))) >> (e2 - 16)
+            got = np.minimum((q * m16 + 0x8000) >> 16, hi2)
+            if P.stage2_16_ok(hi1, m2, e2, -hi2 - 1, hi2):
+                yes += 1
+                assert np.array_equal(got, want)
+            else:
+                no += 1
+                assert not np.array_equal((q * m16 + 0x8000) >> 16, np.round(q.astype(F64) * F64(m2) / F64(2.0 ** e2)).astype(np.int64))
+    assert yes > 500 and no > 0
+    assert not P.stage2_16_ok(255, 1 << 30, 31, -256, 255)       # codes wider than 7 bits
+    assert not P.stage2_16_ok(127, 1 << 15, 16, -128, 127)       # e2 < 17
+    assert not P.stage2_16_ok(127, 1 << 30, 31, 1, 127)          # lower clamp above 0

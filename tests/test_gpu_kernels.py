@@ -326,6 +326,48 @@ def test_gemm_dual_residual(fast, gemm_engine):
     assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
 
 
+@pytest.mark.parametrize("range_check", [False, True], ids=["plain", "range_check"])
+def test_gemm_dual_stage2_16(gemm_engine, range_check):
+    """QASR_F_STAGE2_16: the second requantisation of a two-operand res_act launch in 16-bit fixed point
+    ((q * M16 + 2^15) >> 16, exhaustively checked on the host over q in [0, qmax]: plan.stage2_16_ok)."""
+    from qasr import plan as P
+    B, ci0, ci1, co, T = 3, 256, 128, 256, 333
+    r = rng(33)
+    q0 = r.integers(-64, 64, (B, ci0, T))
+    q1 = r.integers(0, 128, (B, ci1, T))
+    w0 = r.integers(-127, 127, (co, ci0, 1))
+    w1 = r.integers(-127, 127, (co, ci1, 1))
+    b0 = r.integers(-30000, 30000, co)
+    b1 = r.integers(-30000, 30000, co)
+    acc0 = O.conv1d_int(q0, w0, b0, 1, 0, 1, 1)
+    acc1 = O.conv1d_int(q1, w1, b1, 1, 0, 1, 1)
+    m0, e0 = norm_me(*rand_dyadic(r, co, 1e-5, 2e-4))
+    m1, e1 = norm_me(*rand_dyadic(r, co, 1e-5, 2e-4))
+    lens = r.integers(T // 2, T + 1, B).astype(np.int32)
+    proved = 0
+    for ratio in (1.9, 0.7307, 0.3111, 2.01, 1.0):
+        m2, e2 = norm_me(*O.batch_frexp(np.array([ratio])))
+        if not (P.stage2_fast_ok(128, m2, e2) and P.stage2_16_ok(127, m2, e2, -256, 255)):
+            continue
+        proved += 1
+        want = expected_requant(acc0, m0, e0, -128, 127, acc1=acc1, m1=m1, e1=e1, relu1=True,
+                                stage2=(m2[0], e2[0], -256, 255), lens=lens)
+        x0, x1 = to_codes_tensor(q0, True), to_codes_tensor(q1, False)
+        wp0 = ops.pack_weights(torch.from_numpy(w0.astype(np.int8)).to(DEV))
+        wp1 = ops.pack_weights(torch.from_numpy(w1.astype(np.int8)).to(DEV))
+        one = np.full(co, 1e-4, np.float32)
+        ch0, ch1 = ops.chan_table(one, b0, m0, e0, DEV), ops.chan_table(one, b1, m1, e1, DEV)
+        flags = L.F_RELU1 | L.F_STAGE2 | L.F_STAGE2_16 | L.F_B_SIGNED | L.F_MASK | (L.F_RANGE_CHECK if range_check else 0)
+        ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch0, flags=flags, ch1=ch1, qmin=-128, qmax=127, m2=m2[0], e2=e2[0],
+                               qmin2=-256, qmax2=255, out_lens=torch.from_numpy(lens).to(DEV))
+        out = ops.alloc_codes(B, co, T, DEV)
+        ops.conv_gemm(ops.gemm_operand(x0, T, wp0, ci0, 1), ops.gemm_operand(x1, T, wp1, ci1, 1), out, B, co, T, ep)
+        torch.cuda.synchronize()
+        got = from_codes_tensor(out, T, signed=False)
+        assert np.array_equal(got, want), "ratio %g: mismatches: %d / %d" % (ratio, (got != want).sum(), want.size)
+    assert proved >= 2
+
+
 NTC_CASES = [
     # name, B, C_in, C_out, T, k, stride, dil, signed
     ("ntc_k11_s2_c64", 2, 64, 256, 301, 11, 2, 1, True),
