@@ -487,14 +487,19 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int ms = 0; ms < 2; ++ms) {
           if (ms >= MT) break;
           int a0[32], a1[32];
+          // the fast variants know at compile time whether there is a second operand (a runtime choice between the
+          // two register arrays costs 32 moves per chunk)
+          const bool two = EPI != 0 ? (EPI & kEpiDual) != 0 : nseg > 1;
           tmem_ld32(taddr + (uint32_t)(ms * nseg * BN), a0);
-          if (nseg > 1) tmem_ld32(taddr + (uint32_t)(ms * nseg * BN + BN), a1);
+          if (two) tmem_ld32(taddr + (uint32_t)(ms * nseg * BN + BN), a1);
           tmem_ld_wait();
           if (ms == MT - 1) {
             tc_fence_before();
             mbar_arrive_warp(tempty_bar(as));
           }
-          finish(ms, b, tv, len, a0, nseg > 1 ? a1 : a0);
+          if (EPI != 0 && (EPI & kEpiDual)) finish(ms, b, tv, len, a0, a1);
+          else if (EPI != 0) finish(ms, b, tv, len, a0, a0);
+          else finish(ms, b, tv, len, a0, nseg > 1 ? a1 : a0);
         }
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
@@ -784,15 +789,18 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       } else {
         for (int h = 0; h < chunks; ++h) {
           int a0[32], a1[32];
+          const bool two = EPI != 0 ? (EPI & kEpiDual) != 0 : nseg > 1;
           tmem_ld32(taddr + (uint32_t)(h * 32), a0);
-          if (nseg > 1) tmem_ld32(taddr + (uint32_t)(bn + h * 32), a1);
+          if (two) tmem_ld32(taddr + (uint32_t)(bn + h * 32), a1);
           tmem_ld_wait();
           if (h == chunks - 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(ltempty0 + 8u * as);
           }
-          finish(b, tv + h * 32, len, a0, nseg > 1 ? a1 : a0);
+          if (EPI != 0 && (EPI & kEpiDual)) finish(b, tv + h * 32, len, a0, a1);
+          else if (EPI != 0) finish(b, tv + h * 32, len, a0, a0);
+          else finish(b, tv + h * 32, len, a0, nseg > 1 ? a1 : a0);
         }
       }
       if (++as == nbuf) { as = 0; aphase ^= 1u; }

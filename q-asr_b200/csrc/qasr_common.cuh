@@ -291,7 +291,14 @@ __device__ __forceinline__ uint32_t epilogue_fast_s16x4(const EpiArgs& ep, const
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int prev = PREV ? (int)(int8_t)(prev4 >> (8 * i)) : 0;
-    const int q = epilogue_fast<DUAL, PREV, false, RC>(ep, k, a0[i], c0, DUAL ? a1[i] : 0, c1, prev);   // first clamp: [0, hi1]
+    int q;   // first clamp, [0, hi1] by the flag's contract: add + min + ReLU are ONE VIADDMNMX.RELU
+    if (RC) {
+      q = epilogue_fast<DUAL, PREV, false, true>(ep, k, a0[i], c0, DUAL ? a1[i] : 0, c1, prev);
+    } else {
+      int o = contrib_fast(a0[i], c0);
+      if (PREV) o += prev;
+      q = DUAL ? __viaddmin_s32_relu(o, contrib_fast(a1[i], c1), k.hi1) : __vimin_s32_relu(o, k.hi1);
+    }
     p[i] = q * k.m16 + 0x8000;
   }
   const uint32_t q01 = __vmins2(__byte_perm((uint32_t)p[0], (uint32_t)p[1], 0x7632), k.hi16_2);
