@@ -64,6 +64,8 @@ struct GemmArgs {
   int MT;            // M tiles per CTA (1 or 2)
   int m_groups;      // m_tiles / MT
   int n_total;       // B * n_tiles
+  int n_div, n_split; // tile walk: indices below n_split are the FULL time tiles (b = i / n_div, nt = i % n_div), the rest the
+                     // utterances' partial last tiles (b = i - n_split, nt = n_div): the cheap tiles fill the last round
   int n_step;        // CTAs per M group (= stride of the n walk)
   int a_resident;    // weights of the CTA's M group stay in shared memory
   int a_slabs;       // 16 KB weight slabs per M tile (all segments)
@@ -303,19 +305,21 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncwarp();
     pdl_wait();   // weights above are constants of the plan; activations below come from the previous kernel
     if (leader) qasr_stamp_begin(g.stamp);
-    const int n_total = g.n_total, n_step = g.n_step, n_tiles = g.n_tiles, nseg = g.nseg, stages = g.stages;
+    const int n_total = g.n_total, n_step = g.n_step, nseg = g.nseg, stages = g.stages;
     const int a_res = g.a_resident, MT = g.MT;
     const uint32_t stage_bytes = g.stage_bytes;
     int stage = 0;
     uint32_t phase = 0;
     // (time tile, utterance) of the walk carried incrementally: no division on the per-round path
-    const int step_nt = n_step % n_tiles, step_b = n_step / n_tiles;
-    int nt = n_first % n_tiles, b = n_first / n_tiles;
+    const int n_div = g.n_div, n_split = g.n_split;
+    const int step_nt = n_step % n_div, step_b = n_step / n_div;
+    int wnt = n_first % n_div, wb = n_first / n_div;
     const int seg_taps[2] = {g.seg[0].taps, g.seg[1].taps}, seg_cblocks[2] = {g.seg[0].cblocks, g.seg[1].cblocks};
     const int seg_tstep[2] = {BN * g.seg[0].stride, BN * g.seg[1].stride}, seg_dil[2] = {g.seg[0].dil, g.seg[1].dil};
     const int seg_pad[2] = {g.seg[0].pad, g.seg[1].pad};
-    for (int nidx = n_first; nidx < n_total; nidx += n_step, nt += step_nt, b += step_b) {
-      if (nt >= n_tiles) { nt -= n_tiles; ++b; }
+    for (int nidx = n_first; nidx < n_total; nidx += n_step, wnt += step_nt, wb += step_b) {
+      if (wnt >= n_div) { wnt -= n_div; ++wb; }
+      const int nt = nidx >= n_split ? n_div : wnt, b = nidx >= n_split ? nidx - n_split : wb;
 #pragma unroll
       for (int sg = 0; sg < 2; ++sg) {
         if (sg >= nseg) break;
@@ -361,14 +365,15 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_wait(afull_bar, 0u);
       tc_fence_after();
     }
-    const int n_tiles_m = g.n_tiles, step_nt = n_step % n_tiles_m, T_out_m = g.T_out;
-    int nt_mma = n_first % n_tiles_m;
+    const int n_div = g.n_div, n_split = g.n_split, step_nt = n_step % n_div, T_out_m = g.T_out;
+    int wnt = n_first % n_div;
     // per-segment constants live in registers: the kernel-parameter bank costs a dependent load per use
     const int seg_slabs[2] = {g.seg[0].taps * g.seg[0].cblocks, g.seg[1].taps * g.seg[1].cblocks};
     const uint32_t seg_idesc[2] = {g.seg[0].idesc & ~(0x3Fu << 17), g.seg[1].idesc & ~(0x3Fu << 17)};
     const uint32_t seg_a_lo[2] = {a_region_lo + (uint32_t)g.seg[0].slab0 * kSlabLo, a_region_lo + (uint32_t)g.seg[1].slab0 * kSlabLo};
-    for (int nidx = n_first; nidx < n_total; nidx += n_step, nt_mma += step_nt) {
-      if (nt_mma >= n_tiles_m) nt_mma -= n_tiles_m;
+    for (int nidx = n_first; nidx < n_total; nidx += n_step, wnt += step_nt) {
+      if (wnt >= n_div) wnt -= n_div;
+      const int nt_mma = nidx >= n_split ? n_div : wnt;
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       tc_fence_after();
       const uint32_t d_round = tmem_base + (uint32_t)as * acc_per_stage;
@@ -441,7 +446,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int as = 0;
     uint32_t aphase = 0;
     pdl_wait();   // out / prev / out_lens belong to the stream order
-    const int MT = g.MT, nseg = g.nseg, n_tiles = g.n_tiles, T_out = g.T_out;
+    const int MT = g.MT, nseg = g.nseg, T_out = g.T_out;
     const bool masked = g.ep.flags & QASR_F_MASK;
     const bool wide_ok = (reinterpret_cast<uintptr_t>(g.out) & 31) == 0 && (g.out_ld & 31) == 0;   // 32-byte aligned rows
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cgroup * 32);
@@ -459,10 +464,12 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       else finish_t(std::false_type{}, ms, b, tv, len, a0, a1);
     };
 
-    const int n_total = g.n_total, n_step = g.n_step, step_nt = n_step % n_tiles, step_b = n_step / n_tiles;
-    int nt = n_first % n_tiles, b = n_first / n_tiles;
-    for (int nidx = n_first; nidx < n_total; nidx += n_step, nt += step_nt, b += step_b) {
-      if (nt >= n_tiles) { nt -= n_tiles; ++b; }
+    const int n_total = g.n_total, n_step = g.n_step, n_div = g.n_div, n_split = g.n_split;
+    const int step_nt = n_step % n_div, step_b = n_step / n_div;
+    int wnt = n_first % n_div, wb = n_first / n_div;
+    for (int nidx = n_first; nidx < n_total; nidx += n_step, wnt += step_nt, wb += step_b) {
+      if (wnt >= n_div) { wnt -= n_div; ++wb; }
+      const int nt = nidx >= n_split ? n_div : wnt, b = nidx >= n_split ? nidx - n_split : wb;
       const int len = masked ? min(g.ep.out_lens[b], T_out) : T_out;
       const int tv = nt * BN + cgroup * 32;   // first frame of this thread's 32 columns
       const uint32_t taddr = lane_base + (uint32_t)as * acc_per_stage;
@@ -626,8 +633,9 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int n_total = g.n_total, n_step = g.n_step, n_tiles = g.n_tiles, nseg = g.nseg, stages = g.stages, T_out = g.T_out;
-  const int step_nt = n_step % n_tiles, step_b = n_step / n_tiles;
+  const int n_total = g.n_total, n_step = g.n_step, nseg = g.nseg, stages = g.stages, T_out = g.T_out;
+  const int n_div = g.n_div, n_split = g.n_split;
+  const int step_nt = n_step % n_div, step_b = n_step / n_div;
   const int nbuf = min(4, (int)kTmemCols / (nseg * bn));   // accumulator buffers that fit the 512 TMEM columns
 
   if (warp == kProducerWarp) {
@@ -651,11 +659,12 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t stage_bytes = g.stage_bytes;   // 16 KB (128-frame boxes) or 8 KB (64-frame boxes, bn = 128)
-    int nt = n_first % n_tiles, b = n_first / n_tiles;
+    int wnt = n_first % n_div, wb = n_first / n_div;
     const int seg_taps[2] = {g.seg[0].taps, g.seg[1].taps}, seg_cblocks[2] = {g.seg[0].cblocks, g.seg[1].cblocks};
     const int seg_dil[2] = {g.seg[0].dil, g.seg[1].dil}, seg_pad[2] = {g.seg[0].pad, g.seg[1].pad};
-    for (int nidx = n_first; nidx < n_total; nidx += n_step, nt += step_nt, b += step_b) {
-      if (nt >= n_tiles) { nt -= n_tiles; ++b; }
+    for (int nidx = n_first; nidx < n_total; nidx += n_step, wnt += step_nt, wb += step_b) {
+      if (wnt >= n_div) { wnt -= n_div; ++wb; }
+      const int nt = nidx >= n_split ? n_div : wnt, b = nidx >= n_split ? nidx - n_split : wb;
       // frames of this tile, rounded up to 32: the pair splits them in halves of a multiple of 16 (TMA alignment)
       const int cols = min(bn, ((T_out - nt * bn + 31) >> 5) << 5);
       const int t_half = nt * bn + (int)rank * (cols >> 1);
@@ -694,15 +703,16 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     uint32_t aphase = 0;
     mbar_wait(afull_bar, 0u);   // both CTAs' weights have landed
     tc_fence_after();
-    int nt = n_first % n_tiles;
+    int wnt = n_first % n_div;
     const int seg_slabs[2] = {g.seg[0].taps * g.seg[0].cblocks, g.seg[1].taps * g.seg[1].cblocks};
     // instruction descriptor: the operand's own formats, N = this tile's frames, M = 256 across the pair
     const uint32_t fmt_mask = ~((0x3Fu << 17) | (0x1Fu << 24));
     const uint32_t seg_idesc[2] = {(g.seg[0].idesc & fmt_mask) | ((uint32_t)(256 >> 4) << 24),
                                    (g.seg[1].idesc & fmt_mask) | ((uint32_t)(256 >> 4) << 24)};
     const uint32_t seg_a_lo[2] = {a_region_lo + (uint32_t)g.seg[0].slab0 * kSlabLo, a_region_lo + (uint32_t)g.seg[1].slab0 * kSlabLo};
-    for (int nidx = n_first; nidx < n_total; nidx += n_step, nt += step_nt) {
-      if (nt >= n_tiles) nt -= n_tiles;
+    for (int nidx = n_first; nidx < n_total; nidx += n_step, wnt += step_nt) {
+      if (wnt >= n_div) wnt -= n_div;
+      const int nt = nidx >= n_split ? n_div : wnt;
       const int cols = min(bn, ((T_out - nt * bn + 31) >> 5) << 5);
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       tc_fence_after();
@@ -764,9 +774,10 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       if ((EPI & kEpiF32) || ((EPI & ~kEpiC16) == kEpiFast && warp_f32)) finish32<EPI, true>(g, kc, c0, c1, row_ok, cc, b, tv, len, wide_ok, a0, a1);
       else finish32<EPI, false>(g, kc, c0, c1, row_ok, cc, b, tv, len, wide_ok, a0, a1);
     };
-    int nt = n_first % n_tiles, b = n_first / n_tiles;
-    for (int nidx = n_first; nidx < n_total; nidx += n_step, nt += step_nt, b += step_b) {
-      if (nt >= n_tiles) { nt -= n_tiles; ++b; }
+    int wnt = n_first % n_div, wb = n_first / n_div;
+    for (int nidx = n_first; nidx < n_total; nidx += n_step, wnt += step_nt, wb += step_b) {
+      if (wnt >= n_div) { wnt -= n_div; ++wb; }
+      const int nt = nidx >= n_split ? n_div : wnt, b = nidx >= n_split ? nidx - n_split : wb;
       const int len = masked ? min(g.ep.out_lens[b], T_out) : T_out;
       const int tv = nt * bn + cgroup * chunks * 32;   // first frame of this warp's columns
       const uint32_t taddr = lane_base + (uint32_t)as * acc_per_stage;
@@ -814,6 +825,21 @@ gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   if (threadIdx.x == 0) qasr_stamp_end(g.stamp);
   if (warp == kAllocWarp) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// Order of the (utterance, time tile) walk: all FULL tiles first, the utterances' partial last tiles after them.  With 64
+// utterances x 7 tiles of 128 frames (800 frames: 6 full + one of 32) the 448 tiles leave 4 for a last round on 148 / 74 /
+// 37 CTAs per M group; in utterance-major order those were full tiles (4 CTAs x 512 frames against 384 for the rest), now
+// they are 32-frame ones.  Bring-up knob 18 = 0 keeps the utterance-major order.
+static void set_tile_walk(GemmArgs& g, int bn) {
+  const int n_full = g.T_out / bn;
+  if (n_full >= 1 && n_full < g.n_tiles && qasr_debug_get(18) != 0) {
+    g.n_div = n_full;
+    g.n_split = n_full * g.B;
+  } else {
+    g.n_div = g.n_tiles;
+    g.n_split = g.n_total;
   }
 }
 
@@ -958,6 +984,7 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
   g.m_tiles = (C_out + BM - 1) / BM;
   g.n_tiles = (T_out + BN - 1) / BN;
   g.n_total = g.n_tiles * B;
+  set_tile_walk(g, BN);
   // M tiles per CTA: two when both accumulator sets still double-buffer in TMEM (512 columns)
   g.MT = (g.nseg == 1 && g.m_tiles % 2 == 0) ? 2 : 1;
   // less than one wave of (M tile, time tile) pairs (BASELINE config 1: batch 8 x 250 frames): one M tile per CTA doubles
@@ -1022,6 +1049,7 @@ extern "C" int qasr_conv1d_gemm_i8(const qasr_gemm_operand* op0, const qasr_gemm
     g.m_groups = g.m_tiles / 2;
     g.n_tiles = (T_out + g.bn - 1) / g.bn;
     g.n_total = g.n_tiles * B;
+    set_tile_walk(g, g.bn);
     g.stage_bytes = kBBytes;
     // 128-frame tiles: each CTA streams 64 frames of every slab as a [64 frames][128 channels] box in the 64-byte
     // swizzle (8 KB per stage, nothing fetched twice).  Bring-up knob 14 = 0 keeps the full 128-frame boxes.
