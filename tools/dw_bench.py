@@ -47,6 +47,12 @@ if MODE == "plan":
     for (C, k, dil) in ((512, 33, 1), (512, 63, 1), (256, 33, 1), (256, 39, 1)):
         print("C=%d k=%d: rows %6.1f us   tapes %6.1f us   (DW_PLAN_LIKE=%s)" % (C, k, run(C, k, dil, {8: 0, 16: 0}), run(C, k, dil, {8: 0}), os.environ.get("DW_PLAN_LIKE")), flush=True)
     sys.exit(0)
+if MODE == "rows":
+    # rows per tape (knob 17) against the wave arithmetic: 8 resident CTAs of 4 warps per SM = 1184 CTAs per wave
+    for (C, k, dil) in ((512, 33, 1), (512, 63, 1), (512, 75, 1), (256, 33, 1), (256, 39, 1)):
+        print("C=%d k=%d: " % (C, k) + "  ".join("R=%d %5.1f" % (r, run(C, k, dil, {8: 0, 17: r})) for r in (1, 2, 3, 4, 5, 6, 7, 8)) +
+              "  auto %5.1f" % run(C, k, dil, {8: 0, 17: -1}), flush=True)
+    sys.exit(0)
 if MODE == "rt":
     # row-tape walk of the IMMA engine (dwconv_rt.cu) against the row-at-a-time kernel (knob 16 = 0); knob 17 = rows per tape
     for (C, k, dil) in ((512, 33, 1), (512, 51, 1), (512, 63, 1), (512, 75, 1), (256, 33, 1), (256, 39, 1)):
