@@ -326,6 +326,40 @@ def test_gemm_dual_residual(fast, gemm_engine):
     assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
 
 
+@pytest.mark.parametrize("order", [-1, 0], ids=["full_tiles_first", "utterance_major"])
+@pytest.mark.parametrize("shape", [(200, 300, 128), (170, 128, 128), (330, 100, 128), (90, 420, 256)], ids=lambda s: "B%d_T%d_C%d" % s)
+def test_gemm_tile_walk_over_several_rounds(gemm_engine, order, shape):
+    """More (utterance, time tile) pairs than CTAs per M group, so every CTA walks several rounds: the full-tiles-first
+    order (set_tile_walk: partial last tiles after all full ones; T a multiple of the tile, T below one tile and
+    T = 3 tiles + a rest) and the utterance-major order (bring-up knob 18 = 0) against the oracle, ragged lengths."""
+    B, T, co = shape     # 256 output channels: two M tiles, so the CTA-pair engine walks them too
+    ci = 64
+    r = rng(44)
+    q = r.integers(0, 64, (B, ci, T))
+    w = r.integers(-31, 32, (co, ci, 1))
+    bias = r.integers(-3000, 3000, co)
+    acc = O.conv1d_int(q, w, bias, 1, 0, 1, 1)
+    bound = int(np.abs(acc).max())
+    m, e = f32_dyadic(r, co, bound, 0, 63, 1e-4, 2e-3)
+    lens = r.integers(T // 2, T + 1, B).astype(np.int32)
+    want = expected_requant(acc, m, e, -64, 63, relu0=True, lens=lens)
+    x = to_codes_tensor(q, False)
+    wp = ops.pack_weights(torch.from_numpy(w.astype(np.int8)).to(DEV))
+    ch = ops.chan_table(r.uniform(1e-5, 1e-3, co).astype(np.float32), bias, m, e, DEV)
+    ep = ops.make_epilogue(L.EPI_REQUANT_I8, ch, flags=L.F_RELU0 | L.F_MASK | L.F_FAST_F32, qmin=-64, qmax=63,
+                           out_lens=torch.from_numpy(lens).to(DEV))
+    out = ops.alloc_codes(B, co, T, DEV)
+    L.lib().qasr_debug_set(18, order)
+    try:
+        ops.conv_gemm(ops.gemm_operand(x, T, wp, ci, 1), None, out, B, co, T, ep)
+        torch.cuda.synchronize()
+    finally:
+        L.lib().qasr_debug_set(18, -1)
+    got = from_codes_tensor(out, T, signed=False)
+    assert np.array_equal(got, want), "mismatches: %d / %d" % ((got != want).sum(), want.size)
+    assert int(out[:, :, T:].abs().sum()) == 0
+
+
 @pytest.mark.parametrize("range_check", [False, True], ids=["plain", "range_check"])
 def test_gemm_dual_stage2_16(gemm_engine, range_check):
     """QASR_F_STAGE2_16: the second requantisation of a two-operand res_act launch in 16-bit fixed point
