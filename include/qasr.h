@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define QASR_VERSION 100
+#define QASR_VERSION 101   /* 101: QASR_F_CLAMP16, QASR_F_STAGE2_16 */
 
 typedef enum {
   QASR_OK = 0,

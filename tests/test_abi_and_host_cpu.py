@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported(lib):
     for name in declared:
         assert hasattr(lib, name), "libqasr.so does not export %s" % name
         assert name in _lib._SIGS, "no ctypes signature for %s" % name
-    assert lib.qasr_version() == 100
+    assert lib.qasr_version() == 101
 
 
 def test_no_cpu_fallback():
