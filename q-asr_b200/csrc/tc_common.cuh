@@ -29,6 +29,10 @@ __device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
   __syncwarp();
   if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
+// -DQASR_SPIN_WAIT polls with test_wait instead of the suspending try_wait: measured -1 % on the bench step in one same-box
+// A/B (GEMM class 1090 -> 1070 us; the suspend-time hint itself, 100 ns against 2000 ns, made no difference), but a polling
+// MMA warp behind `griddepcontrol.wait` of a long predecessor would reach the trap limit within ~60 ms, and a hybrid
+// (8192 polls, then try_wait) did not reproduce the gain (2.279 ms on another box): the suspending form stays.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   for (uint32_t spin = 0; !done; ++spin) {
