@@ -318,7 +318,7 @@ def secondary_audio(device, flush, steps, warmup):
     pc["featurizer_max_rel_err"] = feat_err
     pc["featurizer_within_1e-5"] = bool(feat_err <= 1e-5 and int(flen[0]) == int(want_len[0]))
     pc["featurizer_note"] = ("float32 FFT kernel against the FLOAT64 oracle, relative to max|feature|; on 20 s of white noise the "
-                             "reference's own float32 torch.stft pipeline measures 0.9e-5 against the same oracle (DESIGN 5): "
+                             "reference's own float32 torch.stft pipeline measures 1.0e-5 against the same oracle on this utterance (DESIGN 5, tests/test_featurizer_cpu.py): "
                              "1e-5 is float32's noise floor here, tests/test_gpu_featurizer.py holds 1e-5 on its cases")
     audio_s = B * L / 16000.0
     feat_bytes = B * L * 4 + B * 64 * int(feat.shape[2]) * 4

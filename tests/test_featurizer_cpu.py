@@ -55,3 +55,18 @@ def test_known_properties():
     assert all(np.flatnonzero(fb[i]).size > 0 for i in range(64))
     w = F.hann_window(320)
     assert abs(w[0]) < 1e-7 and abs(w[-1]) < 1e-7 and abs(w[159] - w[160]) < 1e-6
+
+
+def test_float32_noise_floor_on_the_bench_audio():
+    """What `featurizer_max_rel_err` in the bench line is measured against: on 20 s of the bench's white noise (bench.py
+    bench_audio_chain, seed 3000, utterance 0) the reference's OWN float32 arithmetic (torch.stft pipeline above) already
+    sits ~1e-5, relative to max |feature|, from the float64 oracle -- north_star's 1e-5 is float32's noise floor for this
+    input ("Featurizer tolerance")."""
+    g = torch.Generator().manual_seed(3000)
+    audio = (0.1 * torch.randn(32, 320000, generator=g))[:1].numpy()
+    lengths = np.array([320000], np.int64)
+    ref32, ref_len = torch_reference(audio, lengths)
+    want, want_len = F.melspec(audio, lengths)
+    assert np.array_equal(ref_len, want_len)
+    err = np.abs(ref32 - want).max() / np.abs(want).max()
+    assert 2e-6 < err < 5e-5, err
